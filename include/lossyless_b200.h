@@ -1,0 +1,244 @@
+/*
+ * lossyless_b200.h -- C ABI of liblossyless_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the encode / rate-distortion hot path of YannDubs/lossyless
+ * (SURVEY.md section 8).  Plain pointers and sizes only; no torch types.  Every device
+ * pointer is caller-owned, every launch is ordered on the `stream` argument
+ * (a cudaStream_t passed as void*), nothing synchronises unless stated, and there is no
+ * global state besides a thread-local error string.  All functions return 0 on success
+ * and a negative code on failure (ll_last_error() describes it); nothing asserts.
+ *
+ * "replaces" cites the reference interface (file:line under /root/reference, or the
+ * compressai==1.1.5 / clip==1.0 symbol the reference calls there) that each entry point
+ * stands in for.  INTEGRATION.md shows the reference-side binding.
+ */
+#ifndef LOSSYLESS_B200_H
+#define LOSSYLESS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *ll_stream_t; /* cudaStream_t */
+
+/* element types of activations handed across the boundary */
+enum { LL_F32 = 0, LL_F16 = 1, LL_BF16 = 2 };
+
+/* error codes */
+enum {
+    LL_OK = 0,
+    LL_ERR_INVALID = -1,  /* bad argument (null pointer, size, dtype, alignment) */
+    LL_ERR_CUDA = -2,     /* CUDA runtime / driver error, see ll_last_error() */
+    LL_ERR_CDF = -3,      /* pmf / CDF table does not satisfy the coder's invariants */
+    LL_ERR_CORRUPT = -4,  /* container / bitstream is truncated or malformed */
+    LL_ERR_ARCH = -5      /* device is not sm_100 */
+};
+
+int ll_version(void);
+const char *ll_last_error(void);
+/* 0 if device `dev` can run this library (compute capability 10.x), LL_ERR_ARCH otherwise */
+int ll_check_device(int dev);
+
+/* ------------------------------------------------------------------ host, load time */
+
+/* replaces compressai._CXX.pmf_to_quantized_cdf(pmf, precision) (ops.cpp), reached from
+ * EntropyBottleneck.update() at hub/compressor.py:63 and lossyless/rates.py:299,314.
+ * pmf[n] -> cdf[n+1]. */
+int ll_pmf_to_quantized_cdf(const float *pmf, int n, int precision, int32_t *cdf);
+
+/* replaces compressai EntropyModel._pmf_to_cdf: per channel c,
+ * cdf[c, :len+2] = pmf_to_quantized_cdf(cat(pmf[c, :pmf_length[c]], tail[c]), 16).
+ * pmf [C, Lmax] row-major, tail [C], pmf_length [C]; cdf [C, Lmax+2] is zero-filled. */
+int ll_build_cdf_tables(const float *pmf, const float *tail, const int32_t *pmf_length, int C,
+                        int Lmax, int32_t *cdf);
+
+/* replaces the record loop of ClipCompressor.decompress_dataset (hub/compressor.py:233-238,
+ * read_uints/read_bytes :268-275): walks `n` records (">I len" + bytes) starting at
+ * buf[pos] and writes offsets[n+1] = byte offset of each record's payload (offsets[n] =
+ * end).  Fails with LL_ERR_CORRUPT on truncation. */
+int ll_container_index(const uint8_t *buf, int64_t size, int64_t pos, int64_t n, int64_t *offsets,
+                       int32_t *lens);
+
+/* ------------------------------------------------------------------ device: rANS codec */
+
+/* bytes of per-row scratch ll_eb_rans_encode needs for C symbols (worst case, escapes
+ * included); always a multiple of 4. */
+int ll_rans_stream_cap_bytes(int C);
+
+/* Device-side encoder table (16 B per CDF entry: exact 64-bit reciprocal, start, freq),
+ * derived from the int32 CDF table.  enc_table must hold C*cdf_stride*16 bytes.
+ * replaces the per-image `self._quantized_cdf.tolist()` hand-off in compressai
+ * EntropyModel.compress (hub/compressor.py:98). */
+int ll_rans_build_enc_table(const int32_t *cdf, const int32_t *cdf_len, int C, int cdf_stride,
+                            void *enc_table, ll_stream_t stream);
+
+/* Fused process_z_in + quantise + rANS encode, one stream per row.
+ * replaces hub/compressor.py:95,98,105-109 (process_z_in; EntropyBottleneck.compress) =
+ * compressai EntropyModel.quantize("symbols", medians) + ans.RansEncoder().
+ * encode_with_indexes(symbols, arange(C), cdf, cdf_len, offset), lossyless/rates.py:556-559.
+ *   z        [rows, C] of z_dtype (device)       bias, exp_scale, medians  float32 [C]
+ *            sym = rint((float(z) + bias) * exp_scale - medians); pass bias/exp_scale NULL
+ *            to feed z_in directly (sym = rint(z - medians))
+ *   scratch  [rows, cap] bytes, cap = ll_rans_stream_cap_bytes(C); row r's stream is the
+ *            LAST lens[r] bytes of its slot
+ *   lens     int32 [rows]        symbols_out  optional int32 [rows, C] (NULL to skip) */
+int ll_eb_rans_encode(const void *z, int z_dtype, int64_t rows, int C, const float *bias,
+                      const float *exp_scale, const float *medians, const void *enc_table,
+                      int cdf_stride, const int32_t *cdf_len, const int32_t *offset,
+                      uint8_t *scratch, int32_t *lens, int32_t *symbols_out, ll_stream_t stream);
+
+/* Compacts the per-row streams into one buffer.  mode 0: raw concatenation (what
+ * ClipCompressor.compress returns, one bytes object per row, hub/compressor.py:117-119);
+ * mode 1: container records ">I len" + bytes exactly as compress_dataset writes them
+ * (hub/compressor.py:192-196, write_uints/write_bytes :258-265).
+ *   offsets  int64 [rows+1] (device): start of each row's record in `out`
+ *   out      must hold sum(lens) (+ 4*rows in mode 1) bytes; rows*(cap+4) always suffices */
+int ll_rans_pack(const uint8_t *scratch, const int32_t *lens, int64_t rows, int cap, int mode,
+                 uint8_t *out, int64_t *offsets, ll_stream_t stream);
+
+/* Batched rANS decode + dequantise + process_z_out.
+ * replaces hub/compressor.py:121-125 (decompress) = compressai ans.RansDecoder().
+ * decode_with_indexes + EntropyModel.dequantize(medians) + process_z_out (:111-115),
+ * lossyless/rates.py:561-564.
+ *   data     concatenated streams (device); offsets int64 [rows+1]: stream r is
+ *            data[offsets[r] : offsets[r] + lens[r]]   (lens int32 [rows])
+ *   z_hat    float32 [rows, C] = (sym + medians) / exp_scale - bias  (bias/exp_scale NULL:
+ *            z_hat = sym + medians)            symbols_out optional int32 [rows, C]
+ *   status   int32 [rows]: 0 ok, 1 = stream shorter than the symbols require (corrupt) */
+int ll_rans_decode(const uint8_t *data, const int64_t *offsets, const int32_t *lens, int64_t rows,
+                   int C, const int32_t *cdf, int cdf_stride, const int32_t *cdf_len,
+                   const int32_t *offset, const float *medians, const float *bias,
+                   const float *exp_scale, float *z_hat, int32_t *symbols_out, int32_t *status,
+                   ll_stream_t stream);
+
+/* ------------------------------------------------------- device: EntropyBottleneck */
+
+/* Derived per-channel parameters (softplus(matrix), tanh(factor)) packed for the likelihood
+ * kernels: float32 [LL_EB_NPARAM, C].  Only filters = (3,3,3,3) (the reference's setting,
+ * hub/compressor.py:49-51, config/rate/H_factorized.yaml) is supported. */
+#define LL_EB_NPARAM 58
+int ll_eb_pack_params(const float *const *matrices /*5*/, const float *const *biases /*5*/,
+                      const float *const *factors /*4*/, int C, float *packed, ll_stream_t stream);
+
+/* Fused rate forward: process_z_in -> (+noise | round about median) -> two
+ * logits_cumulative passes -> |sigmoid diff| -> LowerBound(1e-9) -> process_z_out, plus
+ * per-row rates[r] = -sum_c log(q).
+ * replaces HRateFactorizedPrior.forward_help (lossyless/rates.py:534-554) = process_z_in +
+ * compressai EntropyBottleneck.forward (+ _likelihood, _logits_cumulative, LowerBound) +
+ * process_z_out, and hub/compressor.py:95,100-101.
+ *   z [rows,C] z_dtype; noise float32 [rows,C] or NULL (eval mode: dequantise)
+ *   z_hat float32 [rows,C]; q float32 [rows,C] (NULL to skip); rates float32 [rows]
+ *   (NULL to skip; must be zero-filled by the caller, it is accumulated atomically) */
+int ll_eb_forward(const void *z, int z_dtype, int64_t rows, int C, const float *noise,
+                  const float *bias, const float *exp_scale, const float *medians,
+                  const float *packed, float likelihood_bound, float *z_hat, float *q,
+                  float *rates, ll_stream_t stream);
+
+/* Backward of ll_eb_forward in training (noise) mode.  Given g_rates [rows] (dL/drates),
+ * g_zhat [rows,C] or NULL (dL/dz_hat), writes gz float32 [rows,C] (dL/dz), and accumulates
+ * gparam float32 [LL_EB_NPARAM, C] (gradient w.r.t. the *derived* parameters;
+ * softplus'/tanh' chain is applied by the caller), g_bias [C], g_exp_scale [C].
+ * replaces autograd through lossyless/rates.py:534-554. */
+int ll_eb_backward(const void *z, int z_dtype, int64_t rows, int C, const float *noise,
+                   const float *bias, const float *exp_scale, const float *packed,
+                   float likelihood_bound, const float *g_rates, const float *g_zhat, float *gz,
+                   float *gparam, float *g_bias, float *g_exp_scale, ll_stream_t stream);
+
+/* ------------------------------------------------------------ device: CLIP ViT-B/32 */
+
+typedef struct ll_vit ll_vit_t;
+
+typedef struct {
+    int width, layers, heads, patch, res, out_dim; /* ViT-B/32: 768,12,12,32,224,512 */
+    int dtype;                                     /* LL_F16 or LL_BF16: storage/MMA operand type */
+} ll_vit_config_t;
+
+/* Names follow clip.model.VisionTransformer's state dict.  All device pointers in
+ * cfg.dtype except the LayerNorm gains/biases and linear biases (float32).  Layer arrays
+ * have cfg.layers entries.  The library keeps the pointers; the caller keeps them alive. */
+typedef struct {
+    const void *conv1_w;   /* [width, 3*patch*patch]  (conv1.weight flattened) */
+    const void *class_emb; /* [width] */
+    const void *pos_emb;   /* [tokens, width] */
+    const float *ln_pre_w, *ln_pre_b, *ln_post_w, *ln_post_b;
+    const void *proj_t;    /* [out_dim, width] = proj.T, row-major */
+    const void *const *in_proj_w;  /* [3*width, width] */
+    const float *const *in_proj_b; /* [3*width] */
+    const void *const *out_proj_w; /* [width, width] */
+    const float *const *out_proj_b;
+    const float *const *ln1_w, *const *ln1_b, *const *ln2_w, *const *ln2_b;
+    const void *const *fc_w;   /* [4*width, width] */
+    const float *const *fc_b;
+    const void *const *cproj_w; /* [width, 4*width] */
+    const float *const *cproj_b;
+} ll_vit_weights_t;
+
+/* replaces clip.load("ViT-B/32").visual (hub/compressor.py:39-40;
+ * lossyless/architectures.py:367-376). */
+int ll_vit_create(const ll_vit_config_t *cfg, const ll_vit_weights_t *w, ll_vit_t **out);
+void ll_vit_destroy(ll_vit_t *v);
+/* bytes of device workspace ll_vit_forward needs for up to `batch` images */
+int64_t ll_vit_workspace_bytes(const ll_vit_t *v, int64_t batch);
+/* replaces VisionTransformer.forward: `z = self.clip(X)` (hub/compressor.py:93).
+ *   x [batch,3,res,res] x_dtype (LL_F16/LL_BF16/LL_F32, NCHW, device)
+ *   z [batch,out_dim] in cfg.dtype (the reference's fp16 `z` before .float()) */
+int ll_vit_forward(ll_vit_t *v, const void *x, int x_dtype, int64_t batch, void *z,
+                   void *workspace, int64_t workspace_bytes, ll_stream_t stream);
+/* number of kernel launches one ll_vit_forward of `batch` images issues */
+int64_t ll_vit_launches(const ll_vit_t *v, int64_t batch);
+/* images per internal pass (default 256): a pass's activations are sized to stay in L2 */
+int ll_vit_set_chunk(ll_vit_t *v, int64_t chunk);
+
+/* Stand-alone entry points of the encoder's non-GEMM kernels (numerics tests).
+ * ll_layernorm: h[r,:] = LN(x[r,:]) * gamma + beta, fp32 statistics, eps 1e-5 (clip LayerNorm).
+ * ll_attention: qkv [batch*S, 3*H*64] (q|k|v, head-major) -> out [batch*S, H*64];
+ *               softmax(q k^T / 8) v per head, S <= 64 (nn.MultiheadAttention core). */
+int ll_layernorm(const void *x, int64_t rows, int width, const float *gamma, const float *beta,
+                 void *h, int dtype, ll_stream_t stream);
+int ll_attention(const void *qkv, void *out, int64_t batch, int S, int H, int dtype,
+                 ll_stream_t stream);
+
+/* Stand-alone GEMM entry (tests, micro-benchmarks):  D[M,N] = act(A[M,K] @ W[N,K]^T + bias)
+ * (+ residual), A/W/D/residual in `dtype`, bias float32 or NULL, act 0 = none,
+ * 1 = QuickGELU x*sigmoid(1.702x).  K % 64 == 0, N % 128 == 0. */
+int ll_gemm(const void *A, const void *W, const float *bias, const void *residual, void *D,
+            int64_t M, int N, int K, int dtype, int act, ll_stream_t stream);
+
+/* ----------------------------------------------------------- device: distortions */
+
+/* Row-wise L2 normalisation (F.normalize, eps 1e-12) + zs_norm @ zs_norm^T tile, fp32.
+ * replaces lossyless/distortions.py:319-324.
+ *   zs float32 [n, d] (n = 2B) -> zs_norm [n,d], inv_norm [n], logits [n, ld] (tile written
+ *   at column 0; ld >= n lets the caller gather remote tiles to its right) */
+int ll_contrastive_logits(const float *zs, int n, int d, float *zs_norm, float *inv_norm,
+                          float *logits, int ld, ll_stream_t stream);
+/* backward of the above: g_logits [n, ld_g] (local tile) -> g_zs [n, d]; d <= 256. */
+int ll_contrastive_logits_backward(const float *g_logits, int ld_g, const float *zs_norm,
+                                   const float *inv_norm, int n, int d, float *g_zs,
+                                   ll_stream_t stream);
+
+/* InfoNCE over the gathered logits without materialising the masked copy.
+ * replaces ContrastiveDistortion.compute_loss (lossyless/distortions.py:340-405).
+ *   logits [n, n_cols] (own tile first), pos_add = -log(to_mult) or 0, inv_temp = 1/temperature
+ *   loss [n] = cross_entropy(masked(logits)/T, pos_idx);  lse [n] saved for backward */
+int ll_contrastive_ce_forward(const float *logits, int n, int n_cols, int ld, float pos_add,
+                              float inv_temp, float *loss, float *lse, ll_stream_t stream);
+/* grad wrt the LOCAL tile only (lossyless/helpers.py:885-890) and wrt inv_temp. */
+int ll_contrastive_ce_backward(const float *logits, int n, int n_cols, int ld, float pos_add,
+                               float inv_temp, const float *lse, const float *g_loss,
+                               float *g_logits_local, int ld_g, float *g_inv_temp,
+                               ll_stream_t stream);
+
+/* replaces LossyZDistortion.forward (lossyless/distortions.py:445):
+ * dist[r] = sum_c |z_hat - z + 1e-6|;  optional backward sign tensor. */
+int ll_lossy_z_forward(const float *z_hat, const float *z, int64_t rows, int C, float eps,
+                       float *dist, ll_stream_t stream);
+int ll_lossy_z_backward(const float *z_hat, const float *z, int64_t rows, int C, float eps,
+                        const float *g_dist, float *g_zhat, ll_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOSSYLESS_B200_H */

@@ -1,0 +1,322 @@
+// Factorised-prior EntropyBottleneck rate: fused forward and backward (sm_100a).
+//
+// One launch replaces the ~60 tiny ATen / bmm launches of compressai==1.1.5
+// EntropyBottleneck.forward (+ _likelihood, _logits_cumulative, LowerBound) wrapped by
+// process_z_in / process_z_out and the -log q row sum of HRateFactorizedPrior.forward_help
+// (lossyless/rates.py:534-554; hub/compressor.py:95,100-101).
+//
+// Layout: activations [rows, C] row-major; thread t owns channel c (adjacent threads ->
+// adjacent channels -> coalesced 128 B warp accesses), keeps that channel's 58 derived
+// parameters in registers and walks a slab of rows.  Per element: 2 x (66 FMA + 12 tanh) +
+// 2 sigmoid + log; the kernel is SFU/FMA-bound, not HBM-bound.
+#include "ll_common.cuh"
+
+namespace ll {
+
+// packed parameter rows (float32 [58, C]); M* = softplus(matrix), F* = tanh(factor)
+enum : int {
+    kM0 = 0, kB0 = 3, kF0 = 6,
+    kM1 = 9, kB1 = 18, kF1 = 21,
+    kM2 = 24, kB2 = 33, kF2 = 36,
+    kM3 = 39, kB3 = 48, kF3 = 51,
+    kM4 = 54, kB4 = 57,
+    kNP = LL_EB_NPARAM
+};
+__device__ constexpr int kMOff[4] = {kM0, kM1, kM2, kM3};
+__device__ constexpr int kBOff[4] = {kB0, kB1, kB2, kB3};
+__device__ constexpr int kFOff[4] = {kF0, kF1, kF2, kF3};
+
+// logits_cumulative for one scalar; keeps gated activations g[k][j] and tanh values t[k][j]
+struct Trace {
+    float g[4][3];
+    float t[4][3];
+};
+
+__device__ __forceinline__ float logits_fwd(const float (&P)[kNP], float v, Trace &tr)
+{
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float a = fmaf(P[kM0 + j], v, P[kB0 + j]);
+        const float t = tanhf(a);
+        tr.t[0][j] = t;
+        tr.g[0][j] = fmaf(P[kF0 + j], t, a);
+    }
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float a = P[kBOff[k] + j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) a = fmaf(P[kMOff[k] + 3 * j + i], tr.g[k - 1][i], a);
+            const float t = tanhf(a);
+            tr.t[k][j] = t;
+            tr.g[k][j] = fmaf(P[kFOff[k] + j], t, a);
+        }
+    }
+    float out = P[kB4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out = fmaf(P[kM4 + i], tr.g[3][i], out);
+    return out;
+}
+
+// accumulates d(out)/d(params) * gl into G and returns d(out)/dv * gl
+__device__ __forceinline__ float logits_bwd(const float (&P)[kNP], float v, const Trace &tr, float gl, float (&G)[kNP])
+{
+    float gg[3];
+    G[kB4] += gl;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        G[kM4 + i] = fmaf(gl, tr.g[3][i], G[kM4 + i]);
+        gg[i] = gl * P[kM4 + i];
+    }
+#pragma unroll
+    for (int k = 3; k >= 1; --k) {
+        float ga[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float t = tr.t[k][j];
+            G[kFOff[k] + j] = fmaf(gg[j], t, G[kFOff[k] + j]);
+            ga[j] = gg[j] * fmaf(P[kFOff[k] + j], 1.f - t * t, 1.f);
+            G[kBOff[k] + j] += ga[j];
+        }
+        float gprev[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                G[kMOff[k] + 3 * j + i] = fmaf(ga[j], tr.g[k - 1][i], G[kMOff[k] + 3 * j + i]);
+                gprev[i] = fmaf(ga[j], P[kMOff[k] + 3 * j + i], gprev[i]);
+            }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) gg[i] = gprev[i];
+    }
+    float gv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float t = tr.t[0][j];
+        G[kF0 + j] = fmaf(gg[j], t, G[kF0 + j]);
+        const float ga = gg[j] * fmaf(P[kF0 + j], 1.f - t * t, 1.f);
+        G[kB0 + j] += ga;
+        G[kM0 + j] = fmaf(ga, v, G[kM0 + j]);
+        gv = fmaf(ga, P[kM0 + j], gv);
+    }
+    return gv;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void eb_pack_params_kernel(const float *m0, const float *m1, const float *m2, const float *m3, const float *m4,
+                                      const float *b0, const float *b1, const float *b2, const float *b3, const float *b4,
+                                      const float *f0, const float *f1, const float *f2, const float *f3, int C,
+                                      float *__restrict__ packed)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    auto softplus = [](float x) { return x > 20.f ? x : log1pf(expf(x)); };  // torch.nn.functional.softplus
+    const float *M[4] = {m0, m1, m2, m3};
+    const float *B[4] = {b0, b1, b2, b3};
+    const float *F[4] = {f0, f1, f2, f3};
+    for (int j = 0; j < 3; ++j) packed[(kM0 + j) * C + c] = softplus(m0[c * 3 + j]);
+    for (int k = 1; k < 4; ++k)
+        for (int e = 0; e < 9; ++e) packed[(kMOff[k] + e) * C + c] = softplus(M[k][c * 9 + e]);
+    for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 3; ++j) {
+            packed[(kBOff[k] + j) * C + c] = B[k][c * 3 + j];
+            packed[(kFOff[k] + j) * C + c] = tanhf(F[k][c * 3 + j]);
+        }
+    for (int i = 0; i < 3; ++i) packed[(kM4 + i) * C + c] = softplus(m4[c * 3 + i]);
+    packed[kB4 * C + c] = b4[c];
+}
+
+constexpr int kEbThreads = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(kEbThreads)
+eb_forward_kernel(const T *__restrict__ z, int64_t rows, int C, int rows_per_cta, const float *__restrict__ noise,
+                  const float *__restrict__ bias, const float *__restrict__ exp_scale,
+                  const float *__restrict__ medians, const float *__restrict__ packed, float bound,
+                  float *__restrict__ z_hat, float *__restrict__ q_out, float *__restrict__ rates)
+{
+    const int c = blockIdx.x * kEbThreads + threadIdx.x;
+    const bool live = c < C;
+    const int cc = live ? c : C - 1;
+    float P[kNP];
+#pragma unroll
+    for (int i = 0; i < kNP; ++i) P[i] = packed[i * C + cc];
+    const float b = bias ? bias[cc] : 0.f, es = exp_scale ? exp_scale[cc] : 1.f, med = medians[cc];
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r1 = min(rows, r0 + rows_per_cta);
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t idx = r * C + cc;
+        float x = to_float<T>(z[idx]);
+        if (bias) x = __fmul_rn(__fadd_rn(x, b), es);  // process_z_in
+        float v;
+        if (noise)
+            v = x + noise[idx];
+        else
+            v = __fadd_rn(rintf(__fsub_rn(x, med)), med);  // quantize "dequantize"
+        Trace tr;
+        const float lower = logits_fwd(P, v - 0.5f, tr);
+        const float upper = logits_fwd(P, v + 0.5f, tr);
+        const float sum = lower + upper;
+        const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
+        const float lik = fabsf(sigmoidf_(sgn * upper) - sigmoidf_(sgn * lower));
+        const float q = fmaxf(lik, bound);  // LowerBound
+        float nl = live ? -logf(q) : 0.f;
+        if (live) {
+            z_hat[idx] = bias ? __fsub_rn(__fdiv_rn(v, es), b) : v;  // process_z_out
+            if (q_out) q_out[idx] = q;
+        }
+        if (rates) {
+            nl = warp_sum(nl);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&rates[r], nl);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kEbThreads)
+eb_backward_kernel(const T *__restrict__ z, int64_t rows, int C, int rows_per_cta, const float *__restrict__ noise,
+                   const float *__restrict__ bias, const float *__restrict__ exp_scale,
+                   const float *__restrict__ packed, float bound, const float *__restrict__ g_rates,
+                   const float *__restrict__ g_zhat, float *__restrict__ gz, float *__restrict__ gparam,
+                   float *__restrict__ g_bias, float *__restrict__ g_es)
+{
+    const int c = blockIdx.x * kEbThreads + threadIdx.x;
+    if (c >= C) return;
+    float P[kNP], G[kNP];
+#pragma unroll
+    for (int i = 0; i < kNP; ++i) {
+        P[i] = packed[i * C + c];
+        G[i] = 0.f;
+    }
+    const float b = bias ? bias[c] : 0.f, es = exp_scale ? exp_scale[c] : 1.f;
+    float acc_b = 0.f, acc_es = 0.f;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r1 = min(rows, r0 + rows_per_cta);
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t idx = r * C + c;
+        const float zf = to_float<T>(z[idx]);
+        const float zb = zf + b;
+        const float x = bias ? zb * es : zf;
+        const float v = x + noise[idx];
+        Trace trl, tru;
+        const float lower = logits_fwd(P, v - 0.5f, trl);
+        const float upper = logits_fwd(P, v + 0.5f, tru);
+        const float sum = lower + upper;
+        const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
+        const float su = sigmoidf_(sgn * upper), sl = sigmoidf_(sgn * lower);
+        const float diff = su - sl;
+        const float lik = fabsf(diff);
+        const float q = fmaxf(lik, bound);
+        // rate = -log q ;  LowerBound passes the gradient where lik >= bound or grad < 0
+        float g_lik = -g_rates[r] / q;
+        if (!(lik >= bound || g_lik < 0.f)) g_lik = 0.f;
+        const float sd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+        const float gu = g_lik * sd * sgn * su * (1.f - su);
+        const float gl = -g_lik * sd * sgn * sl * (1.f - sl);
+        float gv = logits_bwd(P, v + 0.5f, tru, gu, G) + logits_bwd(P, v - 0.5f, trl, gl, G);
+        if (g_zhat) {
+            const float gh = g_zhat[idx];
+            if (bias) {
+                gv += gh / es;                // z_hat = v / es - b
+                acc_es -= gh * v / (es * es);
+                acc_b -= gh;
+            } else {
+                gv += gh;
+            }
+        }
+        if (bias) {
+            gz[idx] = gv * es;  // x = (z + b) * es
+            acc_b += gv * es;
+            acc_es += gv * zb;
+        } else {
+            gz[idx] = gv;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kNP; ++i) atomicAdd(&gparam[i * C + c], G[i]);
+    if (bias) {
+        atomicAdd(&g_bias[c], acc_b);
+        atomicAdd(&g_es[c], acc_es);
+    }
+}
+
+static int eb_grid(int64_t rows, int C, dim3 &grid, int &rows_per_cta)
+{
+    const int cx = (C + kEbThreads - 1) / kEbThreads;
+    // enough row slabs for ~4 CTAs per SM, at least 8 rows per slab to amortise the parameter load
+    int64_t slabs = (4LL * num_sms() + cx - 1) / cx;
+    int64_t rpc = (rows + slabs - 1) / slabs;
+    if (rpc < 8) rpc = 8;
+    slabs = (rows + rpc - 1) / rpc;
+    if (slabs > 65535) {
+        slabs = 65535;
+        rpc = (rows + slabs - 1) / slabs;
+        slabs = (rows + rpc - 1) / rpc;
+    }
+    rows_per_cta = (int)rpc;
+    grid = dim3((unsigned)cx, (unsigned)slabs, 1);
+    return LL_OK;
+}
+
+}  // namespace ll
+
+using namespace ll;
+
+extern "C" int ll_eb_pack_params(const float *const *m, const float *const *b, const float *const *f, int C,
+                                 float *packed, ll_stream_t stream)
+{
+    LL_REQUIRE(m && b && f && packed && C > 0, "eb_pack_params: bad arguments");
+    for (int i = 0; i < 5; ++i) LL_REQUIRE(m[i] && b[i], "eb_pack_params: null matrix/bias %d", i);
+    for (int i = 0; i < 4; ++i) LL_REQUIRE(f[i], "eb_pack_params: null factor %d", i);
+    eb_pack_params_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(m[0], m[1], m[2], m[3], m[4], b[0], b[1], b[2], b[3], b[4], f[0], f[1], f[2], f[3], C, packed);
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+extern "C" int ll_eb_forward(const void *z, int z_dtype, int64_t rows, int C, const float *noise, const float *bias,
+                             const float *exp_scale, const float *medians, const float *packed, float bound,
+                             float *z_hat, float *q, float *rates, ll_stream_t stream)
+{
+    LL_REQUIRE(z && medians && packed && z_hat, "eb_forward: null pointer");
+    LL_REQUIRE((bias == nullptr) == (exp_scale == nullptr), "eb_forward: bias and exp_scale go together");
+    LL_REQUIRE(rows >= 0 && C > 0, "eb_forward: bad sizes");
+    if (rows == 0) return LL_OK;
+    dim3 grid;
+    int rpc;
+    eb_grid(rows, C, grid, rpc);
+    cudaStream_t s = as_stream(stream);
+    switch (z_dtype) {
+        case LL_F32: eb_forward_kernel<float><<<grid, kEbThreads, 0, s>>>((const float *)z, rows, C, rpc, noise, bias, exp_scale, medians, packed, bound, z_hat, q, rates); break;
+        case LL_F16: eb_forward_kernel<__half><<<grid, kEbThreads, 0, s>>>((const __half *)z, rows, C, rpc, noise, bias, exp_scale, medians, packed, bound, z_hat, q, rates); break;
+        case LL_BF16: eb_forward_kernel<__nv_bfloat16><<<grid, kEbThreads, 0, s>>>((const __nv_bfloat16 *)z, rows, C, rpc, noise, bias, exp_scale, medians, packed, bound, z_hat, q, rates); break;
+        default: return fail(LL_ERR_INVALID, "eb_forward: unknown dtype %d", z_dtype);
+    }
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+extern "C" int ll_eb_backward(const void *z, int z_dtype, int64_t rows, int C, const float *noise, const float *bias,
+                              const float *exp_scale, const float *packed, float bound, const float *g_rates,
+                              const float *g_zhat, float *gz, float *gparam, float *g_bias, float *g_exp_scale,
+                              ll_stream_t stream)
+{
+    LL_REQUIRE(z && noise && packed && g_rates && gz && gparam, "eb_backward: null pointer (noise is required: training mode only)");
+    LL_REQUIRE((bias == nullptr) == (exp_scale == nullptr), "eb_backward: bias and exp_scale go together");
+    LL_REQUIRE(!bias || (g_bias && g_exp_scale), "eb_backward: g_bias / g_exp_scale required with bias");
+    LL_REQUIRE(rows >= 0 && C > 0, "eb_backward: bad sizes");
+    if (rows == 0) return LL_OK;
+    dim3 grid;
+    int rpc;
+    eb_grid(rows, C, grid, rpc);
+    cudaStream_t s = as_stream(stream);
+    switch (z_dtype) {
+        case LL_F32: eb_backward_kernel<float><<<grid, kEbThreads, 0, s>>>((const float *)z, rows, C, rpc, noise, bias, exp_scale, packed, bound, g_rates, g_zhat, gz, gparam, g_bias, g_exp_scale); break;
+        case LL_F16: eb_backward_kernel<__half><<<grid, kEbThreads, 0, s>>>((const __half *)z, rows, C, rpc, noise, bias, exp_scale, packed, bound, g_rates, g_zhat, gz, gparam, g_bias, g_exp_scale); break;
+        case LL_BF16: eb_backward_kernel<__nv_bfloat16><<<grid, kEbThreads, 0, s>>>((const __nv_bfloat16 *)z, rows, C, rpc, noise, bias, exp_scale, packed, bound, g_rates, g_zhat, gz, gparam, g_bias, g_exp_scale); break;
+        default: return fail(LL_ERR_INVALID, "eb_backward: unknown dtype %d", z_dtype);
+    }
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}

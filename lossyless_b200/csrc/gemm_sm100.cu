@@ -1,0 +1,342 @@
+// Persistent, warp-specialised tcgen05 GEMM for the CLIP ViT linear layers (sm_100a).
+//
+//   D[M,N] = act(A[M,K] @ W[N,K]^T + bias[N]) (+ residual[M,N])
+//
+// Every dense contraction of the reference's encoder -- patch-embed conv (as im2col GEMM),
+// attention in/out projections, MLP c_fc / c_proj and the final `@ proj`
+// (clip/model.py VisionTransformer / ResidualAttentionBlock, reached from
+// hub/compressor.py:93 and lossyless/architectures.py:351-354) -- has this shape with both
+// operands K-major, which is what nn.Linear stores.
+//
+// Roles (192 threads, 1 CTA per SM, grid = min(#tiles, #SMs), static round-robin tiles):
+//   warp 0      TMA producer: 128xBK A tile + BNxBK W tile per stage, 128B swizzle, mbarrier tx
+//   warp 1      allocates TMEM; one lane issues tcgen05.mma (M=128, N=BN, K=16) into one of two
+//               TMEM accumulator buffers, commits stage-empty / accumulator-full barriers
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns), bias / QuickGELU / residual in
+//               fp32, 16-bit stores; overlaps the next tile's main loop (double-buffered TMEM)
+#include <cstring>
+
+#include "gemm_sm100.cuh"
+
+namespace ll {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 64 x 16-bit = one 128 B swizzle row
+constexpr int kGemmThreads = 192;
+constexpr int kABytes = kBM * kBK * 2;
+
+template <int BN>
+struct GemmShape {
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
+    static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment
+};
+
+template <typename T>
+struct Pack8;  // 8 x 16-bit <-> 8 floats
+template <>
+struct Pack8<__half> {
+    static __device__ __forceinline__ void unpack(const uint4 &v, float (&f)[8])
+    {
+        const __half2 *h = reinterpret_cast<const __half2 *>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 t = __half22float2(h[i]);
+            f[2 * i] = t.x;
+            f[2 * i + 1] = t.y;
+        }
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[8])
+    {
+        uint4 v;
+        __half2 *h = reinterpret_cast<__half2 *>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        return v;
+    }
+};
+template <>
+struct Pack8<__nv_bfloat16> {
+    static __device__ __forceinline__ void unpack(const uint4 &v, float (&f)[8])
+    {
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 t = __bfloat1622float2(h[i]);
+            f[2 * i] = t.x;
+            f[2 * i + 1] = t.y;
+        }
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[8])
+    {
+        uint4 v;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        return v;
+    }
+};
+
+__device__ __forceinline__ float quick_gelu(float x)
+{
+    // CLIP QuickGELU: x * sigmoid(1.702 x)
+    return x * __frcp_rn(1.f + __expf(-1.702f * x));
+}
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const float *__restrict__ bias, const T *residual, T *D, int M, int N, int K, int act)
+{
+    using S = GemmShape<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sm_a = smem;
+    uint8_t *sm_b = smem + S::kStages * kABytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::kStages * S::kStageBytes);
+    uint64_t *empty_bar = full_bar + S::kStages;
+    uint64_t *tfull_bar = empty_bar + S::kStages;  // [2] accumulator ready for the epilogue
+    uint64_t *tempty_bar = tfull_bar + 2;          // [2] accumulator drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_w);
+        for (int i = 0; i < S::kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) ptx::tmem_alloc<S::kTmemCols>(tmem_slot);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_n = N / BN;
+    const int num_m = (M + kBM - 1) / kBM;
+    const int num_tiles = num_m * num_n;
+    const int num_kb = K / kBK;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / num_n) * kBM;
+                const int n0 = (tile % num_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+                    ptx::tma_load_2d(sm_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, m0);
+                    ptx::tma_load_2d(sm_b + stage * S::kBBytes, &tmap_w, &full_bar[stage], kb * kBK, n0);
+                    if (++stage == S::kStages) stage = 0, phase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, BN, std::is_same<T, __nv_bfloat16>::value ? 1 : 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sm_a + stage * kABytes));
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sm_b + stage * S::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        // +32 B per K=16 step inside the 128 B swizzle row: start-address field += 2
+                        ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    ptx::mma_commit(&empty_bar[stage]);  // frees the smem stage when the MMAs retire
+                    if (++stage == S::kStages) stage = 0, phase ^= 1;
+                }
+                ptx::mma_commit(&tfull_bar[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32)
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (tile / num_n) * kBM;
+            const int n0 = (tile % num_n) * BN;
+            const int row = m0 + quarter * 32 + lane;
+            ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+            T *drow = D + (int64_t)row * N + n0;
+            const T *rrow = residual ? residual + (int64_t)row * N + n0 : nullptr;
+#pragma unroll 1
+            for (int cc = 0; cc < BN / 32; ++cc) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32(taddr + cc * 32, r);
+                ptx::tmem_ld_wait();
+                if (row < M) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[g * 8 + j]);
+                        const int col = cc * 32 + g * 8;
+                        if (bias != nullptr) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + n0 + col));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + n0 + col + 4));
+                            f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
+                            f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+                        }
+                        if (act == 1) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = quick_gelu(f[j]);
+                        }
+                        if (rrow != nullptr) {
+                            float rf[8];
+                            Pack8<T>::unpack(*reinterpret_cast<const uint4 *>(rrow + col), rf);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] += rf[j];
+                        }
+                        *reinterpret_cast<uint4 *>(drow + col) = Pack8<T>::pack(f);
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    // ---------------------------------------------------------------- teardown
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<S::kTmemCols>(tmem_base);
+    }
+}
+
+// --------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, int64_t rows, int64_t K, int box_rows)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    LL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+    LL_REQUIRE(K % kBK == 0 && rows > 0 && box_rows > 0 && box_rows <= 256, "make_tmap_2d: bad shape rows=%lld K=%lld box=%d", (long long)rows, (long long)K, box_rows);
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = dtype == LL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return LL_OK;
+}
+
+template <typename T, int BN>
+static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const float *bias, const void *residual, void *D,
+                       int64_t M, int N, int K, int act, cudaStream_t stream)
+{
+    using S = GemmShape<BN>;
+    static bool configured = false;
+    auto kern = gemm_tcgen05_kernel<T, BN>;
+    if (!configured) {
+        LL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmemBytes));
+        configured = true;
+    }
+    const int tiles = (int)((M + kBM - 1) / kBM) * (N / BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, kGemmThreads, S::kSmemBytes, stream>>>(ta, tw, bias, static_cast<const T *>(residual),
+                                                        static_cast<T *>(D), (int)M, N, K, act);
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+// Tile-N choice: 256 halves the A re-reads and the number of MMA instructions, 128 gives finer
+// tiles when there are too few to balance the persistent grid.
+static int pick_bn(int64_t M, int N)
+{
+    if (N % 256 != 0) return 128;
+    const int64_t tiles256 = ((M + kBM - 1) / kBM) * (N / 256);
+    return tiles256 >= 2 * (int64_t)num_sms() ? 256 : 128;
+}
+
+int gemm_launch_tmaps(const CUtensorMap &ta, const CUtensorMap &tw, int bn, const float *bias, const void *residual,
+                      void *D, int64_t M, int N, int K, int dtype, int act, cudaStream_t stream)
+{
+    if (dtype == LL_F16)
+        return bn == 256 ? launch_impl<__half, 256>(ta, tw, bias, residual, D, M, N, K, act, stream)
+                         : launch_impl<__half, 128>(ta, tw, bias, residual, D, M, N, K, act, stream);
+    return bn == 256 ? launch_impl<__nv_bfloat16, 256>(ta, tw, bias, residual, D, M, N, K, act, stream)
+                     : launch_impl<__nv_bfloat16, 128>(ta, tw, bias, residual, D, M, N, K, act, stream);
+}
+
+int gemm_pick_bn(int64_t M, int N) { return pick_bn(M, N); }
+
+int gemm_launch(const void *A, const void *W, const float *bias, const void *residual, void *D, int64_t M, int N,
+                int K, int dtype, int act, cudaStream_t stream)
+{
+    LL_REQUIRE(A && W && D, "gemm: null pointer");
+    LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "gemm: dtype must be LL_F16 or LL_BF16");
+    LL_REQUIRE(M > 0 && N > 0 && K > 0 && K % kBK == 0 && N % 128 == 0, "gemm: need K %% 64 == 0 and N %% 128 == 0 (M=%lld N=%d K=%d)", (long long)M, N, K);
+    LL_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0 && (!residual || (reinterpret_cast<uintptr_t>(residual) & 15) == 0) &&
+                   (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+               "gemm: D / residual / bias must be 16-byte aligned");
+    const int bn = pick_bn(M, N);
+    CUtensorMap ta, tw;
+    int rc = make_tmap_2d(&ta, A, dtype, M, K, kBM);
+    if (rc != LL_OK) return rc;
+    rc = make_tmap_2d(&tw, W, dtype, N, K, bn);
+    if (rc != LL_OK) return rc;
+    return gemm_launch_tmaps(ta, tw, bn, bias, residual, D, M, N, K, dtype, act, stream);
+}
+
+}  // namespace ll
+
+extern "C" int ll_gemm(const void *A, const void *W, const float *bias, const void *residual, void *D, int64_t M,
+                       int N, int K, int dtype, int act, ll_stream_t stream)
+{
+    return ll::gemm_launch(A, W, bias, residual, D, M, N, K, dtype, act, ll::as_stream(stream));
+}

@@ -1,0 +1,79 @@
+// Shared helpers for liblossyless_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/lossyless_b200.h"
+
+namespace ll {
+
+// thread-local error string behind ll_last_error()
+char *err_buf();
+int fail(int code, const char *fmt, ...);
+
+#define LL_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return ::ll::fail(LL_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,       \
+                              cudaGetErrorString(_e));                                        \
+    } while (0)
+
+#define LL_LAUNCH_CHECK() LL_CUDA_CHECK(cudaGetLastError())
+
+#define LL_REQUIRE(cond, ...)                                        \
+    do {                                                             \
+        if (!(cond)) return ::ll::fail(LL_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+static inline cudaStream_t as_stream(ll_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T>
+__device__ __forceinline__ float to_float(T v);
+template <>
+__device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_float<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+static inline int num_sms()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace ll

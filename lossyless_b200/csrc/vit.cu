@@ -1,0 +1,517 @@
+// CLIP ViT-B/32 image encoder for sm_100a: the non-GEMM kernels (patchify, token assembly +
+// ln_pre, LayerNorm, S=50 attention) and the native runner that strings them together with
+// the tcgen05 GEMM (gemm_sm100.cu).
+//
+// Computes clip.model.VisionTransformer.forward (clip==1.0) as the reference calls it at
+// hub/compressor.py:93 (`z = self.clip(X)`, fp16 weights/activations, fp32 LayerNorm and
+// accumulation) and lossyless/architectures.py:351-354.
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "gemm_sm100.cuh"
+
+namespace ll {
+
+int gemm_launch_tmaps(const CUtensorMap &ta, const CUtensorMap &tw, int bn, const float *bias, const void *residual,
+                      void *D, int64_t M, int N, int K, int dtype, int act, cudaStream_t stream);
+int gemm_pick_bn(int64_t M, int N);
+
+// ------------------------------------------------------------------------- patchify
+// x [B,3,R,R] (NCHW) -> A [B*G*G, 3*P*P], column index = c*P*P + ky*P + kx, the layout of
+// conv1.weight.reshape(width, -1): the stride-P conv becomes one GEMM.  8 elements per thread.
+template <typename TIn, typename T>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const TIn *__restrict__ x, T *__restrict__ A, int64_t B, int R, int P)
+{
+    const int G = R / P;
+    const int Kp = 3 * P * P;
+    const int64_t total = B * G * G * (int64_t)(Kp / 8);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int kc = (int)(i % (Kp / 8)) * 8;
+    const int64_t prow = i / (Kp / 8);
+    const int gx = (int)(prow % G), gy = (int)((prow / G) % G);
+    const int64_t b = prow / (G * G);
+    const int c = kc / (P * P), ky = (kc / P) % P, kx = kc % P;
+    const TIn *src = x + ((b * 3 + c) * R + (gy * P + ky)) * (int64_t)R + gx * P + kx;
+    T out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = from_float<T>(to_float<TIn>(src[j]));
+    *reinterpret_cast<uint4 *>(A + prow * Kp + kc) = *reinterpret_cast<const uint4 *>(out);
+}
+
+// ------------------------------------------------------------------------- LayerNorm family
+// One warp per row of `width` (multiple of 256, <= 1024) 16-bit elements; fp32 statistics
+// (CLIP's LayerNorm subclass computes in fp32 and casts back), eps 1e-5.
+template <typename T, int kChunks>
+__device__ __forceinline__ void warp_layernorm_store(float (&v)[kChunks][8], const float *__restrict__ gamma,
+                                                     const float *__restrict__ beta, T *__restrict__ dst, int lane,
+                                                     int width)
+{
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[c][j];
+    const float mean = warp_sum(s) / (float)width;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = v[c][j] - mean;
+            q += d * d;
+        }
+    const float rstd = rsqrtf(warp_sum(q) / (float)width + 1e-5f);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        const int col = c * 256 + lane * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gamma + col));
+        const float4 g1 = __ldg(reinterpret_cast<const float4 *>(gamma + col + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(beta + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(beta + col + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        T out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = from_float<T>((v[c][j] - mean) * rstd * g[j] + bb[j]);
+        *reinterpret_cast<uint4 *>(dst + col) = *reinterpret_cast<const uint4 *>(out);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void load8(const T *p, float (&f)[8])
+{
+    const uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    const T *h = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = to_float<T>(h[j]);
+}
+
+// h[r] = LN(x[r * row_stride]) ; row_stride lets ln_post read only the CLS rows.
+template <typename T, int kChunks>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const T *__restrict__ x, int64_t rows, int64_t row_stride, const float *__restrict__ gamma,
+                 const float *__restrict__ beta, T *__restrict__ h)
+{
+    constexpr int width = kChunks * 256;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    float v[kChunks][8];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) load8<T>(x + r * row_stride + c * 256 + lane * 8, v[c]);
+    warp_layernorm_store<T, kChunks>(v, gamma, beta, h + r * width, lane, width);
+}
+
+// Token assembly + ln_pre:  x[b, s] = LN( (s == 0 ? class_embedding : patch_out[b, s-1]) + pos[s] ).
+// The sum is rounded to the 16-bit storage type first, as the reference's fp16 add does.
+template <typename T, int kChunks>
+__global__ void __launch_bounds__(256)
+assemble_lnpre_kernel(const T *__restrict__ patch_out, const T *__restrict__ cls, const T *__restrict__ pos,
+                      const float *__restrict__ gamma, const float *__restrict__ beta, T *__restrict__ x, int64_t B,
+                      int S)
+{
+    constexpr int width = kChunks * 256;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= B * S) return;
+    const int64_t b = r / S;
+    const int s = (int)(r % S);
+    const T *src = s == 0 ? cls : patch_out + (b * (S - 1) + (s - 1)) * width;
+    float v[kChunks][8];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+        float a[8], p[8];
+        load8<T>(src + c * 256 + lane * 8, a);
+        load8<T>(pos + (int64_t)s * width + c * 256 + lane * 8, p);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[c][j] = to_float<T>(from_float<T>(a[j] + p[j]));
+    }
+    warp_layernorm_store<T, kChunks>(v, gamma, beta, x + r * width, lane, width);
+}
+
+// ------------------------------------------------------------------------- attention
+// nn.MultiheadAttention(768, 12) core for S <= 64 tokens, head dim 64: one CTA (4 warps) per
+// (image, head); Q/K/V staged in swizzled shared memory; S = QK^T and O = PV on mma.sync
+// m16n8k16 with the score tile kept in registers (softmax in fp32, exp2 with folded scale).
+// 1 % of the encoder's FLOPs; see DESIGN.md for why this is not a tcgen05 kernel (yet).
+template <typename T>
+struct MmaOp;
+template <>
+struct MmaOp<__half> {
+    static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+    {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+    static __device__ __forceinline__ uint32_t pack2(float lo, float hi)
+    {
+        __half2 h = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+};
+template <>
+struct MmaOp<__nv_bfloat16> {
+    static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+    {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+    static __device__ __forceinline__ uint32_t pack2(float lo, float hi)
+    {
+        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+constexpr int kAttRows = 64;  // padded tokens
+constexpr int kHeadDim = 64;
+
+// byte offset of 16-byte chunk `chunk` of row `row` in a [64][64] 16-bit tile, XOR-swizzled
+__device__ __forceinline__ uint32_t att_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+attention_kernel(const T *__restrict__ qkv, T *__restrict__ out, int S, int H, float scale_log2e)
+{
+    __shared__ __align__(128) uint8_t sm[3][kAttRows * 128];
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int W = H * kHeadDim;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const T *base = qkv + (int64_t)b * S * 3 * W + h * kHeadDim;
+
+    // stage Q, K, V (rows >= S zero-filled)
+    for (int i = tid; i < 3 * kAttRows * 8; i += 128) {
+        const int m = i / (kAttRows * 8), row = (i / 8) % kAttRows, chunk = i % 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < S) v = *reinterpret_cast<const uint4 *>(base + (int64_t)row * 3 * W + m * W + chunk * 8);
+        *reinterpret_cast<uint4 *>(&sm[m][att_off(row, chunk)]) = v;
+    }
+    __syncthreads();
+
+    const uint32_t sq = ptx::smem_u32(sm[0]), sk = ptx::smem_u32(sm[1]), sv = ptx::smem_u32(sm[2]);
+    const int r0 = warp * 16;
+    const int mi = lane >> 3, rr = lane & 7;
+
+    // Q fragments for the warp's 16 rows: 4 k-steps of 16
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) ldmatrix_x4(qa[kk], sq + att_off(r0 + rr + (mi & 1) * 8, 2 * kk + (mi >> 1)));
+
+    // scores: 8 key tiles of 8
+    float sc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            uint32_t kb[4];
+            ldmatrix_x4(kb, sk + att_off(8 * j + rr, 4 * p + mi));
+            MmaOp<T>::mma(sc[j], qa[2 * p], kb[0], kb[1]);
+            MmaOp<T>::mma(sc[j], qa[2 * p + 1], kb[2], kb[3]);
+        }
+    }
+
+    // masked softmax over keys < S; thread owns rows g = lane/4 (c0,c1) and g+8 (c2,c3)
+    const int tig = lane & 3;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int key = 8 * j + 2 * tig;
+        if (key >= S) sc[j][0] = sc[j][2] = -INFINITY;
+        if (key + 1 >= S) sc[j][1] = sc[j][3] = -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j][0] = exp2f((sc[j][0] - mx0) * scale_log2e);
+        sc[j][1] = exp2f((sc[j][1] - mx0) * scale_log2e);
+        sc[j][2] = exp2f((sc[j][2] - mx1) * scale_log2e);
+        sc[j][3] = exp2f((sc[j][3] - mx1) * scale_log2e);
+        sum0 += sc[j][0] + sc[j][1];
+        sum1 += sc[j][2] + sc[j][3];
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+
+    // O = P V : P comes straight from the score registers (accumulator layout == A layout)
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[4];
+        pa[0] = MmaOp<T>::pack2(sc[2 * kk][0], sc[2 * kk][1]);
+        pa[1] = MmaOp<T>::pack2(sc[2 * kk][2], sc[2 * kk][3]);
+        pa[2] = MmaOp<T>::pack2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+        pa[3] = MmaOp<T>::pack2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t vb[4];
+            ldmatrix_x4_trans(vb, sv + att_off(16 * kk + rr + (mi & 1) * 8, 2 * q + (mi >> 1)));
+            MmaOp<T>::mma(o[2 * q], pa, vb[0], vb[1]);
+            MmaOp<T>::mma(o[2 * q + 1], pa, vb[2], vb[3]);
+        }
+    }
+
+    // normalise, park the warp's 16x64 output in its own (already consumed) Q rows, store coalesced
+    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    const int g = lane >> 2;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        // columns 8j + 2*tig, +1  -> chunk j, byte offset 4*tig inside the chunk
+        *reinterpret_cast<uint32_t *>(&sm[0][att_off(r0 + g, j) + 4 * tig]) = MmaOp<T>::pack2(o[j][0] * inv0, o[j][1] * inv0);
+        *reinterpret_cast<uint32_t *>(&sm[0][att_off(r0 + g + 8, j) + 4 * tig]) = MmaOp<T>::pack2(o[j][2] * inv1, o[j][3] * inv1);
+    }
+    __syncwarp();
+    T *obase = out + (int64_t)b * S * W + h * kHeadDim;
+    for (int i = lane; i < 16 * 8; i += 32) {
+        const int row = r0 + i / 8, chunk = i % 8;
+        if (row < S) *reinterpret_cast<uint4 *>(obase + (int64_t)row * W + chunk * 8) = *reinterpret_cast<const uint4 *>(&sm[0][att_off(row, chunk)]);
+    }
+}
+
+// ------------------------------------------------------------------------- launch helpers
+template <typename T>
+static int launch_layernorm(const T *x, int64_t rows, int64_t row_stride, const float *g, const float *b, T *h, int width, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
+    switch (width / 256) {
+        case 1: layernorm_kernel<T, 1><<<grid, 256, 0, s>>>(x, rows, row_stride, g, b, h); break;
+        case 2: layernorm_kernel<T, 2><<<grid, 256, 0, s>>>(x, rows, row_stride, g, b, h); break;
+        case 3: layernorm_kernel<T, 3><<<grid, 256, 0, s>>>(x, rows, row_stride, g, b, h); break;
+        case 4: layernorm_kernel<T, 4><<<grid, 256, 0, s>>>(x, rows, row_stride, g, b, h); break;
+        default: return fail(LL_ERR_INVALID, "layernorm: width %d unsupported", width);
+    }
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+template <typename T>
+static int launch_assemble(const T *po, const T *cls, const T *pos, const float *g, const float *b, T *x, int64_t B, int S, int width, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)((B * S * 32 + 255) / 256);
+    switch (width / 256) {
+        case 1: assemble_lnpre_kernel<T, 1><<<grid, 256, 0, s>>>(po, cls, pos, g, b, x, B, S); break;
+        case 2: assemble_lnpre_kernel<T, 2><<<grid, 256, 0, s>>>(po, cls, pos, g, b, x, B, S); break;
+        case 3: assemble_lnpre_kernel<T, 3><<<grid, 256, 0, s>>>(po, cls, pos, g, b, x, B, S); break;
+        case 4: assemble_lnpre_kernel<T, 4><<<grid, 256, 0, s>>>(po, cls, pos, g, b, x, B, S); break;
+        default: return fail(LL_ERR_INVALID, "assemble: width %d unsupported", width);
+    }
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+template <typename T>
+static int launch_patchify(const void *x, int x_dtype, T *A, int64_t B, int R, int P, cudaStream_t s)
+{
+    const int64_t total = B * (R / P) * (R / P) * (int64_t)(3 * P * P / 8);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    switch (x_dtype) {
+        case LL_F32: patchify_kernel<float, T><<<grid, 256, 0, s>>>(static_cast<const float *>(x), A, B, R, P); break;
+        case LL_F16: patchify_kernel<__half, T><<<grid, 256, 0, s>>>(static_cast<const __half *>(x), A, B, R, P); break;
+        case LL_BF16: patchify_kernel<__nv_bfloat16, T><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(x), A, B, R, P); break;
+        default: return fail(LL_ERR_INVALID, "patchify: unknown dtype %d", x_dtype);
+    }
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+template <typename T>
+static int launch_attention(const T *qkv, T *out, int64_t B, int S, int H, cudaStream_t s)
+{
+    const float scale_log2e = 1.4426950408889634f / sqrtf((float)kHeadDim);
+    attention_kernel<T><<<(unsigned)(B * H), 128, 0, s>>>(qkv, out, S, H, scale_log2e);
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+}  // namespace ll
+
+// ============================================================================ runner
+using namespace ll;
+
+struct ll_vit {
+    ll_vit_config_t cfg;
+    ll_vit_weights_t w;
+    std::vector<const void *> in_proj_w, out_proj_w, fc_w, cproj_w;
+    std::vector<const float *> in_proj_b, out_proj_b, fc_b, cproj_b, ln1_w, ln1_b, ln2_w, ln2_b;
+    int tokens, grid, kpatch;
+    int64_t chunk;  // images per pass: keeps one pass's activations L2-resident
+};
+
+namespace {
+
+inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
+
+struct Workspace {
+    uint8_t *patch_a, *patch_o, *x, *h, *qkv, *f, *cls;
+    int64_t total;
+};
+
+Workspace carve(const ll_vit *v, int64_t n, uint8_t *base)
+{
+    const int W = v->cfg.width;
+    const int64_t M = n * v->tokens, Mp = n * (v->tokens - 1);
+    Workspace ws;
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        uint8_t *p = base ? base + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    ws.patch_a = take(Mp * v->kpatch * 2);
+    ws.patch_o = take(Mp * W * 2);
+    ws.x = take(M * W * 2);
+    ws.h = take(M * W * 2);
+    ws.qkv = take(M * 3 * W * 2);
+    ws.f = take(M * 4 * W * 2);
+    ws.cls = take(n * W * 2);
+    ws.total = off;
+    return ws;
+}
+
+template <typename T>
+int forward_chunk(ll_vit *v, const void *x, int x_dtype, int64_t n, void *z, const Workspace &ws, cudaStream_t s)
+{
+    const auto &c = v->cfg;
+    const int W = c.width, S = v->tokens, dt = c.dtype;
+    const int64_t M = n * S, Mp = n * (S - 1);
+    int rc;
+    auto gemm = [&](const void *A, const void *Wt, const float *bias, const void *res, void *D, int64_t m, int N, int K, int act) {
+        return gemm_launch(A, Wt, bias, res, D, m, N, K, dt, act, s);
+    };
+    if ((rc = launch_patchify<T>(x, x_dtype, (T *)ws.patch_a, n, c.res, c.patch, s))) return rc;
+    if ((rc = gemm(ws.patch_a, v->w.conv1_w, nullptr, nullptr, ws.patch_o, Mp, W, v->kpatch, 0))) return rc;
+    if ((rc = launch_assemble<T>((const T *)ws.patch_o, (const T *)v->w.class_emb, (const T *)v->w.pos_emb, v->w.ln_pre_w, v->w.ln_pre_b, (T *)ws.x, n, S, W, s))) return rc;
+    for (int l = 0; l < c.layers; ++l) {
+        if ((rc = launch_layernorm<T>((const T *)ws.x, M, W, v->ln1_w[l], v->ln1_b[l], (T *)ws.h, W, s))) return rc;
+        if ((rc = gemm(ws.h, v->in_proj_w[l], v->in_proj_b[l], nullptr, ws.qkv, M, 3 * W, W, 0))) return rc;
+        if ((rc = launch_attention<T>((const T *)ws.qkv, (T *)ws.h, n, S, c.heads, s))) return rc;
+        if ((rc = gemm(ws.h, v->out_proj_w[l], v->out_proj_b[l], ws.x, ws.x, M, W, W, 0))) return rc;
+        if ((rc = launch_layernorm<T>((const T *)ws.x, M, W, v->ln2_w[l], v->ln2_b[l], (T *)ws.h, W, s))) return rc;
+        if ((rc = gemm(ws.h, v->fc_w[l], v->fc_b[l], nullptr, ws.f, M, 4 * W, W, 1))) return rc;
+        if ((rc = gemm(ws.f, v->cproj_w[l], v->cproj_b[l], ws.x, ws.x, M, W, 4 * W, 0))) return rc;
+    }
+    if ((rc = launch_layernorm<T>((const T *)ws.x, n, (int64_t)S * W, v->w.ln_post_w, v->w.ln_post_b, (T *)ws.cls, W, s))) return rc;
+    if ((rc = gemm(ws.cls, v->w.proj_t, nullptr, nullptr, z, n, c.out_dim, W, 0))) return rc;
+    return LL_OK;
+}
+
+}  // namespace
+
+extern "C" int ll_vit_create(const ll_vit_config_t *cfg, const ll_vit_weights_t *w, ll_vit_t **out)
+{
+    LL_REQUIRE(cfg && w && out, "vit_create: null pointer");
+    LL_REQUIRE(cfg->dtype == LL_F16 || cfg->dtype == LL_BF16, "vit_create: dtype must be LL_F16 or LL_BF16");
+    LL_REQUIRE(cfg->width % 256 == 0 && cfg->width <= 1024 && cfg->width == cfg->heads * kHeadDim, "vit_create: width %d / heads %d unsupported (head dim must be 64, width a multiple of 256)", cfg->width, cfg->heads);
+    LL_REQUIRE(cfg->res % cfg->patch == 0 && (3 * cfg->patch * cfg->patch) % 64 == 0, "vit_create: bad patch/res");
+    LL_REQUIRE(cfg->out_dim % 128 == 0 && cfg->layers > 0, "vit_create: out_dim must be a multiple of 128");
+    const int g = cfg->res / cfg->patch;
+    LL_REQUIRE(g * g + 1 <= kAttRows, "vit_create: %d tokens exceed the attention kernel's %d", g * g + 1, kAttRows);
+    ll_vit *v = new (std::nothrow) ll_vit();
+    LL_REQUIRE(v != nullptr, "vit_create: out of host memory");
+    v->cfg = *cfg;
+    v->w = *w;
+    const int L = cfg->layers;
+    v->in_proj_w.assign(w->in_proj_w, w->in_proj_w + L);
+    v->out_proj_w.assign(w->out_proj_w, w->out_proj_w + L);
+    v->fc_w.assign(w->fc_w, w->fc_w + L);
+    v->cproj_w.assign(w->cproj_w, w->cproj_w + L);
+    v->in_proj_b.assign(w->in_proj_b, w->in_proj_b + L);
+    v->out_proj_b.assign(w->out_proj_b, w->out_proj_b + L);
+    v->fc_b.assign(w->fc_b, w->fc_b + L);
+    v->cproj_b.assign(w->cproj_b, w->cproj_b + L);
+    v->ln1_w.assign(w->ln1_w, w->ln1_w + L);
+    v->ln1_b.assign(w->ln1_b, w->ln1_b + L);
+    v->ln2_w.assign(w->ln2_w, w->ln2_w + L);
+    v->ln2_b.assign(w->ln2_b, w->ln2_b + L);
+    v->grid = g;
+    v->tokens = g * g + 1;
+    v->kpatch = 3 * cfg->patch * cfg->patch;
+    v->chunk = 256;
+    *out = v;
+    return LL_OK;
+}
+
+extern "C" void ll_vit_destroy(ll_vit_t *v) { delete v; }
+
+extern "C" int ll_vit_set_chunk(ll_vit_t *v, int64_t chunk)
+{
+    LL_REQUIRE(v && chunk > 0, "vit_set_chunk: bad arguments");
+    v->chunk = chunk;
+    return LL_OK;
+}
+
+extern "C" int64_t ll_vit_workspace_bytes(const ll_vit_t *v, int64_t batch)
+{
+    if (!v || batch <= 0) return 0;
+    const int64_t n = batch < v->chunk ? batch : v->chunk;
+    return carve(v, n, nullptr).total + 256;
+}
+
+extern "C" int64_t ll_vit_launches(const ll_vit_t *v, int64_t batch)
+{
+    if (!v || batch <= 0) return 0;
+    const int64_t passes = (batch + v->chunk - 1) / v->chunk;
+    return passes * (5 + 7 * (int64_t)v->cfg.layers);
+}
+
+extern "C" int ll_vit_forward(ll_vit_t *v, const void *x, int x_dtype, int64_t batch, void *z, void *workspace,
+                              int64_t workspace_bytes, ll_stream_t stream)
+{
+    LL_REQUIRE(v && x && z && workspace, "vit_forward: null pointer");
+    LL_REQUIRE(batch > 0, "vit_forward: empty batch");
+    LL_REQUIRE(workspace_bytes >= ll_vit_workspace_bytes(v, batch), "vit_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)ll_vit_workspace_bytes(v, batch));
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    const int esz_in = x_dtype == LL_F32 ? 4 : 2;
+    const int64_t img = 3LL * v->cfg.res * v->cfg.res;
+    for (int64_t b0 = 0; b0 < batch; b0 += v->chunk) {
+        const int64_t n = (batch - b0) < v->chunk ? (batch - b0) : v->chunk;
+        const Workspace ws = carve(v, n, base);
+        const void *xc = static_cast<const uint8_t *>(x) + b0 * img * esz_in;
+        void *zc = static_cast<uint8_t *>(z) + b0 * v->cfg.out_dim * 2;
+        int rc = v->cfg.dtype == LL_F16 ? forward_chunk<__half>(v, xc, x_dtype, n, zc, ws, as_stream(stream))
+                                        : forward_chunk<__nv_bfloat16>(v, xc, x_dtype, n, zc, ws, as_stream(stream));
+        if (rc != LL_OK) return rc;
+    }
+    return LL_OK;
+}
+
+// Stand-alone entry points for the numerics tests of the non-GEMM kernels.
+extern "C" int ll_layernorm(const void *x, int64_t rows, int width, const float *gamma, const float *beta, void *h,
+                            int dtype, ll_stream_t stream)
+{
+    LL_REQUIRE(x && gamma && beta && h && rows > 0, "layernorm: bad arguments");
+    return dtype == LL_F16 ? launch_layernorm<__half>((const __half *)x, rows, width, gamma, beta, (__half *)h, width, as_stream(stream))
+                           : launch_layernorm<__nv_bfloat16>((const __nv_bfloat16 *)x, rows, width, gamma, beta, (__nv_bfloat16 *)h, width, as_stream(stream));
+}
+
+extern "C" int ll_attention(const void *qkv, void *out, int64_t batch, int S, int H, int dtype, ll_stream_t stream)
+{
+    LL_REQUIRE(qkv && out && batch > 0 && S > 0 && S <= kAttRows && H > 0, "attention: bad arguments (S must be <= %d)", kAttRows);
+    return dtype == LL_F16 ? launch_attention<__half>((const __half *)qkv, (__half *)out, batch, S, H, as_stream(stream))
+                           : launch_attention<__nv_bfloat16>((const __nv_bfloat16 *)qkv, (__nv_bfloat16 *)out, batch, S, H, as_stream(stream));
+}

@@ -1,0 +1,267 @@
+"""``ClipCompressor``: the reference's torch.hub deployment API on the B200 kernels.
+
+Drop-in for ``hub.ClipCompressor`` of YannDubs/lossyless (hub/compressor.py:16-254): same
+constructor, attributes (``clip, preprocess, z_dim, side_z_dim, scaling, biasing,
+entropy_bottleneck, device``), methods, printed messages, state-dict keys and on-disk
+container format (``>I N`` then N x (``>I len`` + bytes); labels ``np.save(uint16)``).
+
+Differences by design:
+  * encode / decode are batched GPU kernels -- no per-image Python loop, no ``.tolist()``;
+  * ``decompress_dataset(is_cpu=True)`` is accepted for signature compatibility but decoding
+    always runs on the GPU (there is no CPU path in this package);
+  * CLIP weights: ``clip.load`` needs a download; pass ``clip_state_dict=`` (a CLIP checkpoint's
+    state dict or path) or the encoder is given a deterministic seeded random init and says so;
+  * the reference's known defects at this boundary are not reproduced (undefined
+    ``pretrained_path`` at :54, un-imported names in ``make_pickable_`` at :137-148).
+"""
+import struct
+import time
+import warnings
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from ..clip_vit import VisionTransformer, clip_preprocess, load_visual_state_dict
+from ..entropy_models import EntropyBottleneck, EntropyModel, _RansCoder, update_registered_buffers
+
+__all__ = ["ClipCompressor", "write_uints", "write_bytes", "read_uints", "read_bytes"]
+
+try:  # tqdm is what the reference uses for progress; optional here
+    import tqdm as _tqdm
+
+    def _progress(it, **kw):
+        return _tqdm.tqdm(it, **kw)
+except ImportError:  # pragma: no cover
+    def _progress(it, **kw):
+        return it
+
+
+class ClipCompressor(nn.Module):
+    """Our CLIP compressor.
+
+    Parameters
+    ----------
+    pretrained_state_dict : dict or str or Path
+        State dict (or path to it) of the trained bottleneck: ``scaling``, ``biasing`` and the
+        ``entropy_bottleneck.*`` tensors, as published in ``beta*_factorized_rate.pt``.
+    is_jit : bool
+        Accepted for compatibility; there is nothing to JIT (the encoder is one native call).
+    device : str
+        Device on which to load the model.
+    clip_state_dict : dict or str or Path, optional
+        CLIP ViT-B/32 weights (full model with ``visual.*`` keys, or the visual tower only).
+    """
+
+    def __init__(self, pretrained_state_dict, is_jit=False,
+                 device="cuda" if torch.cuda.is_available() else "cpu", clip_state_dict=None):
+        super().__init__()
+        self.clip = VisionTransformer(224, 32, 768, 12, 12, 512)
+        self.preprocess = clip_preprocess(224)
+        if clip_state_dict is not None:
+            if not isinstance(clip_state_dict, dict):
+                clip_state_dict = torch.load(clip_state_dict, map_location="cpu", weights_only=True)
+            self.clip.load_state_dict(load_visual_state_dict(clip_state_dict))
+            self.is_pretrained_clip = True
+        else:
+            warnings.warn("no CLIP weights given (clip_state_dict=...): the ViT-B/32 encoder uses a seeded random "
+                          "initialisation; rates and representations are synthetic.", stacklevel=2)
+            self.is_pretrained_clip = False
+        self.clip.half()  # clip.load(..., device='cuda') keeps the visual tower in fp16
+
+        self.z_dim = 512
+        self.side_z_dim = 512 // 5
+
+        # => as if you use entropy coding that uses different scales in each dim
+        self.scaling = torch.nn.Parameter(torch.ones(self.z_dim))
+        self.biasing = torch.nn.Parameter(torch.zeros(self.z_dim))
+
+        self.entropy_bottleneck = EntropyBottleneck(self.z_dim, init_scale=10, filters=[3, 3, 3, 3])
+
+        if not isinstance(pretrained_state_dict, dict):
+            pretrained_state_dict = torch.load(pretrained_state_dict, map_location="cpu", weights_only=True)
+
+        update_registered_buffers(
+            self.entropy_bottleneck, "entropy_bottleneck",
+            ["_quantized_cdf", "_offset", "_cdf_length"], pretrained_state_dict)
+        self.load_state_dict(pretrained_state_dict, strict=False)
+        self.entropy_bottleneck.update()
+
+        self.device = device
+        self.to(self.device)
+        self.eval()
+
+    def to(self, device):
+        self.device = device
+        return super().to(device)
+
+    # -- representation <-> bottleneck domain (hub/compressor.py:105-115) -----------------
+    def process_z_in(self, z):
+        """Preprocessing of representation before entropy bottleneck."""
+        z_in = (z.float() + self.biasing) * self.scaling.exp()
+        return z_in.unsqueeze(-1).unsqueeze(-1)
+
+    def process_z_out(self, z_hat):
+        """Postprocessing of representation after entropy bottleneck."""
+        z_hat = z_hat.squeeze(-1).squeeze(-1)
+        return (z_hat / self.scaling.exp()) - self.biasing
+
+    def _exp_scale(self):
+        return self.scaling.detach().exp()
+
+    @torch.no_grad()
+    def forward(self, X, is_compress=False):
+        """Featurise a batch of CLIP-normalised images [B,3,224,224], with or without compression.
+
+        Returns a list of B byte strings if ``is_compress`` else ``z_hat`` [B,512]."""
+        z = self.clip(X)
+        if is_compress:
+            # process_z_in + quantise + rANS fused in one kernel
+            return self.entropy_bottleneck.compress(z, bias=self.biasing, exp_scale=self._exp_scale())
+        from ..entropy_models import eb_rate_forward
+
+        z_hat, _, _ = eb_rate_forward(self.entropy_bottleneck, z, None, self.biasing, self.scaling, want_rates=False)
+        return z_hat
+
+    def compress(self, X):
+        """Return compressed features (list of byte strings)."""
+        return self(X, is_compress=True)
+
+    @torch.no_grad()
+    def decompress(self, byte_str):
+        """Decompress a list of byte strings -> z_hat [B,512]."""
+        z_hat = self.entropy_bottleneck.decompress(byte_str, [1, 1], bias=self.biasing, exp_scale=self._exp_scale())
+        return z_hat.squeeze(-1).squeeze(-1)
+
+    def get_rate(self, X):
+        """Actual (after entropy coding) mean rate per image of a batch, in bits."""
+        _, _, lens = self._compress_records(X, mode=0)
+        return float(lens.float().mean().item()) * 8
+
+    def make_pickable_(self):
+        """Ensure that the estimator is pickable, which is necessary for distributed training."""
+        for m in self.modules():
+            if isinstance(m, EntropyModel):
+                m.entropy_coder = None
+        self.clip.refresh_native_()
+
+    def undo_pickable_(self):
+        """Undo `make_pickable_`, e.g. ensures that the coder is available."""
+        for m in self.modules():
+            if isinstance(m, EntropyModel):
+                m.entropy_coder = _RansCoder()
+
+    # -- batched device-side encode ---------------------------------------------------------
+    @torch.no_grad()
+    def _compress_records(self, X, mode):
+        """images -> (packed device bytes, offsets int64 [B+1], lens int32 [B]) without leaving the GPU."""
+        z = self.clip(X)
+        packed, offsets, lens, _ = self.entropy_bottleneck.compress_to_device(
+            z, bias=self.biasing, exp_scale=self._exp_scale(), mode=mode)
+        return packed, offsets, lens
+
+    def compress_batch_to_host(self, X_host, out_host=None):
+        """One step of the encode hot path with HOST buffers: pinned-host images ->
+        H2D -> ViT -> quantise + rANS -> container records -> D2H.  Returns
+        (records: uint8 numpy view of the batch's ``>I len + bytes`` records, n_images)."""
+        X = X_host.to(self.device, non_blocking=True)
+        if X.dtype == torch.float32:
+            X = X.half()
+        packed, offsets, _ = self._compress_records(X, mode=1)
+        total = int(offsets[-1].item())  # one 8-byte D2H: size of this batch's records
+        if out_host is None or out_host.numel() < total:
+            out_host = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+        out_host[:total].copy_(packed[:total], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host[:total], X.shape[0], out_host
+
+    def compress_dataset(self, dataset, file, label_file=None,
+                         kwargs_dataloader=dict(batch_size=128, num_workers=16), is_info=True):
+        """Compress a torchvision-style dataset (items ``(x[3,224,224] CLIP-normalised, *labels)``)
+        and save it to ``file`` (and the labels to ``label_file``)."""
+        from torch.utils.data import DataLoader
+
+        if self.device == "cpu" or str(self.device).startswith("cpu"):
+            raise ValueError("Compression only implemented on GPU (as uses fp16).")
+
+        start = time.time()
+        n, Y, pinned = 0, [], None
+        with Path(file).open("wb") as f:
+            write_uints(f, (0,))  # N, patched below once known
+            for x, *y in _progress(DataLoader(dataset, **kwargs_dataloader)):
+                records, b, pinned = self.compress_batch_to_host(x, pinned)
+                f.write(records.numpy().data)
+                n += b
+                if label_file is not None:
+                    Y += [y[0].cpu().numpy().astype(np.uint16)]
+            f.seek(0)
+            write_uints(f, (n,))
+
+        enc_time = (time.time() - start) / max(n, 1)
+        rate = 8 * Path(file).stat().st_size / max(n, 1)
+
+        if label_file is not None:
+            np.save(label_file, np.concatenate(Y), allow_pickle=False)  # no pickle for portability
+
+        if is_info:
+            print(f"Rate: {rate:.2f} bits/img | Encoding: {1/enc_time:.2f} img/sec ")
+
+    def decompress_dataset(self, file, label_file=None, is_info=True, is_cpu=True, batch_size=8192):
+        """Decompress a dataset saved by ``compress_dataset``; returns ``Z_hat`` float32 [N,512]
+        (and ``Y`` int64 if ``label_file``).  ``is_cpu`` is accepted but decoding runs on the GPU."""
+        if str(self.device).startswith("cpu"):
+            raise N.NativeError("decompress_dataset needs the compressor on a B200 (cuda); there is no CPU path")
+        start = time.time()
+        raw = np.fromfile(str(file), dtype=np.uint8)
+        if raw.size < 4:
+            raise ValueError(f"{file}: truncated container (no record count)")
+        n_Z = struct.unpack(">I", raw[:4].tobytes())[0]
+        offsets = np.zeros(n_Z + 1, dtype=np.int64)
+        lens = np.zeros(n_Z, dtype=np.int32)
+        try:
+            N.call("ll_container_index", raw.ctypes.data, raw.size, 4, n_Z, offsets.ctypes.data, lens.ctypes.data)
+        except N.NativeError as e:
+            raise ValueError(f"{file}: {e}") from None
+        if n_Z and ((lens % 4 != 0).any() or (lens < 8).any()):
+            raise ValueError(f"{file}: malformed record length (rANS streams are >= 8 bytes, multiple of 4)")
+        Z_hat = np.empty((n_Z, self.z_dim), dtype=np.float32)
+        data = torch.from_numpy(np.concatenate([raw, np.zeros(16, dtype=np.uint8)])).to(self.device)
+        off_d, lens_d = torch.from_numpy(offsets).to(self.device), torch.from_numpy(lens).to(self.device)
+        es = self._exp_scale()
+        for i0 in _progress(range(0, n_Z, batch_size)):
+            i1 = min(n_Z, i0 + batch_size)
+            z, _ = self.entropy_bottleneck.decompress_from_device(
+                data, off_d[i0:i1 + 1].contiguous(), lens_d[i0:i1].contiguous(), bias=self.biasing, exp_scale=es)
+            Z_hat[i0:i1] = z.cpu().numpy()
+
+        dec_time = (time.time() - start) / max(n_Z, 1)
+        if is_info:
+            print(f"Decoding: {1/dec_time:.2f} img/sec ")
+
+        if label_file is not None:
+            Y = np.load(label_file, allow_pickle=False).astype(np.int64)
+            return Z_hat, Y
+        return Z_hat
+
+
+# container helpers (same format as hub/compressor.py:258-275 / compressai examples/codec.py)
+def write_uints(fd, values, fmt=">{:d}I"):
+    fd.write(struct.pack(fmt.format(len(values)), *values))
+
+
+def write_bytes(fd, values, fmt=">{:d}s"):
+    if len(values) == 0:
+        return
+    fd.write(struct.pack(fmt.format(len(values)), values))
+
+
+def read_uints(fd, n, fmt=">{:d}I"):
+    sz = struct.calcsize("I")
+    return struct.unpack(fmt.format(n), fd.read(n * sz))
+
+
+def read_bytes(fd, n, fmt=">{:d}s"):
+    sz = struct.calcsize("s")
+    return struct.unpack(fmt.format(n), fd.read(n * sz))[0]
