@@ -191,6 +191,12 @@ int64_t ll_vit_launches(const ll_vit_t *v, int64_t batch);
 /* images per internal pass (default 256): a pass's activations are sized to stay in L2 */
 int ll_vit_set_chunk(ll_vit_t *v, int64_t chunk);
 
+/* Per-GEMM device timing for the roofline report: between begin and end every GEMM launch of
+ * ll_vit_forward is bracketed by cudaEvents on the launch stream; end synchronises and returns
+ * the summed GEMM milliseconds, algorithmic FLOPs (2*M*N*K) and launch count. */
+int ll_vit_profile_begin(ll_vit_t *v);
+int ll_vit_profile_end(ll_vit_t *v, double *gemm_ms, double *gemm_flops, int64_t *gemm_launches);
+
 /* Stand-alone entry points of the encoder's non-GEMM kernels (numerics tests).
  * ll_layernorm: h[r,:] = LN(x[r,:]) * gamma + beta, fp32 statistics, eps 1e-5 (clip LayerNorm).
  * ll_attention: qkv [batch*S, 3*H*64] (q|k|v, head-major) -> out [batch*S, H*64];

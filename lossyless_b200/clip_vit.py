@@ -183,6 +183,17 @@ class VisionTransformer(nn.Module):
         nat = self._native or self._build_native()
         return int(N.load().ll_vit_launches(nat["handle"], int(batch)))
 
+    def profile_begin(self):
+        nat = self._native or self._build_native()
+        N.call("ll_vit_profile_begin", nat["handle"])
+
+    def profile_end(self):
+        """-> (gemm_ms, gemm_flops, gemm_launches) accumulated since profile_begin()."""
+        nat = self._native
+        ms, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        N.call("ll_vit_profile_end", nat["handle"], ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n))
+        return ms.value, fl.value, n.value
+
     @torch.no_grad()
     def forward(self, x):
         """x [B,3,R,R] (fp16 / bf16 / fp32, cuda, CLIP-normalised) -> z [B, output_dim] in the

@@ -360,6 +360,25 @@ struct ll_vit {
     std::vector<const float *> in_proj_b, out_proj_b, fc_b, cproj_b, ln1_w, ln1_b, ln2_w, ln2_b;
     int tokens, grid, kpatch;
     int64_t chunk;  // images per pass: keeps one pass's activations L2-resident
+    // optional per-GEMM timing (bench.py's roofline leg): event pairs on the launch stream
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    double prof_flops = 0.0;
+    int64_t prof_launches = 0;
+    ~ll_vit()
+    {
+        for (auto e : ev_pool) cudaEventDestroy(e);
+    }
+    cudaEvent_t next_event()
+    {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
 };
 
 namespace {
@@ -401,7 +420,14 @@ int forward_chunk(ll_vit *v, const void *x, int x_dtype, int64_t n, void *z, con
     const int64_t M = n * S, Mp = n * (S - 1);
     int rc;
     auto gemm = [&](const void *A, const void *Wt, const float *bias, const void *res, void *D, int64_t m, int N, int K, int act) {
-        return gemm_launch(A, Wt, bias, res, D, m, N, K, dt, act, s);
+        if (!v->profiling) return gemm_launch(A, Wt, bias, res, D, m, N, K, dt, act, s);
+        cudaEvent_t e0 = v->next_event(), e1 = v->next_event();
+        cudaEventRecord(e0, s);
+        const int r = gemm_launch(A, Wt, bias, res, D, m, N, K, dt, act, s);
+        cudaEventRecord(e1, s);
+        v->prof_flops += 2.0 * (double)m * N * K;
+        v->prof_launches += 1;
+        return r;
     };
     if ((rc = launch_patchify<T>(x, x_dtype, (T *)ws.patch_a, n, c.res, c.patch, s))) return rc;
     if ((rc = gemm(ws.patch_a, v->w.conv1_w, nullptr, nullptr, ws.patch_o, Mp, W, v->kpatch, 0))) return rc;
@@ -497,6 +523,34 @@ extern "C" int ll_vit_forward(ll_vit_t *v, const void *x, int x_dtype, int64_t b
                                         : forward_chunk<__nv_bfloat16>(v, xc, x_dtype, n, zc, ws, as_stream(stream));
         if (rc != LL_OK) return rc;
     }
+    return LL_OK;
+}
+
+extern "C" int ll_vit_profile_begin(ll_vit_t *v)
+{
+    LL_REQUIRE(v, "vit_profile_begin: null handle");
+    v->profiling = true;
+    v->ev_used = 0;
+    v->prof_flops = 0.0;
+    v->prof_launches = 0;
+    return LL_OK;
+}
+
+extern "C" int ll_vit_profile_end(ll_vit_t *v, double *gemm_ms, double *gemm_flops, int64_t *gemm_launches)
+{
+    LL_REQUIRE(v && gemm_ms && gemm_flops && gemm_launches, "vit_profile_end: null pointer");
+    v->profiling = false;
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < v->ev_used; i += 2) {
+        LL_CUDA_CHECK(cudaEventSynchronize(v->ev_pool[i + 1]));
+        float t = 0.f;
+        LL_CUDA_CHECK(cudaEventElapsedTime(&t, v->ev_pool[i], v->ev_pool[i + 1]));
+        ms += t;
+    }
+    *gemm_ms = ms;
+    *gemm_flops = v->prof_flops;
+    *gemm_launches = v->prof_launches;
+    v->ev_used = 0;
     return LL_OK;
 }
 

@@ -1,0 +1,82 @@
+"""GPU numerics: the encoder's non-GEMM kernels against plain torch fp32, and the whole
+ViT-B/32 forward against the fp32 CPU oracle (tolerance: 16-bit activations, stated below)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit as ovit
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_layernorm(cuda_device, dtype):
+    from lossyless_b200 import _native as N
+
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    x = (torch.randn(1000, 768, generator=g, device=cuda_device) * 3 + 0.5).to(dtype)
+    w = torch.randn(768, generator=g, device=cuda_device)
+    b = torch.randn(768, generator=g, device=cuda_device)
+    h = torch.empty_like(x)
+    N.call("ll_layernorm", N.ptr(x), 1000, 768, N.ptr(w), N.ptr(b), N.ptr(h), N.dtype_code(x), N.stream())
+    ref = torch.nn.functional.layer_norm(x.float(), (768,), w, b, 1e-5)
+    tol = 4e-3 if dtype == torch.float16 else 3e-2
+    assert (h.float() - ref).abs().max().item() < tol * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("S", [50, 64, 17])
+def test_attention(cuda_device, dtype, S):
+    from lossyless_b200 import _native as N
+
+    B, H, d = 9, 12, 64
+    g = torch.Generator(device=cuda_device).manual_seed(S)
+    qkv = (torch.randn(B * S, 3 * H * d, generator=g, device=cuda_device)).to(dtype)
+    out = torch.empty(B * S, H * d, dtype=dtype, device=cuda_device)
+    N.call("ll_attention", N.ptr(qkv), N.ptr(out), B, S, H, N.dtype_code(qkv), N.stream())
+    q, k, v = qkv.float().reshape(B, S, 3, H, d).permute(2, 0, 3, 1, 4)
+    att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)
+    ref = (att @ v).permute(0, 2, 1, 3).reshape(B * S, H * d)
+    tol = 3e-3 if dtype == torch.float16 else 2e-2
+    assert (out.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
+def _product_vit(cuda_device, layers=12):
+    from lossyless_b200.clip_vit import VisionTransformer
+
+    cfg = ovit.vit_config(layers=layers)
+    sd = ovit.init_state_dict(0, cfg)
+    vit = VisionTransformer(224, 32, 768, layers, 12, 512)
+    vit.load_state_dict(sd)
+    return vit.half().to(cuda_device), sd, cfg
+
+
+def test_vit_two_layers_vs_oracle(cuda_device):
+    vit, sd, cfg = _product_vit(cuda_device, layers=2)
+    x = torch.randn(5, 3, 224, 224, generator=torch.Generator().manual_seed(3)).half()
+    sd16 = {k: v.half().float() for k, v in sd.items()}  # oracle sees the same 16-bit weights
+    with torch.no_grad():
+        ref = ovit.forward(sd16, x.float(), cfg)
+    z = vit(x.to(cuda_device)).float().cpu()
+    err = (z - ref).abs()
+    assert err.max().item() < 2e-2 and err.mean().item() < 3e-3, (err.max().item(), err.mean().item())
+
+
+def test_vit_b32_vs_golden(cuda_device, golden_dir):
+    """Full ViT-B/32 on the committed input; the fp32 oracle output is the golden file.
+    Tolerance for fp16 storage / fp32 accumulation over 12 blocks: max |dz| < 5e-2 on z ~ N(0,1),
+    mean |dz| < 8e-3.  Also checks batch-size / chunking invariance."""
+    g = np.load(os.path.join(golden_dir, "vit_b32.npz"))
+    vit, sd, cfg = _product_vit(cuda_device)
+    x = torch.from_numpy(g["x_f16"]).to(cuda_device)
+    z = vit(x).float().cpu().numpy()
+    err = np.abs(z - g["z"])
+    assert err.max() < 5e-2 and err.mean() < 8e-3, (err.max(), err.mean())
+    assert vit(x.float()).float().cpu().numpy().tolist() == z.tolist()  # fp32 input is cast on load
+    xb = x.repeat(150, 1, 1, 1)  # 300 images: crosses the 256-image internal pass boundary
+    zb = vit(xb).float().cpu().numpy()
+    assert np.array_equal(zb[0::2], np.repeat(z[:1], 150, 0)) and np.array_equal(zb[1::2], np.repeat(z[1:], 150, 0))
+    assert vit.launches(300) == 2 * (5 + 7 * 12)
