@@ -12,8 +12,11 @@
 //   warp 0      TMA producer: 128xBK A tile + BNxBK W tile per stage, 128B swizzle, mbarrier tx
 //   warp 1      allocates TMEM; one lane issues tcgen05.mma (M=128, N=BN, K=16) into one of two
 //               TMEM accumulator buffers, commits stage-empty / accumulator-full barriers
-//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns), bias / QuickGELU / residual in
-//               fp32, 16-bit stores; overlaps the next tile's main loop (double-buffered TMEM)
+//   warps 2..5  epilogue, overlapping the next tile's main loop (double-buffered TMEM): per
+//               32-row x 64-column group tcgen05.ld -> bias / QuickGELU / residual in fp32 ->
+//               16-bit, swizzled st.shared -> TMA store (full 128 B lines; the row-per-thread
+//               accumulator layout would otherwise scatter 16 B pieces over 32 lines per store).
+//               The residual tile arrives by TMA into the same staging buffer one group ahead.
 #include <cstring>
 
 #include "gemm_sm100.cuh"
@@ -24,6 +27,8 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 x 16-bit = one 128 B swizzle row
 constexpr int kGemmThreads = 192;
 constexpr int kABytes = kBM * kBK * 2;
+constexpr int kEpiCols = 64;                    // one 128 B swizzle row of 16-bit outputs
+constexpr int kEpiBufBytes = 32 * kEpiCols * 2;  // 32 rows (one warp's TMEM lanes) x 64 columns
 
 template <int BN>
 struct GemmShape {
@@ -31,8 +36,10 @@ struct GemmShape {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BN == 256) ? 4 : 6;
     static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
-    static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment
+    static constexpr int kGroups = BN / kEpiCols;       // 64-column epilogue groups per tile
+    static constexpr int kStagingBytes = 4 * 2 * kEpiBufBytes;  // 4 epilogue warps x 2 buffers
+    static constexpr int kBarBytes = (2 * kStages + 4 + 8) * 8 + 16;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +1024: alignment
 };
 
 template <typename T>
@@ -82,14 +89,19 @@ struct Pack8<__nv_bfloat16> {
 
 __device__ __forceinline__ float quick_gelu(float x)
 {
-    // CLIP QuickGELU: x * sigmoid(1.702 x)
-    return x * __frcp_rn(1.f + __expf(-1.702f * x));
+    // CLIP QuickGELU: x * sigmoid(1.702 x) = 0.5 x (1 + tanh(0.851 x)); one MUFU op per element
+    // (the epilogue of c_fc is SFU-bound otherwise: ex2 + rcp = 2 MUFU x 32 768 elements per tile)
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
 }
 
 template <typename T, int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    const float *__restrict__ bias, const T *residual, T *D, int M, int N, int K, int act)
+                    const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
+                    const float *__restrict__ bias, int has_residual, int M, int N, int K, int act)
 {
     using S = GemmShape<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -97,11 +109,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sm_a = smem;
     uint8_t *sm_b = smem + S::kStages * kABytes;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::kStages * S::kStageBytes);
+    uint8_t *sm_epi = smem + S::kStages * S::kStageBytes;  // [4 warps][2][32 rows x 128 B], 1024-aligned
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(sm_epi + S::kStagingBytes);
     uint64_t *empty_bar = full_bar + S::kStages;
     uint64_t *tfull_bar = empty_bar + S::kStages;  // [2] accumulator ready for the epilogue
     uint64_t *tempty_bar = tfull_bar + 2;          // [2] accumulator drained
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+    uint64_t *res_bar = tempty_bar + 2;            // [4 warps][2] residual tile landed in the staging buffer
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 8);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -109,6 +123,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_w);
+        ptx::prefetch_tmap(&tmap_d);
+        if (has_residual) ptx::prefetch_tmap(&tmap_r);
+        for (int i = 0; i < 8; ++i) ptx::mbar_init(&res_bar[i], 1);
         for (int i = 0; i < S::kStages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], 1);
@@ -181,54 +198,93 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5)
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32)
+        uint8_t *buf0 = sm_epi + quarter * 2 * kEpiBufBytes;
+        uint64_t *rbar = res_bar + quarter * 2;
+        uint32_t rphase[2] = {0, 0};
+        const int swz = lane & 7;  // 128 B swizzle: 16 B chunk j of row r lives at chunk j ^ (r & 7)
+        uint8_t *my_row0 = buf0 + lane * 128;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (tile / num_n) * kBM;
+            const int m0 = (tile / num_n) * kBM + quarter * 32;
             const int n0 = (tile % num_n) * BN;
-            const int row = m0 + quarter * 32 + lane;
+            if (has_residual && lane == 0) {
+                // first residual group of this tile, fetched while the MMAs are still running
+                ptx::tma_store_wait_read<0>();
+                ptx::mbar_expect_tx(&rbar[0], kEpiBufBytes);
+                ptx::tma_load_2d(buf0, &tmap_r, &rbar[0], n0, m0);
+            }
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-            T *drow = D + (int64_t)row * N + n0;
-            const T *rrow = residual ? residual + (int64_t)row * N + n0 : nullptr;
 #pragma unroll 1
-            for (int cc = 0; cc < BN / 32; ++cc) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(taddr + cc * 32, r);
-                ptx::tmem_ld_wait();
-                if (row < M) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float f[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[g * 8 + j]);
-                        const int col = cc * 32 + g * 8;
-                        if (bias != nullptr) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + n0 + col));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + n0 + col + 4));
-                            f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
-                            f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+            for (int g = 0; g < S::kGroups; ++g) {
+                const int b = g & 1;
+                uint8_t *my_row = my_row0 + b * kEpiBufBytes;
+                if (lane == 0) {
+                    if (has_residual) {
+                        if (g + 1 < S::kGroups) {
+                            // buffer b^1 was last read by the store of group g-1: wait, then prefetch
+                            ptx::tma_store_wait_read<0>();
+                            ptx::mbar_expect_tx(&rbar[b ^ 1], kEpiBufBytes);
+                            ptx::tma_load_2d(buf0 + (b ^ 1) * kEpiBufBytes, &tmap_r, &rbar[b ^ 1], n0 + (g + 1) * kEpiCols, m0);
                         }
-                        if (act == 1) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = quick_gelu(f[j]);
-                        }
-                        if (rrow != nullptr) {
-                            float rf[8];
-                            Pack8<T>::unpack(*reinterpret_cast<const uint4 *>(rrow + col), rf);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] += rf[j];
-                        }
-                        *reinterpret_cast<uint4 *>(drow + col) = Pack8<T>::pack(f);
+                    } else {
+                        ptx::tma_store_wait_read<1>();  // the store that last read buffer b (group g-2) is done
                     }
                 }
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld_32x32(taddr + g * kEpiCols, r0);
+                ptx::tmem_ld_32x32(taddr + g * kEpiCols + 32, r1);
+                ptx::tmem_ld_wait();
+                if (g == S::kGroups - 1) {
+                    // accumulator fully read: hand the TMEM buffer back to the MMA warp early
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                }
+                if (has_residual) {
+                    ptx::mbar_wait(&rbar[b], rphase[b]);
+                    rphase[b] ^= 1;
+                } else {
+                    __syncwarp();  // lane 0's wait_group.read above orders the overwrite of buffer b
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(j < 4 ? r0[j * 8 + e] : r1[(j - 4) * 8 + e]);
+                    const int col = n0 + g * kEpiCols + j * 8;
+                    if (bias != nullptr) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + col));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + col + 4));
+                        f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
+                        f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+                    }
+                    if (act == 1) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = quick_gelu(f[e]);
+                    }
+                    uint4 *slot = reinterpret_cast<uint4 *>(my_row + ((j ^ swz) << 4));
+                    if (has_residual) {
+                        float rf[8];
+                        Pack8<T>::unpack(*slot, rf);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] += rf[e];
+                    }
+                    *slot = Pack8<T>::pack(f);
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_2d(&tmap_d, buf0 + b * kEpiBufBytes, n0 + g * kEpiCols, m0);
+                    ptx::tma_store_commit();
+                }
             }
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
         }
+        if (lane == 0) ptx::tma_store_wait_all();  // global writes complete before the CTA exits
+        __syncwarp();
     }
 
     // ---------------------------------------------------------------- teardown
@@ -276,8 +332,8 @@ int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, int64_t rows, in
 }
 
 template <typename T, int BN>
-static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const float *bias, const void *residual, void *D,
-                       int64_t M, int N, int K, int act, cudaStream_t stream)
+static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr,
+                       const float *bias, int has_residual, int64_t M, int N, int K, int act, cudaStream_t stream)
 {
     using S = GemmShape<BN>;
     static bool configured = false;
@@ -288,8 +344,7 @@ static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const float
     }
     const int tiles = (int)((M + kBM - 1) / kBM) * (N / BN);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, kGemmThreads, S::kSmemBytes, stream>>>(ta, tw, bias, static_cast<const T *>(residual),
-                                                        static_cast<T *>(D), (int)M, N, K, act);
+    kern<<<grid, kGemmThreads, S::kSmemBytes, stream>>>(ta, tw, td, tr, bias, has_residual, (int)M, N, K, act);
     LL_LAUNCH_CHECK();
     return LL_OK;
 }
@@ -303,14 +358,15 @@ static int pick_bn(int64_t M, int N)
     return tiles256 >= 2 * (int64_t)num_sms() ? 256 : 128;
 }
 
-int gemm_launch_tmaps(const CUtensorMap &ta, const CUtensorMap &tw, int bn, const float *bias, const void *residual,
-                      void *D, int64_t M, int N, int K, int dtype, int act, cudaStream_t stream)
+int gemm_launch_tmaps(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr, int bn,
+                      const float *bias, int has_residual, int64_t M, int N, int K, int dtype, int act,
+                      cudaStream_t stream)
 {
     if (dtype == LL_F16)
-        return bn == 256 ? launch_impl<__half, 256>(ta, tw, bias, residual, D, M, N, K, act, stream)
-                         : launch_impl<__half, 128>(ta, tw, bias, residual, D, M, N, K, act, stream);
-    return bn == 256 ? launch_impl<__nv_bfloat16, 256>(ta, tw, bias, residual, D, M, N, K, act, stream)
-                     : launch_impl<__nv_bfloat16, 128>(ta, tw, bias, residual, D, M, N, K, act, stream);
+        return bn == 256 ? launch_impl<__half, 256>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream)
+                         : launch_impl<__half, 128>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+    return bn == 256 ? launch_impl<__nv_bfloat16, 256>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream)
+                     : launch_impl<__nv_bfloat16, 128>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
 }
 
 int gemm_pick_bn(int64_t M, int N) { return pick_bn(M, N); }
@@ -325,12 +381,19 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
                    (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
                "gemm: D / residual / bias must be 16-byte aligned");
     const int bn = pick_bn(M, N);
-    CUtensorMap ta, tw;
+    CUtensorMap ta, tw, td, tr;
     int rc = make_tmap_2d(&ta, A, dtype, M, K, kBM);
     if (rc != LL_OK) return rc;
     rc = make_tmap_2d(&tw, W, dtype, N, K, bn);
     if (rc != LL_OK) return rc;
-    return gemm_launch_tmaps(ta, tw, bn, bias, residual, D, M, N, K, dtype, act, stream);
+    rc = make_tmap_2d(&td, D, dtype, M, N, 32);  // epilogue staging box: 32 rows x 64 columns
+    if (rc != LL_OK) return rc;
+    tr = td;
+    if (residual != nullptr && residual != D) {
+        rc = make_tmap_2d(&tr, residual, dtype, M, N, 32);
+        if (rc != LL_OK) return rc;
+    }
+    return gemm_launch_tmaps(ta, tw, td, tr, bn, bias, residual != nullptr, M, N, K, dtype, act, stream);
 }
 
 }  // namespace ll

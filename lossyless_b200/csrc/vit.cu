@@ -13,9 +13,6 @@
 
 namespace ll {
 
-int gemm_launch_tmaps(const CUtensorMap &ta, const CUtensorMap &tw, int bn, const float *bias, const void *residual,
-                      void *D, int64_t M, int N, int K, int dtype, int act, cudaStream_t stream);
-int gemm_pick_bn(int64_t M, int N);
 
 // ------------------------------------------------------------------------- patchify
 // x [B,3,R,R] (NCHW) -> A [B*G*G, 3*P*P], column index = c*P*P + ky*P + kx, the layout of

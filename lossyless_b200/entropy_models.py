@@ -287,6 +287,10 @@ class EntropyBottleneck(EntropyModel):
         if C != self.channels:
             raise ValueError(f"expected {self.channels} channels, got {C}")
         t = self._coder_tables(z.device)
+        if rows == 0:
+            return (torch.empty(0, dtype=torch.uint8, device=z.device), torch.zeros(1, dtype=torch.int64, device=z.device),
+                    torch.empty(0, dtype=torch.int32, device=z.device),
+                    torch.empty((0, C), dtype=torch.int32, device=z.device) if want_symbols else None)
         cap = N.load().ll_rans_stream_cap_bytes(C)
         scratch = torch.empty((rows, cap), dtype=torch.uint8, device=z.device)
         lens = torch.empty(rows, dtype=torch.int32, device=z.device)
@@ -323,6 +327,8 @@ class EntropyBottleneck(EntropyModel):
             self.entropy_coder = _RansCoder()
         t = self._coder_tables(data.device)
         rows, C = lens.numel(), self.channels
+        if rows == 0:
+            return torch.empty((0, C), dtype=torch.float32, device=data.device), None
         z_hat = torch.empty((rows, C), dtype=torch.float32, device=data.device)
         status = torch.empty(rows, dtype=torch.int32, device=data.device)
         symbols = torch.empty((rows, C), dtype=torch.int32, device=data.device) if want_symbols else None
@@ -431,7 +437,7 @@ class _EBRate(torch.autograd.Function):
     """(z, biasing, scaling, *eb params) -> (z_hat, q, rates) through ll_eb_forward/backward."""
 
     @staticmethod
-    def forward(ctx, eb, z, noise, biasing, scaling, want_rates, *params):
+    def forward(ctx, eb, z, noise, biasing, scaling, exp_scale, *params):
         N.require_cuda(z, "z")
         z = z.contiguous()
         rows, C = z.shape
@@ -439,7 +445,9 @@ class _EBRate(torch.autograd.Function):
         packed, raw = _packed_params(eb, dev)
         has_affine = biasing is not None
         b = biasing.detach().float().contiguous() if has_affine else None
-        es = scaling.detach().float().exp().contiguous() if has_affine else None
+        es = None
+        if has_affine:
+            es = exp_scale.detach().float().contiguous() if exp_scale is not None else scaling.detach().float().exp().contiguous()
         med = eb._get_medians().detach().reshape(-1).float().contiguous()
         z_hat = torch.empty((rows, C), dtype=torch.float32, device=dev)
         q = torch.empty((rows, C), dtype=torch.float32, device=dev)
@@ -494,15 +502,16 @@ class _EBRate(torch.autograd.Function):
         return (None, gz.to(z.dtype), None, g_bias, g_scaling, None, *params_grads)
 
 
-def eb_rate_forward(eb, z, noise, biasing, scaling, want_rates=True):
+def eb_rate_forward(eb, z, noise, biasing, scaling, want_rates=True, exp_scale=None):
     """Fused ``process_z_in -> EntropyBottleneck -> process_z_out`` (+ per-row rate in nats).
 
     z [rows, C]; noise [rows, C] float32 (training) or None (eval: dequantise); biasing /
     scaling are the HRateEstimator parameters (None, None: z is already z_in and the returned
-    z_hat is in the bottleneck's domain).  Returns (z_hat, q, rates)."""
+    z_hat is in the bottleneck's domain); ``exp_scale`` optionally supplies a precomputed
+    exp(scaling) (the codec's CPU-evaluated one).  Returns (z_hat, q, rates)."""
     params = []
     for i in range(5):
         params += [getattr(eb, f"_matrix{i}"), getattr(eb, f"_bias{i}")]
         if i < 4:
             params.append(getattr(eb, f"_factor{i}"))
-    return _EBRate.apply(eb, z, noise, biasing, scaling, want_rates, *params)
+    return _EBRate.apply(eb, z, noise, biasing, scaling, exp_scale, *params)

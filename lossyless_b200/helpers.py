@@ -1,0 +1,233 @@
+"""Hot-path helpers of the reference's ``lossyless/helpers.py`` (the plotting half is out of
+scope): ``BASE_LOG`` (:27), ``Timer`` (:45-56), ``atleast_ndim`` (:330), ``Delta`` (:338-392),
+``Annealer`` (:768-870), ``GatherFromGpus`` (:873-893), ``weights_init`` (:153), optimiser /
+scheduler factories (:492-593) and a minimal attribute-dict for hparams
+(utils/helpers.py ``NamespaceMap``)."""
+import math
+import time
+from functools import reduce
+from numbers import Number
+
+import torch
+import torch.nn as nn
+from torch.distributions import Distribution, constraints
+from torch.distributions.utils import broadcast_all
+
+BASE_LOG = 2  # rates are logged in bits, losses are computed in nats
+
+MEANS = dict(clip=[0.48145466, 0.4578275, 0.40821073])
+STDS = dict(clip=[0.26862954, 0.26130258, 0.27577711])
+
+
+class Timer:
+    """Context manager measuring wall time; synchronises CUDA on both edges (the reference does
+    not, which is only correct because its `.tolist()` synchronises)."""
+
+    def __enter__(self):
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self.start = time.perf_counter()
+        return self
+
+    def __exit__(self, *args):
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self.end = time.perf_counter()
+        self.duration = self.end - self.start
+
+
+def mean(array):
+    return sum(array) / len(array)
+
+
+def prod(iterable):
+    return reduce(lambda a, b: a * b, iterable, 1)
+
+
+def atleast_ndim(x, ndim):
+    if x is None:
+        return None
+    return x.view(list(x.shape) + [1] * (ndim - x.ndim))
+
+
+def batch_flatten(x):
+    shape = x.shape
+    return x.reshape(-1, shape[-1]), shape
+
+
+def batch_unflatten(x, shape):
+    return x.reshape(*shape[:-1], -1)
+
+
+class OrderedSet(dict):
+    """Insertion-ordered set of (hashable) parameters with the set algebra the reference uses."""
+
+    def __init__(self, items=()):
+        super().__init__((i, None) for i in items)
+
+    def __or__(self, other):
+        return OrderedSet(list(self) + [o for o in other if o not in self])
+
+    def __sub__(self, other):
+        other = set(other)
+        return OrderedSet([i for i in self if i not in other])
+
+    def __and__(self, other):
+        other = set(other)
+        return OrderedSet([i for i in self if i in other])
+
+
+class NamespaceMap(dict):
+    """dict with attribute access, nested (enough of utils/helpers.py:44-106 for hparams)."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = NamespaceMap(v) if isinstance(v, dict) and not isinstance(v, NamespaceMap) else v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k) from None
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def weights_init(module, nonlinearity="relu"):
+    """Initialise direct children: Kaiming for conv / linear, recursion through reset_parameters."""
+    for m in module.children():
+        if isinstance(m, nn.modules.conv._ConvNd):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity=nonlinearity)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.Linear):
+            nn.init.kaiming_uniform_(m.weight, nonlinearity=nonlinearity)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.BatchNorm2d):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+        elif hasattr(m, "reset_parameters"):
+            m.reset_parameters()
+        else:
+            weights_init(m, nonlinearity=nonlinearity)
+
+
+class Delta(Distribution):
+    """Point mass at ``loc`` (rsample returns loc)."""
+
+    has_rsample = True
+    arg_constraints = {"loc": constraints.real, "log_density": constraints.real}
+    support = constraints.real
+
+    def __init__(self, loc, log_density=0.0, validate_args=None):
+        self.loc, self.log_density = broadcast_all(loc, log_density)
+        batch_shape = torch.Size() if isinstance(loc, Number) else self.loc.size()
+        super().__init__(batch_shape, validate_args=validate_args)
+
+    @property
+    def mean(self):
+        return self.loc
+
+    @property
+    def variance(self):
+        return torch.zeros_like(self.loc)
+
+    def rsample(self, sample_shape=torch.Size()):
+        return self.loc.expand(list(sample_shape) + list(self.loc.shape))
+
+    def log_prob(self, x):
+        return (x == self.loc).type(x.dtype).log() + self.log_density
+
+
+class Annealer:
+    """Hyper-parameter annealing: linear / geometric / constant from ``initial_value`` to
+    ``final_value`` over ``n_steps_anneal`` calls after ``start_step``."""
+
+    def __init__(self, initial_value, final_value, n_steps_anneal, start_step=0, default=None, mode="geometric"):
+        if n_steps_anneal < 0:
+            n_steps_anneal *= -1
+            initial_value, final_value = final_value, initial_value
+        self.initial_value, self.final_value = initial_value, final_value
+        self.n_steps_anneal, self.start_step = n_steps_anneal, start_step
+        self.default = default if default is not None else self.initial_value
+        self.mode = mode.lower()
+        if self.mode == "linear":
+            self.factor = (self.final_value - self.initial_value) / self.n_steps_anneal
+        elif self.mode == "geometric":
+            self.factor = (self.final_value / self.initial_value) ** (1 / self.n_steps_anneal)
+        elif self.mode != "constant":
+            raise ValueError(f"Unkown mode : {mode}.")
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.n_training_calls = 0
+
+    def is_annealing(self, n_update_calls):
+        return self.mode != "constant" and n_update_calls < (self.n_steps_anneal + self.start_step)
+
+    def __call__(self, is_update=False, n_update_calls=None):
+        if is_update:
+            self.n_training_calls += 1
+        if n_update_calls is None:
+            n_update_calls = self.n_training_calls
+        if self.start_step > n_update_calls:
+            return self.default
+        k = n_update_calls - self.start_step
+        if self.is_annealing(n_update_calls):
+            if self.mode == "geometric":
+                return self.initial_value * self.factor ** k
+            return self.initial_value + self.factor * k
+        return self.final_value
+
+
+class GatherFromGpus(torch.autograd.Function):
+    """all_gather that keeps only the local gradient in backward (the reference's semantics:
+    remote tiles are constants for this rank)."""
+
+    @staticmethod
+    def forward(ctx, tensor):
+        ctx.rank = torch.distributed.get_rank()
+        gathered = [torch.zeros_like(tensor) for _ in range(torch.distributed.get_world_size())]
+        torch.distributed.all_gather(gathered, tensor.contiguous())
+        return tuple(gathered)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return grads[ctx.rank].clone()
+
+
+gather_from_gpus = GatherFromGpus.apply
+
+
+def get_optimizer(parameters, mode, **kwargs):
+    Optimizer = getattr(torch.optim, mode)
+    kwargs = dict(kwargs)
+    if "lr_factor" in kwargs:
+        kwargs["lr"] = kwargs["lr"] * kwargs.pop("lr_factor")
+    return Optimizer(parameters, **kwargs)
+
+
+def get_lr_scheduler(optimizer, scheduler_type, epochs=None, decay_factor=1000, k_steps=3, name=None, **kwargs):
+    if scheduler_type is None:
+        return None
+    if scheduler_type == "expdecay":
+        return torch.optim.lr_scheduler.ExponentialLR(optimizer, (1 / decay_factor) ** (1 / epochs))
+    if scheduler_type == "UniformMultiStepLR":
+        delta = epochs // (k_steps + 1)
+        return torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=[delta * i for i in range(1, k_steps + 1)],
+                                                    gamma=(1 / decay_factor) ** (1 / k_steps))
+    return getattr(torch.optim.lr_scheduler, scheduler_type)(optimizer, **kwargs)
+
+
+def append_optimizer_scheduler_(hparams_opt, hparams_sch, parameters, optimizers, schedulers, name=None):
+    params = [p for p in parameters if p.requires_grad]
+    optimizer = get_optimizer(params, hparams_opt.mode, **hparams_opt.kwargs)
+    optimizers.append(optimizer)
+    for mode in (hparams_sch.modes if hparams_sch is not None else []):
+        sch = get_lr_scheduler(optimizer, mode, name=name, **hparams_sch.kwargs.get(mode, {}))
+        if sch is not None:
+            schedulers.append(dict(scheduler=sch, name=name))
+    return optimizers, schedulers

@@ -109,7 +109,13 @@ class ClipCompressor(nn.Module):
         return (z_hat / self.scaling.exp()) - self.biasing
 
     def _exp_scale(self):
-        return self.scaling.detach().exp()
+        """exp(scaling) evaluated once in float32 on the CPU and cached: the symbols (hence the
+        bitstream) must not depend on which device's expf rounded it."""
+        key = (self.scaling._version, self.scaling.data_ptr(), str(self.scaling.device))
+        if getattr(self, "_es_cache", None) is None or self._es_cache[0] != key:
+            es = self.scaling.detach().float().cpu().exp().to(self.scaling.device)
+            self._es_cache = (key, es)
+        return self._es_cache[1]
 
     @torch.no_grad()
     def forward(self, X, is_compress=False):
@@ -122,7 +128,8 @@ class ClipCompressor(nn.Module):
             return self.entropy_bottleneck.compress(z, bias=self.biasing, exp_scale=self._exp_scale())
         from ..entropy_models import eb_rate_forward
 
-        z_hat, _, _ = eb_rate_forward(self.entropy_bottleneck, z, None, self.biasing, self.scaling, want_rates=False)
+        z_hat, _, _ = eb_rate_forward(self.entropy_bottleneck, z, None, self.biasing, self.scaling,
+                                      want_rates=False, exp_scale=self._exp_scale())
         return z_hat
 
     def compress(self, X):

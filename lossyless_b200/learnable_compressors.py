@@ -1,0 +1,263 @@
+"""``LearnableCompressor``: the rate-distortion model surface of the reference
+(lossyless/learnable_compressors.py:23-450) without PyTorch-Lightning (not installable here):
+same constructor argument (an ``hparams`` attribute dict), ``forward / step / loss /
+final_beta_labda / training_step / validation_step / test_step / configure_optimizers /
+get_specific_parameters / on_test_epoch_start / set_featurize_mode_``, same log keys.
+
+``fit`` is the thin replacement of ``Trainer.fit`` for this path: per batch one optimiser pass per
+entry of ``idcs_to_compressors`` ("main", then "coder"), gradient clipping, optional data-parallel
+gradient all-reduce (buckets only -- the encode path itself has no collective).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .architectures import get_Architecture
+from .distortions import get_distortion_estimator
+from .distributions import CondDist
+from .helpers import BASE_LOG, Annealer, NamespaceMap, OrderedSet, Timer, append_optimizer_scheduler_
+from .rates import get_rate_estimator
+
+__all__ = ["LearnableCompressor", "default_clip_hparams"]
+
+
+class LearnableCompressor(nn.Module):
+    """Main network for learning a neural compression."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        self.hparams = hparams if isinstance(hparams, NamespaceMap) else NamespaceMap(hparams)
+        self.global_step, self.current_epoch = 0, 0
+        self.logged = {}
+
+        self.p_ZlX = self.get_encoder()
+        self.rate_estimator = self.get_rate_estimator()
+        self.distortion_estimator = self.get_distortion_estimator()
+        if self.hparams.evaluation.featurizer.is_online:
+            raise NotImplementedError("the online evaluator (lossyless/predictors.py) is outside the hot path")
+
+        #! careful this is actually 1/beta from the paper
+        final_beta = self.final_beta_labda[0]
+        self.beta_annealer = Annealer(final_beta * 1e-5, final_beta,
+                                      n_steps_anneal=math.ceil(1 / 10 * self.hparams.data.max_steps),
+                                      mode=self.hparams.featurizer.loss.beta_anneal)
+        self.is_features = self.hparams.featurizer.is_features
+        self.out_shape = (self.hparams.encoder.z_dim,) if self.is_features else self.hparams.data.shape
+        self.stage = self.hparams.stage
+
+    # -- construction -------------------------------------------------------------------
+    def get_encoder(self):
+        cfg = self.hparams.encoder
+        return CondDist(self.hparams.data.shape, cfg.z_dim, family=cfg.fam,
+                        Architecture=get_Architecture(cfg.arch, **cfg.arch_kwargs), **cfg.fam_kwargs)
+
+    def get_rate_estimator(self):
+        cfg = self.hparams.rate
+        rate_estimator = get_rate_estimator(cfg.mode, p_ZlX=self.p_ZlX, **cfg.kwargs)
+        rate_estimator.make_pickable_()  # pickable before any process spawn
+        return rate_estimator
+
+    def get_distortion_estimator(self):
+        cfg = self.hparams.distortion
+        return get_distortion_estimator(cfg.mode, **cfg.kwargs)
+
+    # -- representation -----------------------------------------------------------------
+    def forward(self, x, is_compress=False, is_features=None, is_dist=False):
+        """Represent ``x``: codes / (de)quantised features, or the reconstruction."""
+        if is_features is None:
+            is_features = self.is_features
+        p_Zlx = self.p_ZlX(x)
+        z = p_Zlx.rsample()
+        if is_compress:
+            z_hat = self.rate_estimator.compress(z, self)
+        else:
+            z_hat, rates, r_logs, r_other = self.rate_estimator(z, p_Zlx, self)
+            if is_dist and "z_to_dist" in r_other:
+                z_hat = r_other["z_to_dist"]
+        if is_features:
+            return z_hat
+        return self.distortion_estimator.q_YlZ(z_hat)  # direct distortion only
+
+    def step(self, batch, is_rate_only=False):
+        x, targets = batch
+        with Timer() as encoder_timer:
+            p_Zlx = self.p_ZlX(x)  # batch shape [B], event shape [z_dim]
+        z = p_Zlx.rsample()
+        z_hat, rates, r_logs, r_other = self.rate_estimator(z, p_Zlx, self)
+
+        if "n_bits" in r_logs:
+            batch_size = x.size(0)
+            r_logs["encoder_time"] = encoder_timer.duration / batch_size
+            r_logs["sender_time"] = r_logs["encoder_time"] + r_logs["compress_time"]
+            if self.hparams.data.mode == "image":
+                _, __, height, width = x.shape
+                r_logs["bpp"] = r_logs["n_bits"] / (height * width)
+
+        if is_rate_only:
+            r_logs["rate"] = rates.mean() / math.log(BASE_LOG)
+            return rates, r_logs, r_other
+
+        z_to_dist = r_other.pop("z_to_dist") if "z_to_dist" in r_other else z_hat
+        _, aux_target = targets
+        distortions, d_logs, d_other = self.distortion_estimator(z_to_dist, aux_target, p_Zlx, self)
+        loss, logs, other = self.loss(rates, distortions)
+
+        logs.update(r_logs)
+        logs.update(d_logs)
+        logs.update(dict(zmin=z_hat.min(), zmax=z_hat.max(), zmean=z_hat.mean()))
+        other.update(r_other)
+        other.update(d_other)
+        other["X"] = x[0].detach().cpu()
+        other.update(dict(z=z.detach()))
+        return loss, logs, other
+
+    @property
+    def final_beta_labda(self):
+        cfg = self.hparams
+        labda = 1 / cfg.distortion.factor_beta
+        beta = cfg.featurizer.loss.beta * cfg.rate.factor_beta
+        return beta, labda
+
+    def loss(self, rates, distortions):
+        rates, distortions = rates.float(), distortions.float()
+        curr_beta = self.beta_annealer(n_update_calls=self.global_step)
+        final_beta, labda = self.final_beta_labda
+        loose_loss = (labda * distortions + final_beta * rates).mean().detach()
+        rate, distortion = rates.mean(0), distortions.mean(0)
+        # annealed beta drives the gradient, final beta the reported value
+        beta_rate = curr_beta * rate
+        beta_rate = beta_rate - beta_rate.detach() + (final_beta * rate.detach())
+        loss = labda * distortion + beta_rate
+        logs = dict(loose_loss=loose_loss / math.log(BASE_LOG), loss=loss / math.log(BASE_LOG),
+                    rate=rate / math.log(BASE_LOG), distortion=distortion / math.log(BASE_LOG), beta=curr_beta)
+        logs["ratedist"] = logs["rate"] + logs["distortion"]
+        return loss, logs, dict()
+
+    # -- Lightning-style hooks -----------------------------------------------------------
+    def log_dict(self, d, **kw):
+        self.logged.update({k: (float(v) if torch.is_tensor(v) else v) for k, v in d.items()})
+
+    def training_step(self, batch, batch_idx, optimizer_idx=0):
+        curr_step = self.idcs_to_compressors[optimizer_idx]
+        if curr_step == "main":
+            loss, logs, other = self.step(batch)
+            self._save = other
+        elif curr_step == "coder":
+            loss = self.rate_estimator.aux_loss()
+            logs = dict(coder_loss=loss)
+        else:
+            raise ValueError(f"Unkown curr_step={curr_step}.")
+        self.log_dict({f"train/{self.stage}/{k}": v for k, v in logs.items()}, sync_dist=True)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        loss, logs, _ = self.step(batch)
+        self.log_dict({f"val/{self.stage}/{k}": v for k, v in logs.items()}, on_epoch=True, on_step=False, sync_dist=True)
+        return loss
+
+    def test_step(self, batch, batch_idx):
+        is_communicate = self.stage == "comm"
+        loss, logs, _ = self.step(batch, is_rate_only=is_communicate)
+        self.log_dict({f"test/{self.stage}/{k}": v for k, v in logs.items()}, on_epoch=True, on_step=False, sync_dist=True)
+        return loss
+
+    def on_test_epoch_start(self):
+        self.rate_estimator.prepare_compressor_()
+
+    def get_specific_parameters(self, mode):
+        all_param = OrderedSet(self.parameters())
+        coder_param = OrderedSet(self.rate_estimator.aux_parameters())
+        rate_param = OrderedSet(self.rate_estimator.parameters()) - coder_param
+        online_param = OrderedSet([])
+        notrate_param = all_param - (coder_param | online_param | rate_param)
+        try:
+            return dict(all=all_param, coder=coder_param, rate=rate_param, online=online_param,
+                        main=notrate_param | rate_param, notrate=notrate_param)[mode]
+        except KeyError:
+            raise ValueError(f"Unkown parameter mode={mode}.") from None
+
+    def configure_optimizers(self):
+        self.idcs_to_compressors = {}
+        optimizers, schedulers = [], []
+        self.idcs_to_compressors[0] = "main"
+        append_optimizer_scheduler_(self.hparams.optimizer_feat, self.hparams.get("scheduler_feat"),
+                                    self.get_specific_parameters("main"), optimizers, schedulers, name="lr_featurizer")
+        coder_parameters = self.get_specific_parameters("coder")
+        if len(coder_parameters) > 0:
+            self.idcs_to_compressors[1] = "coder"
+            append_optimizer_scheduler_(self.hparams.optimizer_coder, self.hparams.get("scheduler_coder"),
+                                        coder_parameters, optimizers, schedulers, name="lr_coder")
+        return optimizers, schedulers
+
+    def set_featurize_mode_(self):
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.eval()
+        self.rate_estimator.make_pickable_()
+
+    # -- minimal trainer -----------------------------------------------------------------
+    def fit(self, batches, max_steps=None, grad_clip=3.0, process_group=None):
+        """Lightning-free ``Trainer.fit``: per batch, one pass per optimiser ("main" then "coder");
+        ``gradient_clip_val=3`` as config/main.yaml; with ``torch.distributed`` initialised the
+        trainable gradients are all-reduced (mean) in one flat bucket per pass."""
+        optimizers, schedulers = self.configure_optimizers()
+        is_dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self.train()
+        for batch_idx, batch in enumerate(batches):
+            if max_steps is not None and self.global_step >= max_steps:
+                break
+            for oi, opt in enumerate(optimizers):
+                opt.zero_grad(set_to_none=True)
+                loss = self.training_step(batch, batch_idx, optimizer_idx=oi)
+                loss.backward()
+                params = [p for g in opt.param_groups for p in g["params"] if p.grad is not None]
+                if is_dist and params:
+                    allreduce_mean_(params, process_group)
+                if grad_clip:
+                    torch.nn.utils.clip_grad_norm_(params, grad_clip)
+                opt.step()
+            self.global_step += 1
+        for s in schedulers:
+            s["scheduler"].step()
+        return self.logged
+
+
+def allreduce_mean_(params, group=None):
+    """DDP's job for this path: one flat bucket of the trainable gradients, averaged over ranks."""
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    torch.distributed.all_reduce(flat, group=group)
+    flat /= torch.distributed.get_world_size(group)
+    o = 0
+    for p in params:
+        n = p.grad.numel()
+        p.grad.copy_(flat[o:o + n].view_as(p.grad))
+        o += n
+
+
+def default_clip_hparams(distortion="lossy_Z", beta=5e-2, max_steps=1000, n_data=50000, clip_state_dict=None):
+    """hparams of the reference's CLIP bottleneck recipe (config/featurizer/bottleneck_clip_lossyZ.yaml,
+    bin/clip/clip_hub.sh) with ``rate=H_factorized`` and either the lossy-Z or the BINCE
+    (contrastive, config/distortion/BINCE.yaml) distortion."""
+    if distortion == "lossy_Z":
+        dist = dict(mode="lossy_Z", factor_beta=1, kwargs=dict(p_norm=1))
+    elif distortion == "BINCE":
+        dist = dict(mode="contrastive", factor_beta=0.003,
+                    kwargs=dict(is_train_temperature=True, temperature=0.01, effective_batch_size=n_data, is_project=True,
+                                is_cosine=True, project_kwargs=dict(mode="mlp", out_shape=0.5, in_shape=512)))
+    else:
+        raise ValueError(distortion)
+    return NamespaceMap(
+        stage="feat",
+        data=dict(shape=(3, 224, 224), mode="image", max_steps=max_steps, length=n_data),
+        encoder=dict(z_dim=512, fam="deterministic", fam_kwargs={}, arch="clip", arch_kwargs=dict(clip_state_dict=clip_state_dict)),
+        rate=dict(mode="H_factorized", factor_beta=1,
+                  kwargs=dict(z_dim=512, is_endToEnd=False, warmup_k_epoch=0,
+                              kwargs_ent_bottleneck=dict(init_scale=10, filters=[3, 3, 3, 3]))),
+        distortion=dist,
+        featurizer=dict(is_features=True, loss=dict(beta=beta, beta_anneal="linear")),
+        evaluation=dict(featurizer=dict(is_online=False)),
+        optimizer_feat=dict(mode="AdamW", kwargs=dict(lr=1e-3, weight_decay=3e-8)),
+        optimizer_coder=dict(mode="AdamW", kwargs=dict(lr=3e-4, weight_decay=1e-6)),
+        scheduler_feat=None, scheduler_coder=None,
+    )

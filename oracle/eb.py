@@ -62,6 +62,22 @@ def medians(eb):
     return eb["quantiles"][:, 0, 1].clone()
 
 
+class _LowerBound(torch.autograd.Function):
+    """compressai/ops/bound_ops.py LowerBound: max(x, bound); the gradient passes where
+    x >= bound or where it would increase x (grad < 0)."""
+
+    @staticmethod
+    def forward(ctx, x, bound):
+        b = torch.full_like(x, bound)
+        ctx.save_for_backward(x, b)
+        return torch.max(x, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, b = ctx.saved_tensors
+        return ((x >= b) | (g < 0)).type_as(g) * g, None
+
+
 def forward(eb, z_in, noise=None):
     """compressai EntropyBottleneck.forward on a [B,C] input (the reference's 2-D wrapper,
     lossyless/rates.py:55-62).  ``noise`` [B,C] in (-.5,.5) selects training mode (the
@@ -74,7 +90,7 @@ def forward(eb, z_in, noise=None):
         med = eb["quantiles"][:, :, 1:2]
         v = torch.round(x - med) + med
     lik = likelihood(eb, v)
-    lik = torch.clamp(lik, min=LIKELIHOOD_BOUND)
+    lik = _LowerBound.apply(lik, LIKELIHOOD_BOUND)
     return v[:, 0, :].t().contiguous(), lik[:, 0, :].t().contiguous()
 
 
