@@ -208,9 +208,11 @@ int ll_attention(const void *qkv, void *out, int64_t batch, int S, int H, int dt
 
 /* Stand-alone GEMM entry (tests, micro-benchmarks):  D[M,N] = act(A[M,K] @ W[N,K]^T + bias)
  * (+ residual), A/W/D/residual in `dtype`, bias float32 or NULL, act 0 = none,
- * 1 = QuickGELU x*sigmoid(1.702x).  K % 64 == 0, N % 128 == 0. */
+ * 1 = QuickGELU x*sigmoid(1.702x).  K % 64 == 0, N % 64 == 0. */
 int ll_gemm(const void *A, const void *W, const float *bias, const void *residual, void *D,
             int64_t M, int N, int K, int dtype, int act, ll_stream_t stream);
+/* Force the GEMM's tile width (64/128/192/256; 0 = automatic wave-aware choice). Tests, tuning. */
+int ll_gemm_set_tile_n(int bn);
 
 /* ----------------------------------------------------------- device: distortions */
 

@@ -34,8 +34,9 @@ template <int BN>
 struct GemmShape {
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
-    static constexpr int kTmemCols = 2 * BN;  // two accumulator buffers
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
+    static constexpr int kAccStride = (BN == 192) ? 256 : BN;  // TMEM columns between the two accumulators
+    static constexpr int kTmemCols = 2 * kAccStride;           // power of two >= 32
     static constexpr int kGroups = BN / kEpiCols;       // 64-column epilogue groups per tile
     static constexpr int kStagingBytes = 4 * 2 * kEpiBufBytes;  // 4 epilogue warps x 2 buffers
     static constexpr int kBarBytes = (2 * kStages + 4 + 8) * 8 + 16;
@@ -177,7 +178,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint32_t acc_phase = (it >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
+                const uint32_t tmem_d = tmem_base + acc * S::kAccStride;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
@@ -201,6 +202,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint8_t *buf0 = sm_epi + quarter * 2 * kEpiBufBytes;
         uint64_t *rbar = res_bar + quarter * 2;
         uint32_t rphase[2] = {0, 0};
+        uint32_t gc = 0;  // running group counter: staging buffer = gc & 1 (tiles may have an odd group count)
         const int swz = lane & 7;  // 128 B swizzle: 16 B chunk j of row r lives at chunk j ^ (r & 7)
         uint8_t *my_row0 = buf0 + lane * 128;
         int it = 0;
@@ -211,16 +213,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int n0 = (tile % num_n) * BN;
             if (has_residual && lane == 0) {
                 // first residual group of this tile, fetched while the MMAs are still running
+                const int b = gc & 1;
                 ptx::tma_store_wait_read<0>();
-                ptx::mbar_expect_tx(&rbar[0], kEpiBufBytes);
-                ptx::tma_load_2d(buf0, &tmap_r, &rbar[0], n0, m0);
+                ptx::mbar_expect_tx(&rbar[b], kEpiBufBytes);
+                ptx::tma_load_2d(buf0 + b * kEpiBufBytes, &tmap_r, &rbar[b], n0, m0);
             }
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * S::kAccStride;
 #pragma unroll 1
-            for (int g = 0; g < S::kGroups; ++g) {
-                const int b = g & 1;
+            for (int g = 0; g < S::kGroups; ++g, ++gc) {
+                const int b = gc & 1;
                 uint8_t *my_row = my_row0 + b * kEpiBufBytes;
                 if (lane == 0) {
                     if (has_residual) {
@@ -349,24 +352,49 @@ static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
     return LL_OK;
 }
 
-// Tile-N choice: 256 halves the A re-reads and the number of MMA instructions, 128 gives finer
-// tiles when there are too few to balance the persistent grid.
+// Tile-N choice.  The persistent grid runs ceil(tiles / #SMs) rounds of one BN-wide tile each, so
+// the cost of a candidate is rounds * BN (the partially filled last round is what hurts: N = 768
+// with BN = 256 at M = 12 800 is 300 tiles = 3 rounds for 2.03 rounds of work).  Narrower tiles
+// re-read A more often, hence the small penalty.
 static int pick_bn(int64_t M, int N)
 {
-    if (N % 256 != 0) return 128;
-    const int64_t tiles256 = ((M + kBM - 1) / kBM) * (N / 256);
-    return tiles256 >= 2 * (int64_t)num_sms() ? 256 : 128;
+    const int64_t mt = (M + kBM - 1) / kBM;
+    const int sms = num_sms();
+    int best = 0;
+    double best_cost = 0.0;
+    const int cands[4] = {256, 192, 128, 64};
+    for (int bn : cands) {
+        if (N % bn != 0) continue;
+        const int64_t tiles = mt * (N / bn);
+        const int64_t rounds = (tiles + sms - 1) / sms;
+        const double penalty = bn == 256 ? 1.0 : bn == 192 ? 1.02 : bn == 128 ? 1.06 : 1.2;
+        const double cost = (double)rounds * bn * penalty;
+        if (best == 0 || cost < best_cost) best = bn, best_cost = cost;
+    }
+    return best;
+}
+
+static int g_force_bn = 0;  // test / tuning override (ll_gemm_set_tile_n)
+
+template <typename T>
+static int launch_bn(int bn, const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr,
+                     const float *bias, int has_residual, int64_t M, int N, int K, int act, cudaStream_t stream)
+{
+    switch (bn) {
+        case 256: return launch_impl<T, 256>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+        case 192: return launch_impl<T, 192>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+        case 128: return launch_impl<T, 128>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+        case 64: return launch_impl<T, 64>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+    }
+    return fail(LL_ERR_INVALID, "gemm: unsupported tile N %d", bn);
 }
 
 int gemm_launch_tmaps(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr, int bn,
                       const float *bias, int has_residual, int64_t M, int N, int K, int dtype, int act,
                       cudaStream_t stream)
 {
-    if (dtype == LL_F16)
-        return bn == 256 ? launch_impl<__half, 256>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream)
-                         : launch_impl<__half, 128>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
-    return bn == 256 ? launch_impl<__nv_bfloat16, 256>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream)
-                     : launch_impl<__nv_bfloat16, 128>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+    if (dtype == LL_F16) return launch_bn<__half>(bn, ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+    return launch_bn<__nv_bfloat16>(bn, ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
 }
 
 int gemm_pick_bn(int64_t M, int N) { return pick_bn(M, N); }
@@ -376,11 +404,11 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
 {
     LL_REQUIRE(A && W && D, "gemm: null pointer");
     LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "gemm: dtype must be LL_F16 or LL_BF16");
-    LL_REQUIRE(M > 0 && N > 0 && K > 0 && K % kBK == 0 && N % 128 == 0, "gemm: need K %% 64 == 0 and N %% 128 == 0 (M=%lld N=%d K=%d)", (long long)M, N, K);
+    LL_REQUIRE(M > 0 && N > 0 && K > 0 && K % kBK == 0 && N % 64 == 0, "gemm: need K %% 64 == 0 and N %% 64 == 0 (M=%lld N=%d K=%d)", (long long)M, N, K);
     LL_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0 && (!residual || (reinterpret_cast<uintptr_t>(residual) & 15) == 0) &&
                    (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
                "gemm: D / residual / bias must be 16-byte aligned");
-    const int bn = pick_bn(M, N);
+    const int bn = (g_force_bn && N % g_force_bn == 0) ? g_force_bn : pick_bn(M, N);
     CUtensorMap ta, tw, td, tr;
     int rc = make_tmap_2d(&ta, A, dtype, M, K, kBM);
     if (rc != LL_OK) return rc;
@@ -397,6 +425,13 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
 }
 
 }  // namespace ll
+
+extern "C" int ll_gemm_set_tile_n(int bn)
+{
+    if (bn != 0 && bn != 64 && bn != 128 && bn != 192 && bn != 256) return ll::fail(LL_ERR_INVALID, "gemm_set_tile_n: %d not in {0,64,128,192,256}", bn);
+    ll::g_force_bn = bn;
+    return LL_OK;
+}
 
 extern "C" int ll_gemm(const void *A, const void *W, const float *bias, const void *residual, void *D, int64_t M,
                        int N, int K, int dtype, int act, ll_stream_t stream)

@@ -73,3 +73,25 @@ def test_gemm_repeatable_and_back_to_back(cuda_device):
     first = _gemm(A, W)
     for _ in range(20):
         assert torch.equal(_gemm(A, W), first)
+
+
+@pytest.mark.parametrize("bn", [64, 128, 192, 256])
+@pytest.mark.parametrize("use_res", [False, True])
+def test_gemm_every_tile_width(cuda_device, bn, use_res):
+    """each tile-N instantiation (odd epilogue group counts included) with and without the TMA-fed
+    residual, several tiles per CTA so the staging buffers / barrier phases wrap."""
+    from lossyless_b200 import _native as nat
+
+    g = torch.Generator(device=cuda_device).manual_seed(bn)
+    M, Nn, K = 128 * 148 * 2 + 77, 768, 768
+    A = (torch.randn(M, K, generator=g, device=cuda_device) * 0.5).half()
+    W = (torch.randn(Nn, K, generator=g, device=cuda_device) * K ** -0.5).half()
+    bias = torch.randn(Nn, generator=g, device=cuda_device)
+    res = torch.randn(M, Nn, generator=g, device=cuda_device).half() if use_res else None
+    ref = _ref(A, W, bias, res, 0)
+    nat.call("ll_gemm_set_tile_n", bn)
+    try:
+        D = _gemm(A, W, bias, res, 0)
+    finally:
+        nat.call("ll_gemm_set_tile_n", 0)
+    assert (D.float() - ref).abs().max().item() < 6e-3 * max(1.0, ref.abs().max().item())

@@ -1,0 +1,142 @@
+"""GPU: the rate-distortion training step through the reference's module surface
+(LearnableCompressor.step / loss / fit) against the oracle on identical inputs and noise, and
+the CPU-plumbing configuration (banana, z_dim = 2) with its known answer n_bits == 64."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import eb as oeb
+from oracle import losses as olosses
+
+pytestmark = pytest.mark.gpu
+
+
+def _eb_state(rate_estimator):
+    sd = {f"entropy_bottleneck.{k}": v.detach().cpu() for k, v in rate_estimator.entropy_bottleneck.state_dict().items()}
+    return oeb.split_state_dict(sd)
+
+
+@pytest.mark.parametrize("distortion", ["lossy_Z", "BINCE"])
+def test_clip_step_matches_oracle(cuda_device, distortion):
+    """config 3 (frozen CLIP encoder, H_factorized, beta = 0.05, linear anneal): rate, distortion and
+    loss of one training step within 1e-4 relative of the oracle fed with the same z and noise."""
+    from lossyless_b200.learnable_compressors import LearnableCompressor, default_clip_hparams
+
+    B = 16
+    hp = default_clip_hparams(distortion=distortion, beta=5e-2, max_steps=100, n_data=5000)
+    model = LearnableCompressor(hp).to(cuda_device).train()
+    model.global_step = 3
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(B, 3, 224, 224, generator=gen).to(cuda_device)
+    x_pos = torch.randn(B, 3, 224, 224, generator=gen).to(cuda_device)
+    # make the bottleneck non-trivial
+    with torch.no_grad():
+        model.rate_estimator.scaling.add_(torch.randn(512, generator=gen).to(cuda_device) * 0.1 + 1.0)
+        model.rate_estimator.biasing.add_(torch.randn(512, generator=gen).to(cuda_device) * 0.1)
+
+    torch.manual_seed(123)
+    loss, logs, other = model.step((x, (None, x_pos)))
+    loss.backward()
+
+    # replay the noise draws in the same order: forward_help(z) then forward_help(z.detach()) [is_endToEnd=False];
+    # BINCE additionally encodes x_pos through the model (two more draws) before the losses
+    torch.manual_seed(123)
+    noises = [torch.empty(B, 512, device=cuda_device).uniform_(-0.5, 0.5).cpu() for _ in range(4)]
+    z = other["z"].float().cpu()
+    re = model.rate_estimator
+    ebo = _eb_state(re)
+    b, s = re.biasing.detach().cpu(), re.scaling.detach().cpu()
+    zh_in, _ = oeb.forward(ebo, oeb.process_z_in(z, b, s), noises[0])
+    z_hat = oeb.process_z_out(zh_in, b, s)
+    _, q = oeb.forward(ebo, oeb.process_z_in(z, b, s), noises[1])
+    rates = -torch.log(q).sum(-1)
+    if distortion == "lossy_Z":
+        dist = olosses.lossy_z_distortion(z_hat, z)
+    else:
+        with torch.no_grad():
+            z_pos = model.p_ZlX(x_pos).rsample().float().cpu()
+        zp_in, _ = oeb.forward(ebo, oeb.process_z_in(z_pos, b, s), noises[2])
+        z_pos_hat = oeb.process_z_out(zp_in, b, s)
+        lin1, lin2 = model.distortion_estimator.projector.module[0], model.distortion_estimator.projector.module[-1]
+        proj = dict(w1=lin1.weight.detach().cpu(), b1=lin1.bias.detach().cpu(), w2=lin2.weight.detach().cpu(), b2=lin2.bias.detach().cpu())
+        dist, _ = olosses.contrastive_distortion(z_hat, z_pos_hat, proj, temperature=0.01,
+                                                 logit_scale=model.distortion_estimator.logit_scale.detach().cpu(),
+                                                 effective_batch_size=5000)
+    final_beta, labda = model.final_beta_labda
+    ann = olosses.Annealer(final_beta * 1e-5, final_beta, math.ceil(100 / 10), mode="linear")
+    loss_o, logs_o = olosses.rd_loss(rates, dist, ann(3), final_beta, labda)
+    assert float(logs["rate"]) == pytest.approx(float(logs_o["rate"]), rel=1e-4)
+    assert float(logs["distortion"]) == pytest.approx(float(logs_o["distortion"]), rel=1e-4)
+    assert float(loss) == pytest.approx(float(loss_o), rel=1e-4)
+    assert float(logs["beta"]) == pytest.approx(ann(3))
+    # is_endToEnd=False + frozen encoder: only the coder / affine / projector parameters get gradients
+    assert re.entropy_bottleneck._matrix0.grad is not None and re.scaling.grad is not None
+    assert all(p.grad is None for p in model.p_ZlX.parameters())
+
+
+def test_clip_fit_and_real_rate(cuda_device):
+    """a few optimiser passes ("main" + "coder") run and lower the loss; the test-time path builds the
+    tables, codes the batch for real and logs the reference's keys."""
+    from lossyless_b200.learnable_compressors import LearnableCompressor, default_clip_hparams
+
+    hp = default_clip_hparams(distortion="lossy_Z", beta=5e-2, max_steps=40, n_data=5000)
+    model = LearnableCompressor(hp).to(cuda_device)
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(32, 3, 224, 224, generator=gen).to(cuda_device)
+    batch = (x, (None, x))
+    opts, _ = model.configure_optimizers()
+    assert model.idcs_to_compressors == {0: "main", 1: "coder"}
+    assert len(model.get_specific_parameters("coder")) == 1  # the quantiles
+    model.train()
+    first = float(model.step(batch)[0])
+    logged = model.fit([batch] * 30)
+    last = logged["train/feat/loss"] * math.log(2)
+    assert last < first, (first, last)
+    assert "train/feat/coder_loss" in logged and "train/feat/H_q_Z" in logged
+    model.eval()
+    model.on_test_epoch_start()
+    with torch.no_grad():
+        model.test_step(batch, 0)
+    for k in ("n_bits", "compress_time", "receiver_time", "encoder_time", "sender_time", "bpp", "rate", "H_q_Z"):
+        assert f"test/feat/{k}" in model.logged, k
+    assert model.logged["test/feat/n_bits"] >= 64
+    # the real rate cannot beat the model's own entropy estimate by much, nor exceed it wildly
+    assert model.logged["test/feat/n_bits"] > 0.8 * model.logged["test/feat/H_q_Z"]
+
+
+def test_banana_plumbing_config(cuda_device):
+    """BASELINE config 1 shape (z_dim = 2 MLP encoder, H_factorized C = 2, direct distortion): trains,
+    and every coded message is exactly the 8-byte rANS flush: n_bits == 64.0
+    (results/exp_banana_viz_VIC/summarized_metrics_featurizer.csv)."""
+    from lossyless_b200.helpers import NamespaceMap
+    from lossyless_b200.learnable_compressors import LearnableCompressor
+
+    hp = NamespaceMap(
+        stage="feat", data=dict(shape=(2,), mode="distribution", max_steps=50, length=1024000),
+        encoder=dict(z_dim=2, fam="deterministic", fam_kwargs={}, arch="mlp", arch_kwargs=dict(hid_dim=64, n_hid_layers=2, activation="Softplus")),
+        rate=dict(mode="H_factorized", factor_beta=1, kwargs=dict(z_dim=2, kwargs_ent_bottleneck=dict(init_scale=10, filters=[3, 3, 3, 3]))),
+        distortion=dict(mode="direct", factor_beta=1, kwargs=dict(z_dim=2, y_shape=(2,), arch="mlp", arch_kwargs=dict(hid_dim=64, n_hid_layers=2, activation="Softplus"))),
+        featurizer=dict(is_features=True, loss=dict(beta=0.07, beta_anneal="constant")),
+        evaluation=dict(featurizer=dict(is_online=False)),
+        optimizer_feat=dict(mode="Adam", kwargs=dict(lr=3e-3)), optimizer_coder=dict(mode="Adam", kwargs=dict(lr=3e-3)),
+        scheduler_feat=None, scheduler_coder=None)
+    model = LearnableCompressor(hp).to(cuda_device)
+    gen = torch.Generator().manual_seed(0)
+    x = (torch.randn(1024, 2, generator=gen) * torch.tensor([3.0, 1.0])).to(cuda_device)
+    batch = (x, (None, x))
+    model.train()
+    first = float(model.step(batch)[0])
+    logged = model.fit([batch] * 60)
+    assert logged["train/feat/loss"] * math.log(2) < first
+    model.eval()
+    model.on_test_epoch_start()
+    with torch.no_grad():
+        model.test_step(batch, 0)
+    assert model.logged["test/feat/n_bits"] == 64.0
+    z_hat = model(x)
+    assert z_hat.shape == (1024, 2)
+    strings = model(x, is_compress=True)
+    assert len(strings) == 1 and len(strings[0]) == 1024 and all(len(s) == 8 for s in strings[0])
