@@ -195,16 +195,22 @@ class VisionTransformer(nn.Module):
         return ms.value, fl.value, n.value
 
     @torch.no_grad()
-    def forward(self, x):
+    def forward(self, x, out=None):
         """x [B,3,R,R] (fp16 / bf16 / fp32, cuda, CLIP-normalised) -> z [B, output_dim] in the
-        model's 16-bit dtype (the reference's fp16 ``self.clip(X)``)."""
+        model's 16-bit dtype (the reference's fp16 ``self.clip(X)``).  ``out`` optionally receives
+        the result (a contiguous [B, output_dim] view of a larger buffer, for pipelined callers)."""
         N.require_cuda(x, "x")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.input_resolution or x.shape[3] != self.input_resolution:
             raise ValueError(f"expected [B,3,{self.input_resolution},{self.input_resolution}] images, got {tuple(x.shape)}")
         nat = self._native or self._build_native()
         x = x.contiguous()
         B = x.shape[0]
-        z = torch.empty((B, self.output_dim), dtype=nat["dtype"], device=x.device)
+        if out is not None:
+            if out.shape != (B, self.output_dim) or out.dtype != nat["dtype"] or not out.is_contiguous():
+                raise ValueError("out must be a contiguous [B, output_dim] tensor of the model dtype")
+            z = out
+        else:
+            z = torch.empty((B, self.output_dim), dtype=nat["dtype"], device=x.device)
         if B == 0:
             return z
         need = int(N.load().ll_vit_workspace_bytes(nat["handle"], B))

@@ -169,20 +169,53 @@ class ClipCompressor(nn.Module):
             z, bias=self.biasing, exp_scale=self._exp_scale(), mode=mode)
         return packed, offsets, lens
 
-    def compress_batch_to_host(self, X_host, out_host=None):
-        """One step of the encode hot path with HOST buffers: pinned-host images ->
-        H2D -> ViT -> quantise + rANS -> container records -> D2H.  Returns
-        (records: uint8 numpy view of the batch's ``>I len + bytes`` records, n_images)."""
-        X = X_host.to(self.device, non_blocking=True)
-        if X.dtype == torch.float32:
-            X = X.half()
-        packed, offsets, _ = self._compress_records(X, mode=1)
+    def compress_batch_to_host(self, X_host, out_host=None, sub_batch=256):
+        """One step of the encode hot path with HOST buffers: (pinned) host images -> H2D -> ViT ->
+        quantise + rANS -> container records -> D2H.  The batch is walked in sub-batches whose H2D
+        copies run on a side stream, double-buffered against the ViT of the previous sub-batch, so
+        PCIe and the tensor cores overlap.  Returns (records: uint8 host view holding the batch's
+        ``>I len + bytes`` records, n_images, the pinned output buffer for reuse)."""
+        dev = torch.device(self.device)
+        B = X_host.shape[0]
+        if X_host.is_cuda:
+            X = X_host.half() if X_host.dtype == torch.float32 else X_host
+            packed, offsets, _ = self._compress_records(X, mode=1)
+        else:
+            pipe = self._h2d_pipe(dev, X_host, sub_batch)
+            main = torch.cuda.current_stream(dev)
+            z = torch.empty((B, self.z_dim), dtype=torch.float16, device=dev)
+            for k, i0 in enumerate(range(0, B, sub_batch)):
+                i1 = min(B, i0 + sub_batch)
+                slot = k % 2
+                with torch.cuda.stream(pipe["stream"]):
+                    if pipe["consumed"][slot] is not None:
+                        pipe["stream"].wait_event(pipe["consumed"][slot])  # ViT of sub-batch k-2 done with the slot
+                    pipe["buf"][slot][: i1 - i0].copy_(X_host[i0:i1], non_blocking=True)
+                    pipe["ready"][slot].record(pipe["stream"])
+                main.wait_event(pipe["ready"][slot])
+                self.clip(pipe["buf"][slot][: i1 - i0], out=z[i0:i1])
+                ev = torch.cuda.Event()
+                ev.record(main)
+                pipe["consumed"][slot] = ev
+            packed, offsets, _, _ = self.entropy_bottleneck.compress_to_device(
+                z, bias=self.biasing, exp_scale=self._exp_scale(), mode=1)
         total = int(offsets[-1].item())  # one 8-byte D2H: size of this batch's records
         if out_host is None or out_host.numel() < total:
             out_host = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
         out_host[:total].copy_(packed[:total], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return out_host[:total], X.shape[0], out_host
+        torch.cuda.current_stream(dev).synchronize()
+        return out_host[:total], B, out_host
+
+    def _h2d_pipe(self, dev, X_host, sub_batch):
+        """Two device staging slots + a copy stream, created once per (dtype, sub_batch)."""
+        key = (str(dev), X_host.dtype, sub_batch, tuple(X_host.shape[1:]))
+        pipe = getattr(self, "_pipe", None)
+        if pipe is None or pipe["key"] != key:
+            pipe = dict(key=key, stream=torch.cuda.Stream(dev),
+                        buf=[torch.empty((sub_batch,) + tuple(X_host.shape[1:]), dtype=X_host.dtype, device=dev) for _ in range(2)],
+                        ready=[torch.cuda.Event(), torch.cuda.Event()], consumed=[None, None])
+            self._pipe = pipe
+        return pipe
 
     def compress_dataset(self, dataset, file, label_file=None,
                          kwargs_dataloader=dict(batch_size=128, num_workers=16), is_info=True):

@@ -42,3 +42,43 @@ for name, M, Nn, K, act, res in shapes:
     tot_fl += fl * mult
     print(f"{name:6s} M={M:6d} N={Nn:5d} K={K:5d}  {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  (x{mult})")
 print(f"per pass of {n_img} images: GEMM {tot_ms:.3f} ms, {tot_fl / tot_ms / 1e9:.1f} TFLOP/s, {n_img / tot_ms * 1e3:.0f} img/s GEMM-only")
+
+# ---- the encoder's non-GEMM kernels and the codec at the same pass size
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+M = n_img * 50
+qkv = torch.randn(M, 2304, device=dev).half()
+o = torch.empty(M, 768, device=dev).half()
+us = timeit(lambda: N.call("ll_attention", N.ptr(qkv), N.ptr(o), n_img, 50, 12, 1, N.stream()))
+print(f"attention  B={n_img}: {us:8.1f} us  ({(qkv.numel() + o.numel()) * 2 / us / 1e3:.0f} GB/s)  (x12)")
+x = torch.randn(M, 768, device=dev).half()
+h = torch.empty_like(x)
+g = torch.ones(768, device=dev)
+b = torch.zeros(768, device=dev)
+us_ln = timeit(lambda: N.call("ll_layernorm", N.ptr(x), M, 768, N.ptr(g), N.ptr(b), N.ptr(h), 1, N.stream()))
+print(f"layernorm  rows={M}: {us_ln:8.1f} us  ({x.numel() * 4 / us_ln / 1e3:.0f} GB/s)  (x24)")
+
+import warnings
+warnings.filterwarnings("ignore")
+import hubconf
+comp, _ = hubconf.clip_compressor_b005(device="cuda")
+for rows in (256, 1024, 4096):
+    z = (torch.randn(rows, 512, device=dev) * 1.0).half()
+    us_e = timeit(lambda: comp.entropy_bottleneck.compress_to_device(z, comp.biasing, comp._exp_scale(), mode=1), reps=10)
+    zs = (torch.randn(rows, 512, device=dev) * 0.45).half()
+    us_s = timeit(lambda: comp.entropy_bottleneck.compress_to_device(zs, comp.biasing, comp._exp_scale(), mode=1), reps=10)
+    print(f"eb+rans encode+pack rows={rows}: {us_e:8.1f} us (z std 1.0)   {us_s:8.1f} us (z std 0.45)")
+X = torch.randn(n_img, 3, 224, 224, device=dev).half()
+us_v = timeit(lambda: comp.clip(X), reps=10)
+print(f"vit forward B={n_img}: {us_v:8.1f} us -> {n_img / us_v * 1e6:.0f} img/s")
