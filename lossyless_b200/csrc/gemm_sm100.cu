@@ -34,12 +34,12 @@ template <int BN>
 struct GemmShape {
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
+    static constexpr int kStages = (BN == 256) ? 3 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
     static constexpr int kAccStride = (BN == 192) ? 256 : BN;  // TMEM columns between the two accumulators
     static constexpr int kTmemCols = 2 * kAccStride;           // power of two >= 32
     static constexpr int kGroups = BN / kEpiCols;       // 64-column epilogue groups per tile
-    static constexpr int kStagingBytes = 4 * 2 * kEpiBufBytes;  // 4 epilogue warps x 2 buffers
-    static constexpr int kBarBytes = (2 * kStages + 4 + 8) * 8 + 16;
+    static constexpr int kStagingBytes = 4 * kGroups * kEpiBufBytes;  // 4 epilogue warps x one buffer per group
+    static constexpr int kBarBytes = (2 * kStages + 4 + 4 * kGroups) * 8 + 16;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +1024: alignment
 };
 
@@ -115,8 +115,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t *empty_bar = full_bar + S::kStages;
     uint64_t *tfull_bar = empty_bar + S::kStages;  // [2] accumulator ready for the epilogue
     uint64_t *tempty_bar = tfull_bar + 2;          // [2] accumulator drained
-    uint64_t *res_bar = tempty_bar + 2;            // [4 warps][2] residual tile landed in the staging buffer
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 8);
+    uint64_t *res_bar = tempty_bar + 2;            // [4 warps][kGroups] residual tile landed in the staging buffer
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 4 * S::kGroups);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,7 +126,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         ptx::prefetch_tmap(&tmap_w);
         ptx::prefetch_tmap(&tmap_d);
         if (has_residual) ptx::prefetch_tmap(&tmap_r);
-        for (int i = 0; i < 8; ++i) ptx::mbar_init(&res_bar[i], 1);
+        for (int i = 0; i < 4 * S::kGroups; ++i) ptx::mbar_init(&res_bar[i], 1);
         for (int i = 0; i < S::kStages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], 1);
@@ -198,12 +198,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __syncwarp();
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5)
+        // One 32-row x 64-column staging buffer per column group and warp.  With a residual, all of
+        // the tile's residual groups are TMA-loaded into them as soon as the previous tile's stores
+        // have drained -- i.e. while the MMAs of this tile are still running -- and the results
+        // overwrite them in place before the TMA store.
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter + 32)
-        uint8_t *buf0 = sm_epi + quarter * 2 * kEpiBufBytes;
-        uint64_t *rbar = res_bar + quarter * 2;
-        uint32_t rphase[2] = {0, 0};
-        uint32_t gc = 0;  // running group counter: staging buffer = gc & 1 (tiles may have an odd group count)
-        const int swz = lane & 7;  // 128 B swizzle: 16 B chunk j of row r lives at chunk j ^ (r & 7)
+        uint8_t *buf0 = sm_epi + quarter * S::kGroups * kEpiBufBytes;
+        uint64_t *rbar = res_bar + quarter * S::kGroups;
+        uint32_t rphase = 0;           // all of a tile's residual barriers flip together
+        const int swz = lane & 7;      // 128 B swizzle: 16 B chunk j of row r lives at chunk j ^ (r & 7)
         uint8_t *my_row0 = buf0 + lane * 128;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -212,34 +215,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int m0 = (tile / num_n) * kBM + quarter * 32;
             const int n0 = (tile % num_n) * BN;
             if (has_residual && lane == 0) {
-                // first residual group of this tile, fetched while the MMAs are still running
-                const int b = gc & 1;
-                ptx::tma_store_wait_read<0>();
-                ptx::mbar_expect_tx(&rbar[b], kEpiBufBytes);
-                ptx::tma_load_2d(buf0 + b * kEpiBufBytes, &tmap_r, &rbar[b], n0, m0);
+                ptx::tma_store_wait_read<0>();  // previous tile's stores no longer read the buffers
+#pragma unroll
+                for (int g = 0; g < S::kGroups; ++g) {
+                    ptx::mbar_expect_tx(&rbar[g], kEpiBufBytes);
+                    ptx::tma_load_2d(buf0 + g * kEpiBufBytes, &tmap_r, &rbar[g], n0 + g * kEpiCols, m0);
+                }
             }
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * S::kAccStride;
 #pragma unroll 1
-            for (int g = 0; g < S::kGroups; ++g, ++gc) {
-                const int b = gc & 1;
-                uint8_t *my_row = my_row0 + b * kEpiBufBytes;
-                if (lane == 0) {
-                    if (has_residual) {
-                        if (g + 1 < S::kGroups) {
-                            // buffer b^1 was last read by the store of group g-1: wait, then prefetch
-                            ptx::tma_store_wait_read<0>();
-                            ptx::mbar_expect_tx(&rbar[b ^ 1], kEpiBufBytes);
-                            ptx::tma_load_2d(buf0 + (b ^ 1) * kEpiBufBytes, &tmap_r, &rbar[b ^ 1], n0 + (g + 1) * kEpiCols, m0);
-                        }
-                    } else {
-                        ptx::tma_store_wait_read<1>();  // the store that last read buffer b (group g-2) is done
-                    }
-                }
+            for (int g = 0; g < S::kGroups; ++g) {
+                uint8_t *my_row = my_row0 + g * kEpiBufBytes;
                 uint32_t r0[32], r1[32];
                 ptx::tmem_ld_32x32(taddr + g * kEpiCols, r0);
                 ptx::tmem_ld_32x32(taddr + g * kEpiCols + 32, r1);
+                if (!has_residual && lane == 0) {
+                    // buffer g was last read by the previous tile's store of group g: at most the
+                    // kGroups-1 younger stores may still be pending
+                    ptx::tma_store_wait_read<S::kGroups - 1>();
+                }
                 ptx::tmem_ld_wait();
                 if (g == S::kGroups - 1) {
                     // accumulator fully read: hand the TMEM buffer back to the MMA warp early
@@ -248,10 +244,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
                 }
                 if (has_residual) {
-                    ptx::mbar_wait(&rbar[b], rphase[b]);
-                    rphase[b] ^= 1;
+                    ptx::mbar_wait(&rbar[g], rphase);
                 } else {
-                    __syncwarp();  // lane 0's wait_group.read above orders the overwrite of buffer b
+                    __syncwarp();  // orders lane 0's wait_group.read before the overwrite of buffer g
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -281,10 +276,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    ptx::tma_store_2d(&tmap_d, buf0 + b * kEpiBufBytes, n0 + g * kEpiCols, m0);
+                    ptx::tma_store_2d(&tmap_d, buf0 + g * kEpiBufBytes, n0 + g * kEpiCols, m0);
                     ptx::tma_store_commit();
                 }
             }
+            rphase ^= 1;
         }
         if (lane == 0) ptx::tma_store_wait_all();  // global writes complete before the CTA exits
         __syncwarp();

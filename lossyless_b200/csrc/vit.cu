@@ -190,13 +190,19 @@ attention_kernel(const T *__restrict__ qkv, T *__restrict__ out, int S, int H, f
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const T *base = qkv + (int64_t)b * S * 3 * W + h * kHeadDim;
 
-    // stage Q, K, V (rows >= S zero-filled)
+    // stage Q, K, V with 16-byte cp.async (all loads in flight at once); rows >= S zero-filled
     for (int i = tid; i < 3 * kAttRows * 8; i += 128) {
         const int m = i / (kAttRows * 8), row = (i / 8) % kAttRows, chunk = i % 8;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (row < S) v = *reinterpret_cast<const uint4 *>(base + (int64_t)row * 3 * W + m * W + chunk * 8);
-        *reinterpret_cast<uint4 *>(&sm[m][att_off(row, chunk)]) = v;
+        uint8_t *dst = &sm[m][att_off(row, chunk)];
+        if (row < S) {
+            const T *src = base + (int64_t)row * 3 * W + m * W + chunk * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(dst)), "l"(src) : "memory");
+        } else {
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+        }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const uint32_t sq = ptx::smem_u32(sm[0]), sk = ptx::smem_u32(sm[1]), sv = ptx::smem_u32(sm[2]);
