@@ -213,6 +213,8 @@ int ll_gemm(const void *A, const void *W, const float *bias, const void *residua
             int64_t M, int N, int K, int dtype, int act, ll_stream_t stream);
 /* Force the GEMM's tile width (64/128/192/256; 0 = automatic wave-aware choice). Tests, tuning. */
 int ll_gemm_set_tile_n(int bn);
+/* CTA-pair (tcgen05 cta_group::2, 256-row tiles) policy: -1 automatic, 0 never, 1 always. */
+int ll_gemm_set_cta_pair(int mode);
 
 /* ----------------------------------------------------------- device: distortions */
 

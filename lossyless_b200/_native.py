@@ -69,6 +69,7 @@ _SIGNATURES = {
     "ll_attention": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P]),
     "ll_gemm": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "ll_gemm_set_tile_n": (c_int, [c_int]),
+    "ll_gemm_set_cta_pair": (c_int, [c_int]),
     "ll_contrastive_logits": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int, _P]),
     "ll_contrastive_logits_backward": (c_int, [_P, c_int, _P, _P, c_int, c_int, _P, _P]),
     "ll_contrastive_ce_forward": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P]),

@@ -30,17 +30,26 @@ constexpr int kABytes = kBM * kBK * 2;
 constexpr int kEpiCols = 64;                    // one 128 B swizzle row of 16-bit outputs
 constexpr int kEpiBufBytes = 32 * kEpiCols * 2;  // 32 rows (one warp's TMEM lanes) x 64 columns
 
-template <int BN>
+// kCtas = 1: one CTA per 128 x BN tile.  kCtas = 2: a CTA pair (cluster of 2, tcgen05
+// cta_group::2) per 256 x BN tile -- each CTA holds its own 128 A rows and HALF of the W tile, so per
+// CTA and K-block the shared-memory traffic drops from (128 + BN) to (128 + BN/2) rows while the
+// tensor cores of both SMs run the same M = 256 instruction.
+template <int BN, int kCtas>
 struct GemmShape {
-    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kBRows = BN / kCtas;  // W rows staged per CTA
+    static constexpr int kBBytes = kBRows * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN == 256) ? 3 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
     static constexpr int kAccStride = (BN == 192) ? 256 : BN;  // TMEM columns between the two accumulators
     static constexpr int kTmemCols = 2 * kAccStride;           // power of two >= 32
-    static constexpr int kGroups = BN / kEpiCols;       // 64-column epilogue groups per tile
+    static constexpr int kGroups = BN / kEpiCols;              // 64-column epilogue groups per tile
     static constexpr int kStagingBytes = 4 * kGroups * kEpiBufBytes;  // 4 epilogue warps x one buffer per group
+    static constexpr int kMaxSmem = 232448 - 1024;             // 227 KB minus the alignment slack
+    static constexpr int kStagesFit = (kMaxSmem - kStagingBytes - 512) / kStageBytes;
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kBarBytes = (2 * kStages + 4 + 4 * kGroups) * 8 + 16;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;  // +1024: alignment
+    static_assert(kStages >= 3, "not enough shared memory for a 3-stage pipeline");
+    static_assert(kBarBytes <= 512, "barrier block overflows its reservation");
 };
 
 template <typename T>
@@ -98,13 +107,13 @@ __device__ __forceinline__ float quick_gelu(float x)
     return fmaf(hx, t, hx);
 }
 
-template <typename T, int BN>
+template <typename T, int BN, int kCtas>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
                     const float *__restrict__ bias, int has_residual, int M, int N, int K, int act)
 {
-    using S = GemmShape<BN>;
+    using S = GemmShape<BN, kCtas>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -120,6 +129,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = kCtas == 2 ? ptx::cluster_ctarank() : 0;  // 0 = pair leader (issues the MMAs)
+    const int worker = blockIdx.x / kCtas;       // persistent worker (CTA or CTA pair)
+    const int num_workers = gridDim.x / kCtas;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
@@ -133,18 +145,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+            ptx::mbar_init(&tempty_bar[i], 4 * kCtas);  // one arrive per epilogue warp (of both CTAs)
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 1) ptx::tmem_alloc<S::kTmemCols>(tmem_slot);
+    if (warp == 1) {
+        if constexpr (kCtas == 2)
+            ptx::tmem_alloc_pair<S::kTmemCols>(tmem_slot);
+        else
+            ptx::tmem_alloc<S::kTmemCols>(tmem_slot);
+    }
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (kCtas == 2) ptx::cluster_sync();  // peer's barriers are initialised, its TMEM allocated
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    constexpr int kTileM = kBM * kCtas;
     const int num_n = N / BN;
-    const int num_m = (M + kBM - 1) / kBM;
+    const int num_m = (M + kTileM - 1) / kTileM;
     const int num_tiles = num_m * num_n;
     const int num_kb = K / kBK;
 
@@ -153,27 +172,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / num_n) * kBM;
-                const int n0 = (tile % num_n) * BN;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const int m0 = (tile / num_n) * kTileM + (int)cta_rank * kBM;
+                const int n0 = (tile % num_n) * BN + (int)cta_rank * S::kBRows;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-                    ptx::tma_load_2d(sm_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, m0);
-                    ptx::tma_load_2d(sm_b + stage * S::kBBytes, &tmap_w, &full_bar[stage], kb * kBK, n0);
+                    if constexpr (kCtas == 2) {
+                        // both CTAs' bytes are counted on the LEADER's full barrier, which alone arms it
+                        const uint32_t lead_bar = ptx::map_to_cta(&full_bar[stage], 0);
+                        if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+                        ptx::tma_load_2d_pair(sm_a + stage * kABytes, &tmap_a, lead_bar, kb * kBK, m0);
+                        ptx::tma_load_2d_pair(sm_b + stage * S::kBBytes, &tmap_w, lead_bar, kb * kBK, n0);
+                    } else {
+                        ptx::mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+                        ptx::tma_load_2d(sm_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, m0);
+                        ptx::tma_load_2d(sm_b + stage * S::kBBytes, &tmap_w, &full_bar[stage], kb * kBK, n0);
+                    }
                     if (++stage == S::kStages) stage = 0, phase ^= 1;
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, BN, std::is_same<T, __nv_bfloat16>::value ? 1 : 0);
+        // ------------------------------------------------------------ MMA issuer (pair leader only)
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, BN, std::is_same<T, __nv_bfloat16>::value ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -187,12 +214,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
                         // +32 B per K=16 step inside the 128 B swizzle row: start-address field += 2
-                        ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        if constexpr (kCtas == 2)
+                            ptx::mma_f16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else
+                            ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     }
-                    ptx::mma_commit(&empty_bar[stage]);  // frees the smem stage when the MMAs retire
+                    // frees the smem stage (in both CTAs) when the MMAs retire
+                    if constexpr (kCtas == 2)
+                        ptx::mma_commit_pair(&empty_bar[stage]);
+                    else
+                        ptx::mma_commit(&empty_bar[stage]);
                     if (++stage == S::kStages) stage = 0, phase ^= 1;
                 }
-                ptx::mma_commit(&tfull_bar[acc]);
+                if constexpr (kCtas == 2)
+                    ptx::mma_commit_pair(&tfull_bar[acc]);
+                else
+                    ptx::mma_commit(&tfull_bar[acc]);
             }
         }
         __syncwarp();
@@ -209,10 +246,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int swz = lane & 7;      // 128 B swizzle: 16 B chunk j of row r lives at chunk j ^ (r & 7)
         uint8_t *my_row0 = buf0 + lane * 128;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t tempty_lead[2] = {kCtas == 2 ? ptx::map_to_cta(&tempty_bar[0], 0) : 0,
+                                         kCtas == 2 ? ptx::map_to_cta(&tempty_bar[1], 0) : 0};
+        for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (tile / num_n) * kBM + quarter * 32;
+            const int m0 = (tile / num_n) * kTileM + (int)cta_rank * kBM + quarter * 32;
             const int n0 = (tile % num_n) * BN;
             if (has_residual && lane == 0) {
                 ptx::tma_store_wait_read<0>();  // previous tile's stores no longer read the buffers
@@ -241,7 +280,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     // accumulator fully read: hand the TMEM buffer back to the MMA warp early
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+                    if (lane == 0) {
+                        if constexpr (kCtas == 2)
+                            ptx::mbar_arrive_cluster(tempty_lead[acc]);  // the leader's MMA thread waits for both CTAs
+                        else
+                            ptx::mbar_arrive(&tempty_bar[acc]);
+                    }
                 }
                 if (has_residual) {
                     ptx::mbar_wait(&rbar[g], rphase);
@@ -289,9 +333,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ---------------------------------------------------------------- teardown
     ptx::tc_fence_before();
     __syncthreads();
+    if constexpr (kCtas == 2) ptx::cluster_sync();  // the peer may still be read by / signalling this CTA
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<S::kTmemCols>(tmem_base);
+        if constexpr (kCtas == 2)
+            ptx::tmem_dealloc_pair<S::kTmemCols>(tmem_base);
+        else
+            ptx::tmem_dealloc<S::kTmemCols>(tmem_base);
     }
 }
 
@@ -330,70 +378,95 @@ int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, int64_t rows, in
     return LL_OK;
 }
 
-template <typename T, int BN>
+template <typename T, int BN, int kCtas>
 static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr,
                        const float *bias, int has_residual, int64_t M, int N, int K, int act, cudaStream_t stream)
 {
-    using S = GemmShape<BN>;
+    using S = GemmShape<BN, kCtas>;
     static bool configured = false;
-    auto kern = gemm_tcgen05_kernel<T, BN>;
+    auto kern = gemm_tcgen05_kernel<T, BN, kCtas>;
     if (!configured) {
         LL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmemBytes));
         configured = true;
     }
-    const int tiles = (int)((M + kBM - 1) / kBM) * (N / BN);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, kGemmThreads, S::kSmemBytes, stream>>>(ta, tw, td, tr, bias, has_residual, (int)M, N, K, act);
-    LL_LAUNCH_CHECK();
+    const int tiles = (int)((M + kBM * kCtas - 1) / (kBM * kCtas)) * (N / BN);
+    const int workers = num_sms() / kCtas;
+    const int grid = (tiles < workers ? tiles : workers) * kCtas;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = S::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, td, tr, bias, has_residual, (int)M, N, K, act));
     return LL_OK;
 }
 
-// Tile-N choice.  The persistent grid runs ceil(tiles / #SMs) rounds of one BN-wide tile each, so
-// the cost of a candidate is rounds * BN (the partially filled last round is what hurts: N = 768
-// with BN = 256 at M = 12 800 is 300 tiles = 3 rounds for 2.03 rounds of work).  Narrower tiles
-// re-read A more often, hence the small penalty.
-static int pick_bn(int64_t M, int N)
+// Tile choice.  The persistent grid runs ceil(tiles / workers) rounds of one tile each, so the cost
+// of a candidate is rounds * BN (the partially filled last round is what hurts: N = 768 with
+// 128 x 256 tiles at M = 12 800 is 300 tiles = 3 rounds for 2.03 rounds of work).  Narrower tiles
+// re-read A more often, hence the small penalty.  CTA pairs (256-row tiles on 74 workers) are
+// preferred whenever the problem has at least one full round of them.
+static int g_force_bn = 0;    // test / tuning overrides (ll_gemm_set_tile_n, ll_gemm_set_cta_pair)
+static int g_pair_mode = -1;  // -1 auto, 0 never, 1 always
+
+static void pick_tile(int64_t M, int N, int &bn_out, int &ctas_out)
 {
-    const int64_t mt = (M + kBM - 1) / kBM;
     const int sms = num_sms();
-    int best = 0;
+    int best_bn = 0, best_ctas = 1;
     double best_cost = 0.0;
     const int cands[4] = {256, 192, 128, 64};
-    for (int bn : cands) {
-        if (N % bn != 0) continue;
-        const int64_t tiles = mt * (N / bn);
-        const int64_t rounds = (tiles + sms - 1) / sms;
-        const double penalty = bn == 256 ? 1.0 : bn == 192 ? 1.02 : bn == 128 ? 1.06 : 1.2;
-        const double cost = (double)rounds * bn * penalty;
-        if (best == 0 || cost < best_cost) best = bn, best_cost = cost;
+    for (int ctas = 2; ctas >= 1; --ctas) {
+        if (ctas == 2 && (g_pair_mode == 0 || (g_pair_mode < 0 && M < 256 * (sms / 2)))) continue;
+        if (ctas == 1 && g_pair_mode == 1) continue;
+        const int64_t mt = (M + kBM * ctas - 1) / (kBM * ctas);
+        const int workers = sms / ctas;
+        for (int bn : cands) {
+            if (N % bn != 0) continue;
+            if (g_force_bn && bn != g_force_bn && N % g_force_bn == 0) continue;
+            if (ctas == 2 && bn == 64) continue;  // 32-row W halves are not worth a pair
+            const int64_t tiles = mt * (N / bn);
+            const int64_t rounds = (tiles + workers - 1) / workers;
+            const double penalty = (bn == 256 ? 1.0 : bn == 192 ? 1.02 : bn == 128 ? 1.06 : 1.2) * (ctas == 2 ? 0.85 : 1.0);
+            const double cost = (double)rounds * bn * penalty;
+            if (best_bn == 0 || cost < best_cost) best_bn = bn, best_ctas = ctas, best_cost = cost;
+        }
     }
-    return best;
+    bn_out = best_bn;
+    ctas_out = best_ctas;
 }
 
-static int g_force_bn = 0;  // test / tuning override (ll_gemm_set_tile_n)
-
-template <typename T>
+template <typename T, int kCtas>
 static int launch_bn(int bn, const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr,
                      const float *bias, int has_residual, int64_t M, int N, int K, int act, cudaStream_t stream)
 {
     switch (bn) {
-        case 256: return launch_impl<T, 256>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
-        case 192: return launch_impl<T, 192>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
-        case 128: return launch_impl<T, 128>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
-        case 64: return launch_impl<T, 64>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+        case 256: return launch_impl<T, 256, kCtas>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+        case 192: return launch_impl<T, 192, kCtas>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+        case 128: return launch_impl<T, 128, kCtas>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+        case 64:
+            if constexpr (kCtas == 1) return launch_impl<T, 64, 1>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
     }
-    return fail(LL_ERR_INVALID, "gemm: unsupported tile N %d", bn);
+    return fail(LL_ERR_INVALID, "gemm: unsupported tile N %d for %d CTA(s)", bn, kCtas);
 }
 
 int gemm_launch_tmaps(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr, int bn,
-                      const float *bias, int has_residual, int64_t M, int N, int K, int dtype, int act,
+                      int ctas, const float *bias, int has_residual, int64_t M, int N, int K, int dtype, int act,
                       cudaStream_t stream)
 {
-    if (dtype == LL_F16) return launch_bn<__half>(bn, ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
-    return launch_bn<__nv_bfloat16>(bn, ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+    if (dtype == LL_F16)
+        return ctas == 2 ? launch_bn<__half, 2>(bn, ta, tw, td, tr, bias, has_residual, M, N, K, act, stream)
+                         : launch_bn<__half, 1>(bn, ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
+    return ctas == 2 ? launch_bn<__nv_bfloat16, 2>(bn, ta, tw, td, tr, bias, has_residual, M, N, K, act, stream)
+                     : launch_bn<__nv_bfloat16, 1>(bn, ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
 }
 
-int gemm_pick_bn(int64_t M, int N) { return pick_bn(M, N); }
 
 int gemm_launch(const void *A, const void *W, const float *bias, const void *residual, void *D, int64_t M, int N,
                 int K, int dtype, int act, cudaStream_t stream)
@@ -404,11 +477,12 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
     LL_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0 && (!residual || (reinterpret_cast<uintptr_t>(residual) & 15) == 0) &&
                    (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
                "gemm: D / residual / bias must be 16-byte aligned");
-    const int bn = (g_force_bn && N % g_force_bn == 0) ? g_force_bn : pick_bn(M, N);
+    int bn = 0, ctas = 1;
+    pick_tile(M, N, bn, ctas);
     CUtensorMap ta, tw, td, tr;
     int rc = make_tmap_2d(&ta, A, dtype, M, K, kBM);
     if (rc != LL_OK) return rc;
-    rc = make_tmap_2d(&tw, W, dtype, N, K, bn);
+    rc = make_tmap_2d(&tw, W, dtype, N, K, bn / ctas);  // a CTA of a pair stages half of the W tile
     if (rc != LL_OK) return rc;
     rc = make_tmap_2d(&td, D, dtype, M, N, 32);  // epilogue staging box: 32 rows x 64 columns
     if (rc != LL_OK) return rc;
@@ -417,7 +491,7 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
         rc = make_tmap_2d(&tr, residual, dtype, M, N, 32);
         if (rc != LL_OK) return rc;
     }
-    return gemm_launch_tmaps(ta, tw, td, tr, bn, bias, residual != nullptr, M, N, K, dtype, act, stream);
+    return gemm_launch_tmaps(ta, tw, td, tr, bn, ctas, bias, residual != nullptr, M, N, K, dtype, act, stream);
 }
 
 }  // namespace ll
@@ -426,6 +500,13 @@ extern "C" int ll_gemm_set_tile_n(int bn)
 {
     if (bn != 0 && bn != 64 && bn != 128 && bn != 192 && bn != 256) return ll::fail(LL_ERR_INVALID, "gemm_set_tile_n: %d not in {0,64,128,192,256}", bn);
     ll::g_force_bn = bn;
+    return LL_OK;
+}
+
+extern "C" int ll_gemm_set_cta_pair(int mode)
+{
+    if (mode < -1 || mode > 1) return ll::fail(LL_ERR_INVALID, "gemm_set_cta_pair: mode must be -1 (auto), 0 (off) or 1 (on)");
+    ll::g_pair_mode = mode;
     return LL_OK;
 }
 

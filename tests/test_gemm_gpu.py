@@ -95,3 +95,45 @@ def test_gemm_every_tile_width(cuda_device, bn, use_res):
     finally:
         nat.call("ll_gemm_set_tile_n", 0)
     assert (D.float() - ref).abs().max().item() < 6e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("bn", [128, 192, 256])
+@pytest.mark.parametrize("M,use_res,act", [(128 * 148 * 2 + 77, False, 0), (12800, True, 0), (300, False, 1), (25600, True, 1)])
+def test_gemm_cta_pair(cuda_device, bn, M, use_res, act):
+    """tcgen05 cta_group::2 path (256-row tiles on CTA pairs), forced on: ragged M (the peer CTA of the
+    last pair partly or fully out of range), residual, QuickGELU, several tiles per pair."""
+    from lossyless_b200 import _native as nat
+
+    g = torch.Generator(device=cuda_device).manual_seed(bn + M)
+    Nn, K = 768, 768
+    A = (torch.randn(M, K, generator=g, device=cuda_device) * 0.5).half()
+    W = (torch.randn(Nn, K, generator=g, device=cuda_device) * K ** -0.5).half()
+    bias = torch.randn(Nn, generator=g, device=cuda_device)
+    res = torch.randn(M, Nn, generator=g, device=cuda_device).half() if use_res else None
+    ref = _ref(A, W, bias, res, act)
+    nat.call("ll_gemm_set_tile_n", bn)
+    nat.call("ll_gemm_set_cta_pair", 1)
+    try:
+        D = _gemm(A, W, bias, res, act)
+        D2 = _gemm(A, W, bias, res, act)
+    finally:
+        nat.call("ll_gemm_set_tile_n", 0)
+        nat.call("ll_gemm_set_cta_pair", -1)
+    assert torch.equal(D, D2)
+    assert (D.float() - ref).abs().max().item() < 6e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_cta_pair_long_k(cuda_device):
+    from lossyless_b200 import _native as nat
+
+    g = torch.Generator(device=cuda_device).manual_seed(77)
+    M, Nn, K = 20000, 768, 3072
+    A = (torch.randn(M, K, generator=g, device=cuda_device) * 0.5).half()
+    W = (torch.randn(Nn, K, generator=g, device=cuda_device) * K ** -0.5).half()
+    nat.call("ll_gemm_set_cta_pair", 1)
+    try:
+        D = _gemm(A, W)
+    finally:
+        nat.call("ll_gemm_set_cta_pair", -1)
+    ref = _ref(A, W, None, None, 0)
+    assert (D.float() - ref).abs().max().item() < 6e-3 * max(1.0, ref.abs().max().item())

@@ -13,6 +13,9 @@ dev = torch.device("cuda")
 shapes = [("patch", n_img * 49, 768, 3072, 0, False), ("qkv", n_img * 50, 2304, 768, 0, False),
           ("out", n_img * 50, 768, 768, 0, True), ("fc1", n_img * 50, 3072, 768, 1, False),
           ("fc2", n_img * 50, 768, 3072, 0, True), ("proj", n_img, 512, 768, 0, False)]
+pair_mode = int(os.environ.get("LL_PAIR", "-1"))
+N.call("ll_gemm_set_cta_pair", pair_mode)
+print(f"--- cta_pair mode {pair_mode}, {n_img} images per pass")
 tot_ms, tot_fl = 0.0, 0.0
 for name, M, Nn, K, act, res in shapes:
     nbuf = 3  # rotate buffers so A/D are not trivially L2 resident from the previous launch
@@ -42,6 +45,9 @@ for name, M, Nn, K, act, res in shapes:
     tot_fl += fl * mult
     print(f"{name:6s} M={M:6d} N={Nn:5d} K={K:5d}  {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  (x{mult})")
 print(f"per pass of {n_img} images: GEMM {tot_ms:.3f} ms, {tot_fl / tot_ms / 1e9:.1f} TFLOP/s, {n_img / tot_ms * 1e3:.0f} img/s GEMM-only")
+
+if os.environ.get("LL_GEMM_ONLY"):
+    sys.exit(0)
 
 # ---- the encoder's non-GEMM kernels and the codec at the same pass size
 def timeit(fn, reps=20):

@@ -25,6 +25,10 @@ for s in $STAGES; do
     smoke) run smoke 200 python __graft_entry__.py smoke ;;
     bench) run bench 400 python bench.py --steps 10 --warmup 3 ;;
     gemmbench) run gemmbench 200 python tools/gemm_bench.py 256 ;;
+    pairbench) run pairbench0 200 env LL_PAIR=0 LL_GEMM_ONLY=1 python tools/gemm_bench.py 256
+               run pairbench1 200 env LL_PAIR=1 LL_GEMM_ONLY=1 python tools/gemm_bench.py 256
+               run pairbench1_512 200 env LL_PAIR=1 LL_GEMM_ONLY=1 python tools/gemm_bench.py 512
+               run pairbench0_512 200 env LL_PAIR=0 LL_GEMM_ONLY=1 python tools/gemm_bench.py 512 ;;
     ncu_gemm) run ncu_gemm 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 8 -c 5 -f -o gpurun_out/prof_gemm python tools/gemm_bench.py 256 ;;
     ncu_list) run ncu_list 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --batch 256 --no-cpu-baseline ;;
   esac
