@@ -9,10 +9,10 @@
 // operands K-major, which is what nn.Linear stores.
 //
 // Roles (192 threads, 1 CTA per SM, grid = min(#tiles, #SMs), static round-robin tiles):
-//   warp 0      TMA producer: 128xBK A tile + BNxBK W tile per stage, 128B swizzle, mbarrier tx
-//   warp 1      allocates TMEM; one lane issues tcgen05.mma (M=128, N=BN, K=16) into one of two
+//   warp 4      TMA producer: 128xBK A tile + BNxBK W tile per stage, 128B swizzle, mbarrier tx
+//   warp 5      allocates TMEM; one lane issues tcgen05.mma (M=128, N=BN, K=16) into one of two
 //               TMEM accumulator buffers, commits stage-empty / accumulator-full barriers
-//   warps 2..5  epilogue, overlapping the next tile's main loop (double-buffered TMEM): per
+//   warps 0..3  epilogue, overlapping the next tile's main loop (double-buffered TMEM): per
 //               32-row x 64-column group tcgen05.ld -> bias / QuickGELU / residual in fp32 ->
 //               16-bit, swizzled st.shared -> TMA store (full 128 B lines; the row-per-thread
 //               accumulator layout would otherwise scatter 16 B pieces over 32 lines per store).
@@ -26,6 +26,11 @@ namespace ll {
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 x 16-bit = one 128 B swizzle row
 constexpr int kGemmThreads = 192;
+// Warp roles.  The SM sub-partition schedulers favour the higher warp id among eligible warps, and
+// warp w runs on sub-partition w % 4: the two latency-critical single-thread roles get the HIGHEST
+// ids so the ALU-heavy epilogue warps sharing their sub-partitions (0 and 1) cannot starve them.
+constexpr int kProducerWarp = 4;
+constexpr int kMmaWarp = 5;
 constexpr int kABytes = kBM * kBK * 2;
 constexpr int kEpiCols = 64;                    // one 128 B swizzle row of 16-bit outputs
 constexpr int kEpiBufBytes = 32 * kEpiCols * 2;  // 32 rows (one warp's TMEM lanes) x 64 columns
@@ -133,7 +138,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int worker = blockIdx.x / kCtas;       // persistent worker (CTA or CTA pair)
     const int num_workers = gridDim.x / kCtas;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kProducerWarp && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_w);
         ptx::prefetch_tmap(&tmap_d);
@@ -149,7 +154,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         if constexpr (kCtas == 2)
             ptx::tmem_alloc_pair<S::kTmemCols>(tmem_slot);
         else
@@ -167,7 +172,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int num_tiles = num_m * num_n;
     const int num_kb = K / kBK;
 
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
@@ -193,7 +198,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ------------------------------------------------------------ MMA issuer (pair leader only)
         if (lane == 0 && cta_rank == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, BN, std::is_same<T, __nv_bfloat16>::value ? 1 : 0);
@@ -234,7 +239,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         __syncwarp();
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------ epilogue (warps 0..3)
         // One 32-row x 64-column staging buffer per column group and warp.  With a residual, all of
         // the tile's residual groups are TMA-loaded into them as soon as the previous tile's stores
         // have drained -- i.e. while the MMAs of this tile are still running -- and the results
@@ -334,7 +339,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     ptx::tc_fence_before();
     __syncthreads();
     if constexpr (kCtas == 2) ptx::cluster_sync();  // the peer may still be read by / signalling this CTA
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         ptx::tc_fence_after();
         if constexpr (kCtas == 2)
             ptx::tmem_dealloc_pair<S::kTmemCols>(tmem_base);
