@@ -188,7 +188,8 @@ int ll_vit_forward(ll_vit_t *v, const void *x, int x_dtype, int64_t batch, void 
                    void *workspace, int64_t workspace_bytes, ll_stream_t stream);
 /* number of kernel launches one ll_vit_forward of `batch` images issues */
 int64_t ll_vit_launches(const ll_vit_t *v, int64_t batch);
-/* images per internal pass (default 256): a pass's activations are sized to stay in L2 */
+/* max images per internal pass (default 378 = one full round of 74 CTA pairs x 256 token rows);
+ * a batch is split into near-equal passes */
 int ll_vit_set_chunk(ll_vit_t *v, int64_t chunk);
 
 /* Per-GEMM device timing for the roofline report: between begin and end every GEMM launch of

@@ -272,9 +272,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll 1
             for (int g = 0; g < S::kGroups; ++g) {
                 uint8_t *my_row = my_row0 + g * kEpiBufBytes;
+                // bias for the group's 64 columns first: the (L1-resident, warp-uniform) loads complete
+                // under the TMEM load latency instead of stalling the arithmetic below
+                float4 bv[16];
+                if (bias != nullptr && !(act & 0x400)) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) bv[q] = __ldg(reinterpret_cast<const float4 *>(bias + n0 + g * kEpiCols) + q);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 uint32_t r0[32], r1[32];
-                ptx::tmem_ld_32x32(taddr + g * kEpiCols, r0);
-                ptx::tmem_ld_32x32(taddr + g * kEpiCols + 32, r1);
+                if (!(act & 0x800)) {
+                    ptx::tmem_ld_32x32(taddr + g * kEpiCols, r0);
+                    ptx::tmem_ld_32x32(taddr + g * kEpiCols + 32, r1);
+                }
                 if (!has_residual && lane == 0) {
                     // buffer g was last read by the previous tile's store of group g: at most the
                     // kGroups-1 younger stores may still be pending
@@ -302,14 +314,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     float f[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(j < 4 ? r0[j * 8 + e] : r1[(j - 4) * 8 + e]);
-                    const int col = n0 + g * kEpiCols + j * 8;
-                    if (bias != nullptr) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + col));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + col + 4));
+                    {
+                        const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
                         f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
                         f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
                     }
-                    if (act == 1) {
+                    if ((act & 0xff) == 1) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] = quick_gelu(f[e]);
                     }
@@ -320,11 +330,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] += rf[e];
                     }
-                    *slot = Pack8<T>::pack(f);
+                    if (!(act & 0x200)) *slot = Pack8<T>::pack(f);
                 }
-                ptx::fence_proxy_async_smem();
+                if (!(act & 0x1000)) ptx::fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !(act & 0x100)) {
                     ptx::tma_store_2d(&tmap_d, buf0 + g * kEpiBufBytes, n0 + g * kEpiCols, m0);
                     ptx::tma_store_commit();
                 }
@@ -428,7 +438,7 @@ static void pick_tile(int64_t M, int N, int &bn_out, int &ctas_out)
     double best_cost = 0.0;
     const int cands[4] = {256, 192, 128, 64};
     for (int ctas = 2; ctas >= 1; --ctas) {
-        if (ctas == 2 && (g_pair_mode == 0 || (g_pair_mode < 0 && M < 256 * (sms / 2)))) continue;
+        if (ctas == 2 && (g_pair_mode == 0 || (g_pair_mode < 0 && M < 128 * (sms / 2)))) continue;
         if (ctas == 1 && g_pair_mode == 1) continue;
         const int64_t mt = (M + kBM * ctas - 1) / (kBM * ctas);
         const int workers = sms / ctas;

@@ -480,7 +480,7 @@ extern "C" int ll_vit_create(const ll_vit_config_t *cfg, const ll_vit_weights_t 
     v->grid = g;
     v->tokens = g * g + 1;
     v->kpatch = 3 * cfg->patch * cfg->patch;
-    v->chunk = 256;
+    v->chunk = 378;  // 74 CTA pairs x 256 rows = 18 944 tokens: every GEMM of a pass is a whole number of rounds
     *out = v;
     return LL_OK;
 }
@@ -517,8 +517,11 @@ extern "C" int ll_vit_forward(ll_vit_t *v, const void *x, int x_dtype, int64_t b
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     const int esz_in = x_dtype == LL_F32 ? 4 : 2;
     const int64_t img = 3LL * v->cfg.res * v->cfg.res;
-    for (int64_t b0 = 0; b0 < batch; b0 += v->chunk) {
-        const int64_t n = (batch - b0) < v->chunk ? (batch - b0) : v->chunk;
+    // near-equal passes (e.g. 1024 -> 3 x 342 rather than 378 + 378 + 268): no under-filled last pass
+    const int64_t passes = (batch + v->chunk - 1) / v->chunk;
+    const int64_t per = (batch + passes - 1) / passes;
+    for (int64_t b0 = 0; b0 < batch; b0 += per) {
+        const int64_t n = (batch - b0) < per ? (batch - b0) : per;
         const Workspace ws = carve(v, n, base);
         const void *xc = static_cast<const uint8_t *>(x) + b0 * img * esz_in;
         void *zc = static_cast<uint8_t *>(z) + b0 * v->cfg.out_dim * 2;

@@ -76,7 +76,9 @@ def test_vit_b32_vs_golden(cuda_device, golden_dir):
     err = np.abs(z - g["z"])
     assert err.max() < 5e-2 and err.mean() < 8e-3, (err.max(), err.mean())
     assert vit(x.float()).float().cpu().numpy().tolist() == z.tolist()  # fp32 input is cast on load
-    xb = x.repeat(150, 1, 1, 1)  # 300 images: crosses the 256-image internal pass boundary
+    xb = x.repeat(200, 1, 1, 1)  # 400 images: two internal passes (378-image limit) of 200
     zb = vit(xb).float().cpu().numpy()
-    assert np.array_equal(zb[0::2], np.repeat(z[:1], 150, 0)) and np.array_equal(zb[1::2], np.repeat(z[1:], 150, 0))
-    assert vit.launches(300) == 2 * (5 + 7 * 12)
+    assert np.array_equal(zb[0::2], np.repeat(z[:1], 200, 0)) and np.array_equal(zb[1::2], np.repeat(z[1:], 200, 0))
+    assert vit.launches(400) == 2 * (5 + 7 * 12)
+    vit.set_chunk(64)  # many small passes give the same bits
+    assert np.array_equal(vit(xb[:130]).float().cpu().numpy(), zb[:130])

@@ -13,9 +13,11 @@ dev = torch.device("cuda")
 shapes = [("patch", n_img * 49, 768, 3072, 0, False), ("qkv", n_img * 50, 2304, 768, 0, False),
           ("out", n_img * 50, 768, 768, 0, True), ("fc1", n_img * 50, 3072, 768, 1, False),
           ("fc2", n_img * 50, 768, 3072, 0, True), ("proj", n_img, 512, 768, 0, False)]
+DBG = int(os.environ.get("LL_DBG", "0"), 0)
 pair_mode = int(os.environ.get("LL_PAIR", "-1"))
 N.call("ll_gemm_set_cta_pair", pair_mode)
-print(f"--- cta_pair mode {pair_mode}, {n_img} images per pass")
+N.call("ll_gemm_set_tile_n", int(os.environ.get("LL_BN", "0")))
+print(f"--- cta_pair mode {pair_mode}, {n_img} images per pass, dbg {DBG:#x}")
 tot_ms, tot_fl = 0.0, 0.0
 for name, M, Nn, K, act, res in shapes:
     nbuf = 3  # rotate buffers so A/D are not trivially L2 resident from the previous launch
@@ -26,7 +28,7 @@ for name, M, Nn, K, act, res in shapes:
 
     def run(i):
         A, D = As[i % nbuf], Ds[i % nbuf]
-        N.call("ll_gemm", N.ptr(A), N.ptr(W), N.ptr(bias), N.ptr(D) if res else None, N.ptr(D), M, Nn, K, 1, act, N.stream())
+        N.call("ll_gemm", N.ptr(A), N.ptr(W), N.ptr(bias), N.ptr(D) if res else None, N.ptr(D), M, Nn, K, 1, act | DBG, N.stream())
 
     for i in range(3):
         run(i)
