@@ -87,6 +87,9 @@ __device__ __forceinline__ void load8(const T *p, float (&f)[8])
 }
 
 // h[r] = LN(x[r * row_stride]) ; row_stride lets ln_post read only the CLS rows.
+// Persistent warps: gamma / beta stay in registers (they are 4x the bytes of a row of x when
+// re-read per row, and were what the first version of this kernel spent its L1 bandwidth on), each
+// warp strides over rows with the next row's loads issued before the current row is reduced.
 template <typename T, int kChunks>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const T *__restrict__ x, int64_t rows, int64_t row_stride, const float *__restrict__ gamma,
@@ -94,12 +97,58 @@ layernorm_kernel(const T *__restrict__ x, int64_t rows, int64_t row_stride, cons
 {
     constexpr int width = kChunks * 256;
     const int lane = threadIdx.x & 31;
-    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= rows) return;
-    float v[kChunks][8];
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float g[kChunks][8], bb[kChunks][8];
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) load8<T>(x + r * row_stride + c * 256 + lane * 8, v[c]);
-    warp_layernorm_store<T, kChunks>(v, gamma, beta, h + r * width, lane, width);
+    for (int c = 0; c < kChunks; ++c) {
+        const int col = c * 256 + lane * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4 *>(gamma + col + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(beta + col)), b1 = __ldg(reinterpret_cast<const float4 *>(beta + col + 4));
+        g[c][0] = g0.x, g[c][1] = g0.y, g[c][2] = g0.z, g[c][3] = g0.w, g[c][4] = g1.x, g[c][5] = g1.y, g[c][6] = g1.z, g[c][7] = g1.w;
+        bb[c][0] = b0.x, bb[c][1] = b0.y, bb[c][2] = b0.z, bb[c][3] = b0.w, bb[c][4] = b1.x, bb[c][5] = b1.y, bb[c][6] = b1.z, bb[c][7] = b1.w;
+    }
+    uint4 raw[kChunks];
+    if (warp0 < rows) {
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) raw[c] = *reinterpret_cast<const uint4 *>(x + warp0 * row_stride + c * 256 + lane * 8);
+    }
+    for (int64_t r = warp0; r < rows; r += nwarps) {
+        float v[kChunks][8];
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            const T *hv = reinterpret_cast<const T *>(&raw[c]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[c][j] = to_float<T>(hv[j]);
+        }
+        const int64_t rn = r + nwarps;
+        if (rn < rows) {
+#pragma unroll
+            for (int c = 0; c < kChunks; ++c) raw[c] = *reinterpret_cast<const uint4 *>(x + rn * row_stride + c * 256 + lane * 8);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[c][j];
+        const float mean = warp_sum(s) / (float)width;
+        float q = 0.f;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = v[c][j] - mean;
+                q += d * d;
+            }
+        const float rstd = rsqrtf(warp_sum(q) / (float)width + 1e-5f);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            T out[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) out[j] = from_float<T>((v[c][j] - mean) * rstd * g[c][j] + bb[c][j]);
+            *reinterpret_cast<uint4 *>(h + r * width + c * 256 + lane * 8) = *reinterpret_cast<const uint4 *>(out);
+        }
+    }
 }
 
 // Token assembly + ln_pre:  x[b, s] = LN( (s == 0 ? class_embedding : patch_out[b, s-1]) + pos[s] ).
@@ -300,7 +349,10 @@ attention_kernel(const T *__restrict__ qkv, T *__restrict__ out, int S, int H, f
 template <typename T>
 static int launch_layernorm(const T *x, int64_t rows, int64_t row_stride, const float *g, const float *b, T *h, int width, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)((rows * 32 + 255) / 256);
+    // persistent: 2 resident CTAs of 8 warps per SM (104 registers / thread), each warp strides over rows
+    const int64_t want = (rows * 32 + 255) / 256;
+    const int64_t cap = 2LL * num_sms();
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
     switch (width / 256) {
         case 1: layernorm_kernel<T, 1><<<grid, 256, 0, s>>>(x, rows, row_stride, g, b, h); break;
         case 2: layernorm_kernel<T, 2><<<grid, 256, 0, s>>>(x, rows, row_stride, g, b, h); break;
