@@ -268,6 +268,7 @@ def main():
     for _ in range(max(2, min(args.steps, 5))):
         step_device()
     gemm_ms, gemm_flops, gemm_launches = comp.clip.profile_end()
+    breakdown = {k: v / max(2, min(args.steps, 5)) for k, v in comp.clip.profile_breakdown().items()}
     pk = peaks()
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     vit_launches = comp.clip.launches(B)
@@ -284,7 +285,8 @@ def main():
                      "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
                      "peak_source": pk["source"], "gemm_ms_per_step": gemm_ms / max(2, min(args.steps, 5)),
                      "gemm_launches_per_step": gemm_launches // max(2, min(args.steps, 5)),
-                     "algorithmic_gflop_per_img": GFLOP_GEMM_PER_IMG},
+                     "algorithmic_gflop_per_img": GFLOP_GEMM_PER_IMG,
+                     "kernel_ms_per_step": breakdown},
         "clocks": clocks.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -197,6 +197,9 @@ int ll_vit_set_chunk(ll_vit_t *v, int64_t chunk);
  * the summed GEMM milliseconds, algorithmic FLOPs (2*M*N*K) and launch count. */
 int ll_vit_profile_begin(ll_vit_t *v);
 int ll_vit_profile_end(ll_vit_t *v, double *gemm_ms, double *gemm_flops, int64_t *gemm_launches);
+/* event-timed milliseconds of the last begin/end window per kernel family:
+ * ms4 = {GEMM, attention, LayerNorm, patchify + token assembly} */
+int ll_vit_profile_breakdown(const ll_vit_t *v, double *ms4);
 
 /* Stand-alone entry points of the encoder's non-GEMM kernels (numerics tests).
  * ll_layernorm: h[r,:] = LN(x[r,:]) * gamma + beta, fp32 statistics, eps 1e-5 (clip LayerNorm).

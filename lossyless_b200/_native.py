@@ -65,6 +65,7 @@ _SIGNATURES = {
     "ll_vit_set_chunk": (c_int, [_P, c_int64]),
     "ll_vit_profile_begin": (c_int, [_P]),
     "ll_vit_profile_end": (c_int, [_P, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64)]),
+    "ll_vit_profile_breakdown": (c_int, [_P, POINTER(ctypes.c_double)]),
     "ll_layernorm": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P]),
     "ll_attention": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P]),
     "ll_gemm": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),

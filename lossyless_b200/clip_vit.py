@@ -194,6 +194,12 @@ class VisionTransformer(nn.Module):
         N.call("ll_vit_profile_end", nat["handle"], ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n))
         return ms.value, fl.value, n.value
 
+    def profile_breakdown(self):
+        """-> dict of event-timed ms per kernel family for the last profile window."""
+        arr = (ctypes.c_double * 4)()
+        N.call("ll_vit_profile_breakdown", self._native["handle"], arr)
+        return dict(gemm=arr[0], attention=arr[1], layernorm=arr[2], patchify_assemble=arr[3])
+
     @torch.no_grad()
     def forward(self, x, out=None):
         """x [B,3,R,R] (fp16 / bf16 / fp32, cuda, CLIP-normalised) -> z [B, output_dim] in the

@@ -421,6 +421,8 @@ struct ll_vit {
     size_t ev_used = 0;
     double prof_flops = 0.0;
     int64_t prof_launches = 0;
+    std::vector<int> ev_cat;         // category of each event pair: 0 gemm, 1 attention, 2 layernorm, 3 other
+    double prof_ms[4] = {0, 0, 0, 0};
     ~ll_vit()
     {
         for (auto e : ev_pool) cudaEventDestroy(e);
@@ -474,29 +476,36 @@ int forward_chunk(ll_vit *v, const void *x, int x_dtype, int64_t n, void *z, con
     const int W = c.width, S = v->tokens, dt = c.dtype;
     const int64_t M = n * S, Mp = n * (S - 1);
     int rc;
-    auto gemm = [&](const void *A, const void *Wt, const float *bias, const void *res, void *D, int64_t m, int N, int K, int act) {
-        if (!v->profiling) return gemm_launch(A, Wt, bias, res, D, m, N, K, dt, act, s);
+    // when profiling, every launch is bracketed by an event pair tagged with its category
+    auto timed = [&](int cat, auto &&launch) {
+        if (!v->profiling) return launch();
         cudaEvent_t e0 = v->next_event(), e1 = v->next_event();
+        v->ev_cat.push_back(cat);
         cudaEventRecord(e0, s);
-        const int r = gemm_launch(A, Wt, bias, res, D, m, N, K, dt, act, s);
+        const int r = launch();
         cudaEventRecord(e1, s);
-        v->prof_flops += 2.0 * (double)m * N * K;
-        v->prof_launches += 1;
         return r;
     };
-    if ((rc = launch_patchify<T>(x, x_dtype, (T *)ws.patch_a, n, c.res, c.patch, s))) return rc;
+    auto gemm = [&](const void *A, const void *Wt, const float *bias, const void *res, void *D, int64_t m, int N, int K, int act) {
+        if (v->profiling) {
+            v->prof_flops += 2.0 * (double)m * N * K;
+            v->prof_launches += 1;
+        }
+        return timed(0, [&] { return gemm_launch(A, Wt, bias, res, D, m, N, K, dt, act, s); });
+    };
+    if ((rc = timed(3, [&] { return launch_patchify<T>(x, x_dtype, (T *)ws.patch_a, n, c.res, c.patch, s); }))) return rc;
     if ((rc = gemm(ws.patch_a, v->w.conv1_w, nullptr, nullptr, ws.patch_o, Mp, W, v->kpatch, 0))) return rc;
-    if ((rc = launch_assemble<T>((const T *)ws.patch_o, (const T *)v->w.class_emb, (const T *)v->w.pos_emb, v->w.ln_pre_w, v->w.ln_pre_b, (T *)ws.x, n, S, W, s))) return rc;
+    if ((rc = timed(3, [&] { return launch_assemble<T>((const T *)ws.patch_o, (const T *)v->w.class_emb, (const T *)v->w.pos_emb, v->w.ln_pre_w, v->w.ln_pre_b, (T *)ws.x, n, S, W, s); }))) return rc;
     for (int l = 0; l < c.layers; ++l) {
-        if ((rc = launch_layernorm<T>((const T *)ws.x, M, W, v->ln1_w[l], v->ln1_b[l], (T *)ws.h, W, s))) return rc;
+        if ((rc = timed(2, [&] { return launch_layernorm<T>((const T *)ws.x, M, W, v->ln1_w[l], v->ln1_b[l], (T *)ws.h, W, s); }))) return rc;
         if ((rc = gemm(ws.h, v->in_proj_w[l], v->in_proj_b[l], nullptr, ws.qkv, M, 3 * W, W, 0))) return rc;
-        if ((rc = launch_attention<T>((const T *)ws.qkv, (T *)ws.h, n, S, c.heads, s))) return rc;
+        if ((rc = timed(1, [&] { return launch_attention<T>((const T *)ws.qkv, (T *)ws.h, n, S, c.heads, s); }))) return rc;
         if ((rc = gemm(ws.h, v->out_proj_w[l], v->out_proj_b[l], ws.x, ws.x, M, W, W, 0))) return rc;
-        if ((rc = launch_layernorm<T>((const T *)ws.x, M, W, v->ln2_w[l], v->ln2_b[l], (T *)ws.h, W, s))) return rc;
+        if ((rc = timed(2, [&] { return launch_layernorm<T>((const T *)ws.x, M, W, v->ln2_w[l], v->ln2_b[l], (T *)ws.h, W, s); }))) return rc;
         if ((rc = gemm(ws.h, v->fc_w[l], v->fc_b[l], nullptr, ws.f, M, 4 * W, W, 1))) return rc;
         if ((rc = gemm(ws.f, v->cproj_w[l], v->cproj_b[l], ws.x, ws.x, M, W, 4 * W, 0))) return rc;
     }
-    if ((rc = launch_layernorm<T>((const T *)ws.x, n, (int64_t)S * W, v->w.ln_post_w, v->w.ln_post_b, (T *)ws.cls, W, s))) return rc;
+    if ((rc = timed(2, [&] { return launch_layernorm<T>((const T *)ws.x, n, (int64_t)S * W, v->w.ln_post_w, v->w.ln_post_b, (T *)ws.cls, W, s); }))) return rc;
     if ((rc = gemm(ws.cls, v->w.proj_t, nullptr, nullptr, z, n, c.out_dim, W, 0))) return rc;
     return LL_OK;
 }
@@ -589,6 +598,7 @@ extern "C" int ll_vit_profile_begin(ll_vit_t *v)
     LL_REQUIRE(v, "vit_profile_begin: null handle");
     v->profiling = true;
     v->ev_used = 0;
+    v->ev_cat.clear();
     v->prof_flops = 0.0;
     v->prof_launches = 0;
     return LL_OK;
@@ -598,17 +608,24 @@ extern "C" int ll_vit_profile_end(ll_vit_t *v, double *gemm_ms, double *gemm_flo
 {
     LL_REQUIRE(v && gemm_ms && gemm_flops && gemm_launches, "vit_profile_end: null pointer");
     v->profiling = false;
-    double ms = 0.0;
+    for (double &m : v->prof_ms) m = 0.0;
     for (size_t i = 0; i + 1 < v->ev_used; i += 2) {
         LL_CUDA_CHECK(cudaEventSynchronize(v->ev_pool[i + 1]));
         float t = 0.f;
         LL_CUDA_CHECK(cudaEventElapsedTime(&t, v->ev_pool[i], v->ev_pool[i + 1]));
-        ms += t;
+        v->prof_ms[v->ev_cat[i / 2] & 3] += t;
     }
-    *gemm_ms = ms;
+    *gemm_ms = v->prof_ms[0];
     *gemm_flops = v->prof_flops;
     *gemm_launches = v->prof_launches;
     v->ev_used = 0;
+    return LL_OK;
+}
+
+extern "C" int ll_vit_profile_breakdown(const ll_vit_t *v, double *ms4)
+{
+    LL_REQUIRE(v && ms4, "vit_profile_breakdown: null pointer");
+    for (int i = 0; i < 4; ++i) ms4[i] = v->prof_ms[i];
     return LL_OK;
 }
 
