@@ -165,6 +165,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if constexpr (kCtas == 2) ptx::cluster_sync();  // peer's barriers are initialised, its TMEM allocated
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous
+    // kernel's tail; from here on global memory written by predecessors is touched
+    pdl_wait();
+    pdl_launch_dependents();
 
     constexpr int kTileM = kBM * kCtas;
     const int num_n = N / BN;
@@ -412,13 +416,15 @@ static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = S::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kCtas;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     LL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, td, tr, bias, has_residual, (int)M, N, K, act));
     return LL_OK;
 }

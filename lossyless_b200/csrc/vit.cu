@@ -21,6 +21,8 @@ template <typename TIn, typename T>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const TIn *__restrict__ x, T *__restrict__ A, int64_t B, int R, int P)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     const int G = R / P;
     const int Kp = 3 * P * P;
     const int64_t total = B * G * G * (int64_t)(Kp / 8);
@@ -108,6 +110,8 @@ layernorm_kernel(const T *__restrict__ x, int64_t rows, int64_t row_stride, cons
         g[c][0] = g0.x, g[c][1] = g0.y, g[c][2] = g0.z, g[c][3] = g0.w, g[c][4] = g1.x, g[c][5] = g1.y, g[c][6] = g1.z, g[c][7] = g1.w;
         bb[c][0] = b0.x, bb[c][1] = b0.y, bb[c][2] = b0.z, bb[c][3] = b0.w, bb[c][4] = b1.x, bb[c][5] = b1.y, bb[c][6] = b1.z, bb[c][7] = b1.w;
     }
+    pdl_wait();  // x is produced by the previous kernel (gamma / beta above are weights)
+    pdl_launch_dependents();
     uint4 raw[kChunks];
     if (warp0 < rows) {
 #pragma unroll
@@ -159,6 +163,8 @@ assemble_lnpre_kernel(const T *__restrict__ patch_out, const T *__restrict__ cls
                       const float *__restrict__ gamma, const float *__restrict__ beta, T *__restrict__ x, int64_t B,
                       int S)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     constexpr int width = kChunks * 256;
     const int lane = threadIdx.x & 31;
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -238,6 +244,8 @@ attention_kernel(const T *__restrict__ qkv, T *__restrict__ out, int S, int H, f
     const int W = H * kHeadDim;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const T *base = qkv + (int64_t)b * S * 3 * W + h * kHeadDim;
+    pdl_wait();
+    pdl_launch_dependents();
 
     // stage Q, K, V with 16-byte cp.async (all loads in flight at once); rows >= S zero-filled
     for (int i = tid; i < 3 * kAttRows * 8; i += 128) {
@@ -354,10 +362,10 @@ static int launch_layernorm(const T *x, int64_t rows, int64_t row_stride, const 
     const int64_t cap = 2LL * num_sms();
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     switch (width / 256) {
-        case 1: layernorm_kernel<T, 1><<<grid, 256, 0, s>>>(x, rows, row_stride, g, b, h); break;
-        case 2: layernorm_kernel<T, 2><<<grid, 256, 0, s>>>(x, rows, row_stride, g, b, h); break;
-        case 3: layernorm_kernel<T, 3><<<grid, 256, 0, s>>>(x, rows, row_stride, g, b, h); break;
-        case 4: layernorm_kernel<T, 4><<<grid, 256, 0, s>>>(x, rows, row_stride, g, b, h); break;
+        case 1: LL_CUDA_CHECK(launch_pdl(layernorm_kernel<T, 1>, dim3(grid), dim3(256), 0, s, x, rows, row_stride, g, b, h)); break;
+        case 2: LL_CUDA_CHECK(launch_pdl(layernorm_kernel<T, 2>, dim3(grid), dim3(256), 0, s, x, rows, row_stride, g, b, h)); break;
+        case 3: LL_CUDA_CHECK(launch_pdl(layernorm_kernel<T, 3>, dim3(grid), dim3(256), 0, s, x, rows, row_stride, g, b, h)); break;
+        case 4: LL_CUDA_CHECK(launch_pdl(layernorm_kernel<T, 4>, dim3(grid), dim3(256), 0, s, x, rows, row_stride, g, b, h)); break;
         default: return fail(LL_ERR_INVALID, "layernorm: width %d unsupported", width);
     }
     LL_LAUNCH_CHECK();
@@ -369,10 +377,10 @@ static int launch_assemble(const T *po, const T *cls, const T *pos, const float 
 {
     const unsigned grid = (unsigned)((B * S * 32 + 255) / 256);
     switch (width / 256) {
-        case 1: assemble_lnpre_kernel<T, 1><<<grid, 256, 0, s>>>(po, cls, pos, g, b, x, B, S); break;
-        case 2: assemble_lnpre_kernel<T, 2><<<grid, 256, 0, s>>>(po, cls, pos, g, b, x, B, S); break;
-        case 3: assemble_lnpre_kernel<T, 3><<<grid, 256, 0, s>>>(po, cls, pos, g, b, x, B, S); break;
-        case 4: assemble_lnpre_kernel<T, 4><<<grid, 256, 0, s>>>(po, cls, pos, g, b, x, B, S); break;
+        case 1: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 1>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S)); break;
+        case 2: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 2>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S)); break;
+        case 3: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 3>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S)); break;
+        case 4: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 4>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S)); break;
         default: return fail(LL_ERR_INVALID, "assemble: width %d unsupported", width);
     }
     LL_LAUNCH_CHECK();
@@ -385,9 +393,9 @@ static int launch_patchify(const void *x, int x_dtype, T *A, int64_t B, int R, i
     const int64_t total = B * (R / P) * (R / P) * (int64_t)(3 * P * P / 8);
     const unsigned grid = (unsigned)((total + 255) / 256);
     switch (x_dtype) {
-        case LL_F32: patchify_kernel<float, T><<<grid, 256, 0, s>>>(static_cast<const float *>(x), A, B, R, P); break;
-        case LL_F16: patchify_kernel<__half, T><<<grid, 256, 0, s>>>(static_cast<const __half *>(x), A, B, R, P); break;
-        case LL_BF16: patchify_kernel<__nv_bfloat16, T><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(x), A, B, R, P); break;
+        case LL_F32: LL_CUDA_CHECK(launch_pdl(patchify_kernel<float, T>, dim3(grid), dim3(256), 0, s, static_cast<const float *>(x), A, B, R, P)); break;
+        case LL_F16: LL_CUDA_CHECK(launch_pdl(patchify_kernel<__half, T>, dim3(grid), dim3(256), 0, s, static_cast<const __half *>(x), A, B, R, P)); break;
+        case LL_BF16: LL_CUDA_CHECK(launch_pdl(patchify_kernel<__nv_bfloat16, T>, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16 *>(x), A, B, R, P)); break;
         default: return fail(LL_ERR_INVALID, "patchify: unknown dtype %d", x_dtype);
     }
     LL_LAUNCH_CHECK();
@@ -398,7 +406,7 @@ template <typename T>
 static int launch_attention(const T *qkv, T *out, int64_t B, int S, int H, cudaStream_t s)
 {
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)kHeadDim);
-    attention_kernel<T><<<(unsigned)(B * H), 128, 0, s>>>(qkv, out, S, H, scale_log2e);
+    LL_CUDA_CHECK(launch_pdl(attention_kernel<T>, dim3((unsigned)(B * H)), dim3(128), 0, s, qkv, out, S, H, scale_log2e));
     LL_LAUNCH_CHECK();
     return LL_OK;
 }
