@@ -209,6 +209,8 @@ int ll_layernorm(const void *x, int64_t rows, int width, const float *gamma, con
                  void *h, int dtype, ll_stream_t stream);
 int ll_attention(const void *qkv, void *out, int64_t batch, int S, int H, int dtype,
                  ll_stream_t stream);
+/* attention implementation: 1 = tcgen05 (default), 0 = mma.sync reference kernel */
+int ll_attention_set_impl(int impl);
 
 /* Stand-alone GEMM entry (tests, micro-benchmarks):  D[M,N] = act(A[M,K] @ W[N,K]^T + bias)
  * (+ residual), A/W/D/residual in `dtype`, bias float32 or NULL, act 0 = none,

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "ll_vit_profile_breakdown": (c_int, [_P, POINTER(ctypes.c_double)]),
     "ll_layernorm": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P]),
     "ll_attention": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "ll_attention_set_impl": (c_int, [c_int]),
     "ll_gemm": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "ll_gemm_set_tile_n": (c_int, [c_int]),
     "ll_gemm_set_cta_pair": (c_int, [c_int]),

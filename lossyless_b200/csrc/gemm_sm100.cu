@@ -397,6 +397,23 @@ int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, int64_t rows, in
     return LL_OK;
 }
 
+int make_tmap_3d(CUtensorMap *map, const void *base, int dtype, int64_t batch, int64_t rows, int64_t cols, int box_rows)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    LL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+    LL_REQUIRE(cols % 64 == 0 && rows > 0 && batch > 0 && box_rows > 0 && box_rows <= 256, "make_tmap_3d: bad shape");
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = dtype == LL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = fn(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+    return LL_OK;
+}
+
 template <typename T, int BN, int kCtas>
 static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr,
                        const float *bias, int has_residual, int64_t M, int N, int K, int act, cudaStream_t stream)

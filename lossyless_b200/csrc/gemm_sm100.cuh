@@ -14,6 +14,9 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
 
 // Encodes a 2-D K-major tensor map: tensor [rows, K] row-major, box [box_rows, 64], 128B swizzle.
 int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, int64_t rows, int64_t K, int box_rows);
+// 3-D map over [batch, rows, cols] (cols contiguous), box [1, box_rows, 64], 128B swizzle: rows beyond
+// `rows` of one batch entry are zero-filled on load and clipped on store (per-image token tiles).
+int make_tmap_3d(CUtensorMap *map, const void *base, int dtype, int64_t batch, int64_t rows, int64_t cols, int box_rows);
 
 namespace ptx {
 
@@ -62,6 +65,22 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
             smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *smem_src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 
 // 2-D tiled TMA store, shared -> global, bulk-group completion (SASS: UTMASTG)
@@ -207,11 +226,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
     return d;
 }
 
-// cute::UMMA::InstrDescriptor for kind::f16: fp32 accumulate, both operands K-major.
-__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int is_bf16)
+// cute::UMMA::InstrDescriptor for kind::f16: fp32 accumulate, A K-major; B K-major or MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int is_bf16, int b_mn_major = 0)
 {
-    return (1u << 4) | ((uint32_t)is_bf16 << 7) | ((uint32_t)is_bf16 << 10) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(m >> 4) << 24);
+    return (1u << 4) | ((uint32_t)is_bf16 << 7) | ((uint32_t)is_bf16 << 10) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -402,9 +402,14 @@ static int launch_patchify(const void *x, int x_dtype, T *A, int64_t B, int R, i
     return LL_OK;
 }
 
+int launch_attention_tc(const void *qkv, void *out, int64_t B, int S, int H, int dtype, cudaStream_t stream);
+static int g_attention_impl = 1;  // 1: tcgen05 (attention_sm100.cu), 0: mma.sync kernel above
+
 template <typename T>
 static int launch_attention(const T *qkv, T *out, int64_t B, int S, int H, cudaStream_t s)
 {
+    if (g_attention_impl == 1)
+        return launch_attention_tc(qkv, out, B, S, H, std::is_same<T, __half>::value ? LL_F16 : LL_BF16, s);
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)kHeadDim);
     LL_CUDA_CHECK(launch_pdl(attention_kernel<T>, dim3((unsigned)(B * H)), dim3(128), 0, s, qkv, out, S, H, scale_log2e));
     LL_LAUNCH_CHECK();
@@ -644,6 +649,13 @@ extern "C" int ll_layernorm(const void *x, int64_t rows, int width, const float 
     LL_REQUIRE(x && gamma && beta && h && rows > 0, "layernorm: bad arguments");
     return dtype == LL_F16 ? launch_layernorm<__half>((const __half *)x, rows, width, gamma, beta, (__half *)h, width, as_stream(stream))
                            : launch_layernorm<__nv_bfloat16>((const __nv_bfloat16 *)x, rows, width, gamma, beta, (__nv_bfloat16 *)h, width, as_stream(stream));
+}
+
+extern "C" int ll_attention_set_impl(int impl)
+{
+    LL_REQUIRE(impl == 0 || impl == 1, "attention_set_impl: 0 (mma.sync) or 1 (tcgen05)");
+    ll::g_attention_impl = impl;
+    return LL_OK;
 }
 
 extern "C" int ll_attention(const void *qkv, void *out, int64_t batch, int S, int H, int dtype, ll_stream_t stream)

@@ -27,16 +27,22 @@ def test_layernorm(cuda_device, dtype):
     assert (h.float() - ref).abs().max().item() < tol * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("S", [50, 64, 17])
-def test_attention(cuda_device, dtype, S):
+@pytest.mark.parametrize("S,B", [(50, 9), (64, 4), (17, 3), (50, 378)])
+def test_attention(cuda_device, dtype, S, B, impl):
+    """impl 1 = tcgen05 kernel (two (image, head) pairs per CTA; B*H odd exercises the tail), 0 = mma.sync"""
     from lossyless_b200 import _native as N
 
-    B, H, d = 9, 12, 64
+    H, d = 12 if B != 3 else 3, 64
     g = torch.Generator(device=cuda_device).manual_seed(S)
     qkv = (torch.randn(B * S, 3 * H * d, generator=g, device=cuda_device)).to(dtype)
-    out = torch.empty(B * S, H * d, dtype=dtype, device=cuda_device)
-    N.call("ll_attention", N.ptr(qkv), N.ptr(out), B, S, H, N.dtype_code(qkv), N.stream())
+    out = torch.full((B * S, H * d), float("nan"), dtype=dtype, device=cuda_device)
+    N.call("ll_attention_set_impl", impl)
+    try:
+        N.call("ll_attention", N.ptr(qkv), N.ptr(out), B, S, H, N.dtype_code(qkv), N.stream())
+    finally:
+        N.call("ll_attention_set_impl", 1)
     q, k, v = qkv.float().reshape(B, S, 3, H, d).permute(2, 0, 3, 1, 4)
     att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)
     ref = (att @ v).permute(0, 2, 1, 3).reshape(B * S, H * d)
