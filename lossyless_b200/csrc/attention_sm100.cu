@@ -1,11 +1,11 @@
-// S <= 64-token, head-dim-64 attention on tcgen05 (sm_100a).
+// S <= 64-token, head-dim-64 attention on tcgen05 (sm_100a): persistent, warp-specialised.
 //
 // nn.MultiheadAttention core of CLIP's ResidualAttentionBlock (clip/model.py; reached from
 // hub/compressor.py:93): out[b, :, h] = softmax(q k^T / 8) v for every (image b, head h).
 //
-// The legacy mma.sync path runs at a small fraction of the tcgen05 rate on B200 (the first
-// version of this kernel kept the HMMA pipe ~100 % busy for 30-40 us per layer), so the two
-// contractions are issued as tcgen05 MMAs with M = 128 = two (image, head) pairs per CTA:
+// Legacy mma.sync runs at a small fraction of the tcgen05 rate on B200 (the mma.sync version of this
+// kernel keeps the HMMA pipe ~100 % busy for 30-40 us per layer), so both contractions are tcgen05
+// MMAs with M = 128 = two (image, head) pairs per work item:
 //
 //   S[128 x 128] = [Q_a; Q_b] . [K_a; K_b]^T     4 x (M128, N128, K16)  -- diagonal 64x64 blocks used
 //   P            = softmax of each row over its own pair's <= 64 keys (fp32, thread per row),
@@ -13,19 +13,25 @@
 //   O[128 x 64]  = P . [V_a; V_b]                8 x (M128, N64, K16), V consumed MN-major exactly
 //                  as TMA lays it out (rows = keys, 128 B of head dim per row)
 //
-// Q/K/V tiles arrive by TMA from the [B, S, 3W] qkv tensor (rows >= S zero-filled by the 3-D tensor
-// map), O leaves through swizzled staging + TMA store (rows >= S clipped).  Half of the S / O MMA work
-// is wasted on the off-diagonal blocks; it is still several times cheaper than the HMMA path.
+// Roles (192 threads, 2 CTAs per SM, each CTA loops over work items):
+//   warp 4     TMA producer: Q,K (as soon as the previous S = QK^T has retired) and V (as soon as the
+//              previous O = PV has retired) from the [B, S, 3W] qkv tensor; rows >= S zero-filled
+//   warp 5     TMEM owner + MMA issuer; S(i+1) is issued before O(i) so the tensor core works on the
+//              next item's scores while the softmax warps are busy with this one
+//   warps 0-3  softmax + output: tcgen05.ld S -> P (fp16/bf16) -> smem; tcgen05.ld O -> scale by 1/sum
+//              -> swizzled staging -> TMA store (rows >= S clipped by the 3-D tensor map)
 #include <cmath>
 
 #include "gemm_sm100.cuh"
 
 namespace ll {
 
-constexpr int kAtRows = 64;          // padded tokens per (image, head)
-constexpr int kAtTile = 128 * 128;   // bytes of a 128-row x 64-element 16-bit tile
-constexpr int kAtSmem = 5 * kAtTile + 64 + 1024;  // Q, K, V, P0, P1 + barriers + alignment slack
-constexpr uint32_t kAtTmemCols = 256;              // S: columns [0,128), O: [128,192)
+constexpr int kAtRows = 64;         // padded tokens per (image, head)
+constexpr int kAtTile = 128 * 128;  // bytes of a 128-row x 64-element 16-bit tile
+constexpr int kAtStage = 4 * 32 * 128;  // output staging: 4 warps x 32 rows x 128 B
+constexpr int kAtSmem = 5 * kAtTile + kAtStage + 128 + 1024;  // Q, K, V, P0, P1, staging, barriers, alignment
+constexpr uint32_t kAtTmemCols = 256;                          // S: columns [0,128), O: [128,192)
+constexpr int kAtThreads = 192;
 
 template <typename T>
 struct AtPack;
@@ -46,28 +52,38 @@ struct AtPack<__nv_bfloat16> {
     }
 };
 
+enum AtBar { kQkFull = 0, kQkEmpty, kVFull, kVEmpty, kSFull, kSFree, kPFull, kPEmpty, kOFull, kOFree, kAtNumBars };
+
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kAtThreads, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out,
                     int num_pairs, int S, int H, float scale_log2e)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *sq = smem, *sk = smem + kAtTile, *sv = smem + 2 * kAtTile, *sp = smem + 3 * kAtTile;
-    uint64_t *load_bar = reinterpret_cast<uint64_t *>(smem + 5 * kAtTile);
-    uint64_t *mma_bar = load_bar + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_bar + 1);
+    uint8_t *stg = smem + 5 * kAtTile;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stg + kAtStage);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar + kAtNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int W = H * 64;
     if (tid == 0) {
         ptx::prefetch_tmap(&tmap_qkv);
         ptx::prefetch_tmap(&tmap_out);
-        ptx::mbar_init(load_bar, 1);
-        ptx::mbar_init(mma_bar, 1);
+        ptx::mbar_init(&bar[kQkFull], 1);
+        ptx::mbar_init(&bar[kQkEmpty], 1);
+        ptx::mbar_init(&bar[kVFull], 1);
+        ptx::mbar_init(&bar[kVEmpty], 1);
+        ptx::mbar_init(&bar[kSFull], 1);
+        ptx::mbar_init(&bar[kSFree], 4);
+        ptx::mbar_init(&bar[kPFull], 4);
+        ptx::mbar_init(&bar[kPEmpty], 1);
+        ptx::mbar_init(&bar[kOFull], 1);
+        ptx::mbar_init(&bar[kOFree], 4);
         ptx::fence_barrier_init();
     }
-    if (warp == 0) ptx::tmem_alloc<kAtTmemCols>(tmem_slot);
+    if (warp == 5) ptx::tmem_alloc<kAtTmemCols>(tmem_slot);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -75,124 +91,164 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     pdl_wait();
     pdl_launch_dependents();
 
-    // the CTA's two (image, head) pairs; an odd tail repeats the last pair (its stores are harmless duplicates)
-    const int p0 = 2 * blockIdx.x;
-    const int p1 = min(p0 + 1, num_pairs - 1);
-    const int b0 = p0 / H, h0 = p0 % H, b1 = p1 / H, h1 = p1 % H;
+    const int num_items = (num_pairs + 1) / 2;
 
-    if (tid == 0) {
-        ptx::mbar_expect_tx(load_bar, 6 * (kAtTile / 2));
-        ptx::tma_load_3d(sq, &tmap_qkv, load_bar, h0 * 64, 0, b0);
-        ptx::tma_load_3d(sq + kAtTile / 2, &tmap_qkv, load_bar, h1 * 64, 0, b1);
-        ptx::tma_load_3d(sk, &tmap_qkv, load_bar, W + h0 * 64, 0, b0);
-        ptx::tma_load_3d(sk + kAtTile / 2, &tmap_qkv, load_bar, W + h1 * 64, 0, b1);
-        ptx::tma_load_3d(sv, &tmap_qkv, load_bar, 2 * W + h0 * 64, 0, b0);
-        ptx::tma_load_3d(sv + kAtTile / 2, &tmap_qkv, load_bar, 2 * W + h1 * 64, 0, b1);
-        ptx::mbar_wait(load_bar, 0);
-        ptx::tc_fence_after();
-        // S = [Q_a; Q_b] [K_a; K_b]^T : both operands K-major, 64 = 4 x 16 along the head dim
-        constexpr uint32_t idesc_s = ptx::make_idesc_f16(128, 128, std::is_same<T, __nv_bfloat16>::value ? 1 : 0);
-        const uint64_t dq = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sq));
-        const uint64_t dk = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sk));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        ptx::mma_commit(mma_bar);
-    }
-    __syncwarp();
-    ptx::mbar_wait(mma_bar, 0);
-    ptx::tc_fence_after();
-
-    // ---- softmax: thread = S row; rows [0,64) belong to pair a (keys in columns [0,64)), rows [64,128) to pair b
-    const int half = tid >> 6;          // which pair this row belongs to
-    const int row_in = tid & 63;        // token index inside the pair
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float inv_sum = 0.f;
-    {
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld_32x32(taddr + half * 64, r0);
-        ptx::tmem_ld_32x32(taddr + half * 64 + 32, r1);
-        ptx::tmem_ld_wait();
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            const float v = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
-            if (j < S) mx = fmaxf(mx, v);
-        }
-        float sum = 0.f;
-        uint32_t packed[32];
-#pragma unroll
-        for (int j = 0; j < 64; j += 2) {
-            const float v0 = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
-            const float v1 = __uint_as_float(j + 1 < 32 ? r0[j + 1] : r1[j + 1 - 32]);
-            const float e0 = j < S ? exp2f((v0 - mx) * scale_log2e) : 0.f;
-            const float e1 = j + 1 < S ? exp2f((v1 - mx) * scale_log2e) : 0.f;
-            sum += e0 + e1;
-            packed[j / 2] = AtPack<T>::pack2(e0, e1);
-        }
-        inv_sum = row_in < S ? 1.f / sum : 0.f;
-        // P row: this pair's keys in tile `half`, zeros in the other tile (block-diagonal P)
-        uint8_t *own = sp + half * kAtTile + tid * 128;
-        uint8_t *oth = sp + (half ^ 1) * kAtTile + tid * 128;
-        const int swz = tid & 7;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            *reinterpret_cast<uint4 *>(own + ((c ^ swz) << 4)) = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-            *reinterpret_cast<uint4 *>(oth + ((c ^ swz) << 4)) = make_uint4(0, 0, 0, 0);
-        }
-    }
-    ptx::fence_proxy_async_smem();  // P (generic-proxy writes) -> visible to the tensor core's async proxy
-    ptx::tc_fence_before();
-    __syncthreads();
-
-    if (tid == 0) {
-        ptx::tc_fence_after();
-        // O = P V : A = P (K-major, two 64-key tiles), B = V read MN-major (rows = keys, 128 B of head dim each):
-        // one K = 16 step is 16 key rows = 2048 B of V
-        constexpr uint32_t idesc_o = ptx::make_idesc_f16(128, 64, std::is_same<T, __nv_bfloat16>::value ? 1 : 0, 1);
-        const uint64_t dv = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sv));  // same LBO/SBO fields: 8-row groups 1024 B apart
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint64_t dp = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sp + (k >> 2) * kAtTile)) + 2 * (k & 3);
-            ptx::mma_f16_ss(tmem_base + 128, dp, dv + (uint64_t)(k * 128), idesc_o, k != 0);
-        }
-        ptx::mma_commit(mma_bar);
-    }
-    __syncwarp();
-    ptx::mbar_wait(mma_bar, 1);
-    ptx::tc_fence_after();
-
-    // ---- O: scale by 1/sum, park in the (consumed) Q tile, TMA store per pair (rows >= S clipped by the map)
-    {
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld_32x32(taddr + 128, r0);
-        ptx::tmem_ld_32x32(taddr + 128 + 32, r1);
-        ptx::tmem_ld_wait();
-        uint8_t *orow = sq + tid * 128;
-        const int swz = tid & 7;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = c * 8 + e * 2;
-                const float v0 = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]) * inv_sum;
-                const float v1 = __uint_as_float(j + 1 < 32 ? r0[j + 1] : r1[j + 1 - 32]) * inv_sum;
-                w[e] = AtPack<T>::pack2(v0, v1);
+    if (warp == 4) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+                // an odd tail repeats the last pair (its store is a harmless duplicate)
+                const int p0 = 2 * item, p1 = min(p0 + 1, num_pairs - 1);
+                const int b0 = p0 / H, h0 = p0 % H, b1 = p1 / H, h1 = p1 % H;
+                const uint32_t ph = it & 1;
+                ptx::mbar_wait(&bar[kQkEmpty], ph ^ 1);
+                ptx::mbar_expect_tx(&bar[kQkFull], 2 * kAtTile);
+                ptx::tma_load_3d(sq, &tmap_qkv, &bar[kQkFull], h0 * 64, 0, b0);
+                ptx::tma_load_3d(sq + kAtTile / 2, &tmap_qkv, &bar[kQkFull], h1 * 64, 0, b1);
+                ptx::tma_load_3d(sk, &tmap_qkv, &bar[kQkFull], W + h0 * 64, 0, b0);
+                ptx::tma_load_3d(sk + kAtTile / 2, &tmap_qkv, &bar[kQkFull], W + h1 * 64, 0, b1);
+                ptx::mbar_wait(&bar[kVEmpty], ph ^ 1);
+                ptx::mbar_expect_tx(&bar[kVFull], kAtTile);
+                ptx::tma_load_3d(sv, &tmap_qkv, &bar[kVFull], 2 * W + h0 * 64, 0, b0);
+                ptx::tma_load_3d(sv + kAtTile / 2, &tmap_qkv, &bar[kVFull], 2 * W + h1 * 64, 0, b1);
             }
-            *reinterpret_cast<uint4 *>(orow + ((c ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr int kBf16 = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+            constexpr uint32_t idesc_s = ptx::make_idesc_f16(128, 128, kBf16);
+            constexpr uint32_t idesc_o = ptx::make_idesc_f16(128, 64, kBf16, /*b_mn_major=*/1);
+            const uint64_t dq = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sq));
+            const uint64_t dk = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sk));
+            // V read MN-major: same descriptor fields (8-row groups 1024 B apart); one K = 16 step = 16 key rows = 2048 B
+            const uint64_t dv = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sv));
+            const uint64_t dp0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sp));
+            const uint64_t dp1 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sp + kAtTile));
+            const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            auto issue_s = [&](int it) {
+                const uint32_t ph = it & 1;
+                ptx::mbar_wait(&bar[kQkFull], ph);
+                if (it > 0) ptx::mbar_wait(&bar[kSFree], ph ^ 1);  // softmax warps hold S(it-1) in registers
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                ptx::mma_commit(&bar[kSFull]);
+                ptx::mma_commit(&bar[kQkEmpty]);
+            };
+            if (my_items > 0) issue_s(0);
+            for (int it = 0; it < my_items; ++it) {
+                if (it + 1 < my_items) issue_s(it + 1);  // next item's scores while this item's softmax runs
+                const uint32_t ph = it & 1;
+                ptx::mbar_wait(&bar[kPFull], ph);
+                ptx::mbar_wait(&bar[kVFull], ph);
+                ptx::mbar_wait(&bar[kOFree], ph ^ 1);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    ptx::mma_f16_ss(tmem_base + 128, (k < 4 ? dp0 : dp1) + 2 * (k & 3), dv + (uint64_t)(k * 128), idesc_o, k != 0);
+                ptx::mma_commit(&bar[kOFull]);
+                ptx::mma_commit(&bar[kVEmpty]);
+                ptx::mma_commit(&bar[kPEmpty]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------ softmax + output (warps 0..3)
+        const int half = tid >> 6;    // which pair of the item this S row belongs to
+        const int row_in = tid & 63;  // token index inside the pair
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int swz = tid & 7;
+        uint8_t *p_own = sp + half * kAtTile + tid * 128;
+        uint8_t *p_oth = sp + (half ^ 1) * kAtTile + tid * 128;
+        uint8_t *my_stg = stg + warp * (32 * 128);
+        int it = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+            const int p0 = 2 * item, p1 = min(p0 + 1, num_pairs - 1);
+            const int pme = half ? p1 : p0;
+            const uint32_t ph = it & 1;
+            uint32_t r0[32], r1[32];
+            ptx::mbar_wait(&bar[kSFull], ph);
+            ptx::tc_fence_after();
+            ptx::tmem_ld_32x32(taddr + half * 64, r0);
+            ptx::tmem_ld_32x32(taddr + half * 64 + 32, r1);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bar[kSFree]);
+
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) {
+                const float v = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
+                if (j < S) mx = fmaxf(mx, v);
+            }
+            float sum = 0.f;
+            uint32_t packed[32];
+#pragma unroll
+            for (int j = 0; j < 64; j += 2) {
+                const float v0 = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
+                const float v1 = __uint_as_float(j + 1 < 32 ? r0[j + 1] : r1[j + 1 - 32]);
+                const float e0 = j < S ? exp2f((v0 - mx) * scale_log2e) : 0.f;
+                const float e1 = j + 1 < S ? exp2f((v1 - mx) * scale_log2e) : 0.f;
+                sum += e0 + e1;
+                packed[j / 2] = AtPack<T>::pack2(e0, e1);
+            }
+            const float inv_sum = row_in < S ? 1.f / sum : 0.f;
+
+            // P row: this pair's keys in tile `half`, zeros in the other tile (block-diagonal P)
+            ptx::mbar_wait(&bar[kPEmpty], ph ^ 1);  // O(it-1) no longer reads P
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                *reinterpret_cast<uint4 *>(p_own + ((c ^ swz) << 4)) = make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+                *reinterpret_cast<uint4 *>(p_oth + ((c ^ swz) << 4)) = make_uint4(0, 0, 0, 0);
+            }
+            ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bar[kPFull]);
+
+            ptx::mbar_wait(&bar[kOFull], ph);
+            ptx::tc_fence_after();
+            ptx::tmem_ld_32x32(taddr + 128, r0);
+            ptx::tmem_ld_32x32(taddr + 128 + 32, r1);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                ptx::mbar_arrive(&bar[kOFree]);
+                ptx::tma_store_wait_read<0>();  // this warp's previous store has drained its staging rows
+            }
+            __syncwarp();
+            uint8_t *orow = my_stg + lane * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = c * 8 + e * 2;
+                    const float v0 = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]) * inv_sum;
+                    const float v1 = __uint_as_float(j + 1 < 32 ? r0[j + 1] : r1[j + 1 - 32]) * inv_sum;
+                    w[e] = AtPack<T>::pack2(v0, v1);
+                }
+                *reinterpret_cast<uint4 *>(orow + ((c ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && (half == 0 || p1 != p0)) {
+                // rows [32*(warp&1), +32) of pair `pme`; the map clips rows >= S
+                ptx::tma_store_3d(&tmap_out, my_stg, (pme % H) * 64, (warp & 1) * 32, pme / H);
+                ptx::tma_store_commit();
+            }
+        }
+        if (lane == 0) ptx::tma_store_wait_all();
+        __syncwarp();
     }
-    ptx::fence_proxy_async_smem();
+
     ptx::tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-        ptx::tma_store_3d(&tmap_out, sq, h0 * 64, 0, b0);
-        if (p1 != p0) ptx::tma_store_3d(&tmap_out, sq + kAtTile / 2, h1 * 64, 0, b1);
-        ptx::tma_store_commit();
-        ptx::tma_store_wait_all();
-    }
-    __syncthreads();
-    if (warp == 0) {
+    if (warp == 5) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<kAtTmemCols>(tmem_base);
     }
@@ -210,12 +266,13 @@ static int launch_attention_tc_t(const void *qkv, void *out, int64_t B, int S, i
     CUtensorMap tq, to;
     int rc = make_tmap_3d(&tq, qkv, dtype, B, S, 3LL * H * 64, kAtRows);
     if (rc != LL_OK) return rc;
-    rc = make_tmap_3d(&to, out, dtype, B, S, (int64_t)H * 64, kAtRows);
+    rc = make_tmap_3d(&to, out, dtype, B, S, (int64_t)H * 64, 32);  // per-warp stores of 32 token rows
     if (rc != LL_OK) return rc;
     const int num_pairs = (int)(B * H);
+    const int items = (num_pairs + 1) / 2;
+    const int grid = items < 2 * num_sms() ? items : 2 * num_sms();
     const float scale_log2e = 1.4426950408889634f / sqrtf(64.f);
-    LL_CUDA_CHECK(launch_pdl(kern, dim3((unsigned)((num_pairs + 1) / 2)), dim3(128), (size_t)kAtSmem, stream, tq, to, num_pairs, S, H,
-                             scale_log2e));
+    LL_CUDA_CHECK(launch_pdl(kern, dim3((unsigned)grid), dim3(kAtThreads), (size_t)kAtSmem, stream, tq, to, num_pairs, S, H, scale_log2e));
     return LL_OK;
 }
 
