@@ -13,10 +13,12 @@
 //   O[128 x 64]  = P . [V_a; V_b]                8 x (M128, N64, K16), V consumed MN-major exactly
 //                  as TMA lays it out (rows = keys, 128 B of head dim per row)
 //
-// Roles (192 threads, 2 CTAs per SM, each CTA loops over work items):
-//   warp 4     TMA producer: Q,K (as soon as the previous S = QK^T has retired) and V (as soon as the
-//              previous O = PV has retired) from the [B, S, 3W] qkv tensor; rows >= S zero-filled
-//   warp 5     TMEM owner + MMA issuer; S(i+1) is issued before O(i) so the tensor core works on the
+// Roles (224 threads, 2 CTAs per SM, each CTA loops over work items):
+//   warp 4     TMA producer for Q,K: reloaded as soon as the previous S = QK^T has retired
+//   warp 5     TMA producer for V: reloaded as soon as the previous O = PV has retired (separate warps so
+//              the next item's Q,K never queue behind a V load that waits for the current O); both read the
+//              [B, S, 3W] qkv tensor through a 3-D map, rows >= S zero-filled
+//   warp 6     TMEM owner + MMA issuer; S(i+1) is issued before O(i) so the tensor core works on the
 //              next item's scores while the softmax warps are busy with this one
 //   warps 0-3  softmax + output: tcgen05.ld S -> P (fp16/bf16) -> smem; tcgen05.ld O -> scale by 1/sum
 //              -> swizzled staging -> TMA store (rows >= S clipped by the 3-D tensor map)
@@ -31,7 +33,7 @@ constexpr int kAtTile = 128 * 128;  // bytes of a 128-row x 64-element 16-bit ti
 constexpr int kAtStage = 4 * 32 * 128;  // output staging: 4 warps x 32 rows x 128 B
 constexpr int kAtSmem = 5 * kAtTile + kAtStage + 128 + 1024;  // Q, K, V, P0, P1, staging, barriers, alignment
 constexpr uint32_t kAtTmemCols = 256;                          // S: columns [0,128), O: [128,192)
-constexpr int kAtThreads = 192;
+constexpr int kAtThreads = 224;
 
 template <typename T>
 struct AtPack;
@@ -51,6 +53,13 @@ struct AtPack<__nv_bfloat16> {
         return *reinterpret_cast<uint32_t *>(&h);
     }
 };
+
+__device__ __forceinline__ float fast_exp2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 enum AtBar { kQkFull = 0, kQkEmpty, kVFull, kVEmpty, kSFull, kSFree, kPFull, kPEmpty, kOFull, kOFree, kAtNumBars };
 
@@ -83,7 +92,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         ptx::mbar_init(&bar[kOFree], 4);
         ptx::fence_barrier_init();
     }
-    if (warp == 5) ptx::tmem_alloc<kAtTmemCols>(tmem_slot);
+    if (warp == 6) ptx::tmem_alloc<kAtTmemCols>(tmem_slot);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -94,28 +103,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     const int num_items = (num_pairs + 1) / 2;
 
     if (warp == 4) {
-        // ------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------ TMA producer: Q, K
         if (lane == 0) {
             int it = 0;
             for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-                // an odd tail repeats the last pair (its store is a harmless duplicate)
+                // an odd tail repeats the last pair (its store is skipped)
                 const int p0 = 2 * item, p1 = min(p0 + 1, num_pairs - 1);
                 const int b0 = p0 / H, h0 = p0 % H, b1 = p1 / H, h1 = p1 % H;
-                const uint32_t ph = it & 1;
-                ptx::mbar_wait(&bar[kQkEmpty], ph ^ 1);
+                ptx::mbar_wait(&bar[kQkEmpty], (it & 1) ^ 1);
                 ptx::mbar_expect_tx(&bar[kQkFull], 2 * kAtTile);
                 ptx::tma_load_3d(sq, &tmap_qkv, &bar[kQkFull], h0 * 64, 0, b0);
                 ptx::tma_load_3d(sq + kAtTile / 2, &tmap_qkv, &bar[kQkFull], h1 * 64, 0, b1);
                 ptx::tma_load_3d(sk, &tmap_qkv, &bar[kQkFull], W + h0 * 64, 0, b0);
                 ptx::tma_load_3d(sk + kAtTile / 2, &tmap_qkv, &bar[kQkFull], W + h1 * 64, 0, b1);
-                ptx::mbar_wait(&bar[kVEmpty], ph ^ 1);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ------------------------------------------------------------ TMA producer: V
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+                const int p0 = 2 * item, p1 = min(p0 + 1, num_pairs - 1);
+                const int b0 = p0 / H, h0 = p0 % H, b1 = p1 / H, h1 = p1 % H;
+                ptx::mbar_wait(&bar[kVEmpty], (it & 1) ^ 1);
                 ptx::mbar_expect_tx(&bar[kVFull], kAtTile);
                 ptx::tma_load_3d(sv, &tmap_qkv, &bar[kVFull], 2 * W + h0 * 64, 0, b0);
                 ptx::tma_load_3d(sv + kAtTile / 2, &tmap_qkv, &bar[kVFull], 2 * W + h1 * 64, 0, b1);
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == 6) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr int kBf16 = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
@@ -185,6 +203,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                 const float v = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
                 if (j < S) mx = fmaxf(mx, v);
             }
+            const float neg_mx = -mx * scale_log2e;
             float sum = 0.f;
             uint32_t packed[32];
 #pragma unroll
@@ -248,7 +267,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 6) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<kAtTmemCols>(tmem_base);
     }
