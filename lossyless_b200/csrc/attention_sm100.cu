@@ -146,30 +146,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             const uint64_t dp0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sp));
             const uint64_t dp1 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sp + kAtTile));
             const int my_items = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-            auto issue_s = [&](int it) {
-                const uint32_t ph = it & 1;
-                ptx::mbar_wait(&bar[kQkFull], ph);
-                if (it > 0) ptx::mbar_wait(&bar[kSFree], ph ^ 1);  // softmax warps hold S(it-1) in registers
-                ptx::tc_fence_after();
+            // Event-driven issue: S(i+1) = Q K^T as soon as its Q,K have landed and the softmax warps hold
+            // S(i) in registers; O(i) = P V as soon as P(i), V(i) are ready and O(i-1) has been read.  Polling
+            // both conditions keeps a late Q,K load for the next item from delaying this item's O.
+            int next_s = 0, next_o = 0;
+            while (next_o < my_items) {
+                bool progressed = false;
+                if (next_s < my_items && next_s <= next_o + 1) {
+                    const uint32_t ph = next_s & 1;
+                    if (ptx::mbar_test(&bar[kQkFull], ph) && (next_s == 0 || ptx::mbar_test(&bar[kSFree], ph ^ 1))) {
+                        ptx::tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-                ptx::mma_commit(&bar[kSFull]);
-                ptx::mma_commit(&bar[kQkEmpty]);
-            };
-            if (my_items > 0) issue_s(0);
-            for (int it = 0; it < my_items; ++it) {
-                if (it + 1 < my_items) issue_s(it + 1);  // next item's scores while this item's softmax runs
-                const uint32_t ph = it & 1;
-                ptx::mbar_wait(&bar[kPFull], ph);
-                ptx::mbar_wait(&bar[kVFull], ph);
-                ptx::mbar_wait(&bar[kOFree], ph ^ 1);
-                ptx::tc_fence_after();
+                        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_base, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                        ptx::mma_commit(&bar[kSFull]);
+                        ptx::mma_commit(&bar[kQkEmpty]);
+                        ++next_s;
+                        progressed = true;
+                    }
+                }
+                if (next_o < next_s) {
+                    const uint32_t ph = next_o & 1;
+                    if (ptx::mbar_test(&bar[kPFull], ph) && ptx::mbar_test(&bar[kVFull], ph) && ptx::mbar_test(&bar[kOFree], ph ^ 1)) {
+                        ptx::tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    ptx::mma_f16_ss(tmem_base + 128, (k < 4 ? dp0 : dp1) + 2 * (k & 3), dv + (uint64_t)(k * 128), idesc_o, k != 0);
-                ptx::mma_commit(&bar[kOFull]);
-                ptx::mma_commit(&bar[kVEmpty]);
-                ptx::mma_commit(&bar[kPEmpty]);
+                        for (int k = 0; k < 8; ++k)
+                            ptx::mma_f16_ss(tmem_base + 128, (k < 4 ? dp0 : dp1) + 2 * (k & 3), dv + (uint64_t)(k * 128), idesc_o, k != 0);
+                        ptx::mma_commit(&bar[kOFull]);
+                        ptx::mma_commit(&bar[kVEmpty]);
+                        ptx::mma_commit(&bar[kPEmpty]);
+                        ++next_o;
+                        progressed = true;
+                    }
+                }
+                if (!progressed) __nanosleep(20);
             }
         }
         __syncwarp();
