@@ -403,7 +403,7 @@ static int launch_patchify(const void *x, int x_dtype, T *A, int64_t B, int R, i
 }
 
 int launch_attention_tc(const void *qkv, void *out, int64_t B, int S, int H, int dtype, cudaStream_t stream);
-static int g_attention_impl = 1;  // 1: tcgen05 (attention_sm100.cu), 0: mma.sync kernel above
+static int g_attention_impl = 0;  // 0: mma.sync kernel above (default: measured faster in situ), 1: tcgen05 (attention_sm100.cu)
 
 template <typename T>
 static int launch_attention(const T *qkv, T *out, int64_t B, int S, int H, cudaStream_t s)

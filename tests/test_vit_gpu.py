@@ -42,7 +42,7 @@ def test_attention(cuda_device, dtype, S, B, impl):
     try:
         N.call("ll_attention", N.ptr(qkv), N.ptr(out), B, S, H, N.dtype_code(qkv), N.stream())
     finally:
-        N.call("ll_attention_set_impl", 1)
+        N.call("ll_attention_set_impl", 0)
     q, k, v = qkv.float().reshape(B, S, 3, H, d).permute(2, 0, 3, 1, 4)
     att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)
     ref = (att @ v).permute(0, 2, 1, 3).reshape(B * S, H * d)
