@@ -1,0 +1,98 @@
+"""GPU, world_size 2 over NCCL (skipped on a 1-GPU box): the two paths that shard.
+  * encode: every rank codes a contiguous slice with no collective on the data path; the merged
+    container file is byte-identical to the single-GPU file;
+  * training: the contrastive distortion's all_gather of logit tiles + the gradient bucket all-reduce
+    reproduce the oracle's two-rank loss (lossyless/distortions.py:327-336 quirk included)."""
+import os
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Images(torch.utils.data.Dataset):
+    def __init__(self, n):
+        g = torch.Generator().manual_seed(0)
+        self.x = torch.randn(n, 3, 224, 224, generator=g).half()
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def __getitem__(self, i):
+        return self.x[i], i % 7
+
+
+def _worker(rank, world, port, tmp):
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    import torch.distributed as dist
+
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import hubconf
+    from lossyless_b200.distortions import ContrastiveDistortion
+    from lossyless_b200.learnable_compressors import allreduce_mean_
+    from lossyless_b200.parallel import compress_dataset_sharded
+    from oracle import losses as olosses
+
+    comp, _ = hubconf.clip_compressor_b005(device=f"cuda:{rank}")
+    ds = _Images(45)
+    compress_dataset_sharded(comp, ds, os.path.join(tmp, "sharded.bin"), label_file=os.path.join(tmp, "y.npy"), batch_size=16)
+    if rank == 0:
+        comp.compress_dataset(ds, os.path.join(tmp, "single.bin"), kwargs_dataloader=dict(batch_size=16, num_workers=0), is_info=False)
+
+    # contrastive distortion with the real all_gather: same projector on both ranks, different data
+    gen = torch.Generator().manual_seed(7)
+    proj = dict(w1=torch.randn(128, 512, generator=gen) * 0.05, b1=torch.zeros(128), w2=torch.randn(256, 128, generator=gen) * 0.1, b2=torch.zeros(256))
+    zs = [torch.randn(8, 512, generator=gen) for _ in range(4)]
+    m = ContrastiveDistortion(temperature=0.01, is_train_temperature=True, effective_batch_size=5000,
+                              project_kwargs=dict(mode="mlp", out_shape=0.5, in_shape=512), is_already_featurized=True)
+    with torch.no_grad():
+        l1, l2 = m.projector.module[0], m.projector.module[-1]
+        l1.weight.copy_(proj["w1"]), l1.bias.zero_(), l2.weight.copy_(proj["w2"]), l2.bias.zero_()
+    m = m.cuda()
+    z, zp = zs[2 * rank].cuda().requires_grad_(True), zs[2 * rank + 1].cuda()
+    d, logs, _ = m(z, zp, None, None)
+    other = olosses.contrastive_local_logits(zs[2 * (1 - rank)], zs[2 * (1 - rank) + 1], proj)
+    ref, _ = olosses.contrastive_distortion(zs[2 * rank], zs[2 * rank + 1], proj, rank=rank, other_tiles=[other],
+                                            temperature=0.01, logit_scale=torch.log(torch.tensor(1 / 0.07)), effective_batch_size=5000)
+    assert torch.allclose(d.detach().cpu(), ref, rtol=1e-4, atol=1e-5), (d, ref)
+    assert logs["n_negatives"] == 2 * 16 - 1
+    d.sum().backward()
+    params = [p for p in m.parameters() if p.grad is not None]
+    before = [p.grad.clone() for p in params]
+    allreduce_mean_(params)
+    g0 = [torch.zeros_like(b) for b in before]
+    for b, g in zip(before, g0):
+        t = b.clone()
+        dist.all_reduce(t)
+        g.copy_(t / world)
+    assert all(torch.allclose(p.grad, g) for p, g in zip(params, g0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpus(cuda_device):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_worker, args=(2, port, tmp), nprocs=2, join=True)
+        a = open(os.path.join(tmp, "sharded.bin"), "rb").read()
+        b = open(os.path.join(tmp, "single.bin"), "rb").read()
+        y = np.load(os.path.join(tmp, "y.npy"))
+    assert a == b
+    assert y.tolist() == [i % 7 for i in range(45)] and y.dtype == np.uint16
