@@ -81,13 +81,12 @@ class VisionTransformer(nn.Module):
         self.input_resolution, self.patch_size = input_resolution, patch_size
         self.width, self.layers, self.heads, self.output_dim = width, layers, heads, output_dim
         self.conv1 = _Conv(width, patch_size)
-        scale = width ** -0.5
-        self.class_embedding = nn.Parameter(scale * torch.randn(width))
-        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.class_embedding = nn.Parameter(torch.empty(width))
+        self.positional_embedding = nn.Parameter(torch.empty((input_resolution // patch_size) ** 2 + 1, width))
         self.ln_pre = _LayerNorm(width)
         self.transformer = _Transformer(width, layers)
         self.ln_post = _LayerNorm(width)
-        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self.proj = nn.Parameter(torch.empty(width, output_dim))
         self._native = None
         self.initialize_parameters()
 
@@ -99,6 +98,11 @@ class VisionTransformer(nn.Module):
         W, L = self.width, self.layers
         proj_std = (W ** -0.5) * ((2 * L) ** -0.5)
         attn_std, fc_std = W ** -0.5, (2 * W) ** -0.5
+        # every tensor comes from the seeded generator (never the global RNG): all ranks of a
+        # multi-GPU job must hold the same encoder
+        self.class_embedding.copy_(torch.randn(W, generator=g) * W ** -0.5)
+        self.positional_embedding.copy_(torch.randn(self.positional_embedding.shape, generator=g) * W ** -0.5)
+        self.proj.copy_(torch.randn(W, self.output_dim, generator=g) * W ** -0.5)
         self.conv1.weight.copy_(torch.randn(self.conv1.weight.shape, generator=g) * (3 * self.patch_size ** 2) ** -0.5)
         for blk in self.transformer.resblocks:
             blk.attn.in_proj_weight.copy_(torch.randn(3 * W, W, generator=g) * attn_std)
