@@ -18,6 +18,8 @@
 //               accumulator layout would otherwise scatter 16 B pieces over 32 lines per store).
 //               The residual tile arrives by TMA into the same staging buffer one group ahead.
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 #include "gemm_sm100.cuh"
 
@@ -388,8 +390,47 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
+// Tensor maps are pure functions of (pointer, shape, box): the encoder re-launches the same ~60 GEMMs on
+// the same workspace every pass, so the driver-side encode (~1-2 us each, 4 per GEMM) is cached.
+struct TmapKey {
+    const void *base;
+    int64_t d0, d1, d2;
+    int box_rows, dtype, rank;
+    bool operator==(const TmapKey &o) const
+    {
+        return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && box_rows == o.box_rows && dtype == o.dtype && rank == o.rank;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey &k) const
+    {
+        size_t h = reinterpret_cast<size_t>(k.base);
+        for (int64_t v : {k.d0, k.d1, k.d2, (int64_t)k.box_rows, (int64_t)k.dtype, (int64_t)k.rank}) h = h * 1000003u ^ (size_t)v;
+        return h;
+    }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mutex;
+
+static bool tmap_cache_get(const TmapKey &k, CUtensorMap *out)
+{
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    auto it = g_tmap_cache.find(k);
+    if (it == g_tmap_cache.end()) return false;
+    *out = it->second;
+    return true;
+}
+static void tmap_cache_put(const TmapKey &k, const CUtensorMap &m)
+{
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    if (g_tmap_cache.size() > 4096) g_tmap_cache.clear();
+    g_tmap_cache[k] = m;
+}
+
 int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, int64_t rows, int64_t K, int box_rows)
 {
+    const TmapKey key{base, K, rows, 1, box_rows, dtype, 2};
+    if (tmap_cache_get(key, map)) return LL_OK;
     EncodeTiledFn fn = encode_tiled_fn();
     if (fn == nullptr) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     LL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
@@ -402,11 +443,14 @@ int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, int64_t rows, in
     CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    tmap_cache_put(key, *map);
     return LL_OK;
 }
 
 int make_tmap_3d(CUtensorMap *map, const void *base, int dtype, int64_t batch, int64_t rows, int64_t cols, int box_rows)
 {
+    const TmapKey key{base, cols, rows, batch, box_rows, dtype, 3};
+    if (tmap_cache_get(key, map)) return LL_OK;
     EncodeTiledFn fn = encode_tiled_fn();
     if (fn == nullptr) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     LL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
@@ -419,6 +463,7 @@ int make_tmap_3d(CUtensorMap *map, const void *base, int dtype, int64_t batch, i
     CUresult r = fn(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+    tmap_cache_put(key, *map);
     return LL_OK;
 }
 

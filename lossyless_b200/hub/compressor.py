@@ -169,7 +169,7 @@ class ClipCompressor(nn.Module):
             z, bias=self.biasing, exp_scale=self._exp_scale(), mode=mode)
         return packed, offsets, lens
 
-    def compress_batch_to_host(self, X_host, out_host=None, sub_batch=256):
+    def compress_batch_to_host(self, X_host, out_host=None, sub_batch=378):
         """One step of the encode hot path with HOST buffers: (pinned) host images -> H2D -> ViT ->
         quantise + rANS -> container records -> D2H.  The batch is walked in sub-batches whose H2D
         copies run on a side stream, double-buffered against the ViT of the previous sub-batch, so
