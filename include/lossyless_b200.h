@@ -223,6 +223,22 @@ int ll_gemm_set_tile_n(int bn);
 /* CTA-pair (tcgen05 cta_group::2, 256-row tiles) policy: -1 automatic, 0 never, 1 always. */
 int ll_gemm_set_cta_pair(int mode);
 
+/* ------------------------------------------------------ device: CLIP preprocessing */
+
+/* uint8 images -> bicubic resize (Pillow's 8-bit ImagingResample, bit-exact) -> centre crop n_px ->
+ * /255 -> (x - mean) / std -> [B, 3, n_px, n_px] in out_dtype.
+ * replaces the CPU transform the reference's DataLoader applies before compress_dataset
+ * (clip `_transform` returned by clip.load, hub/compressor.py:39; utils/data/images.py:383-389).
+ *   img      uint8, layout 0: [B, H, W, 3] (PIL / numpy), layout 1: [B, 3, H, W]          (device)
+ *   coef_h   int32 [n_px, ksize_h], bounds_h int32 [n_px, 2] = (first input column, count) per output
+ *            column of the crop window; coef_v / bounds_v likewise for rows: Pillow's 22-bit
+ *            fixed-point coefficients, computed by the caller (lossyless_b200/preprocess.py)   (device)
+ *   mean3, std3  float[3] on the HOST;   tmp uint8 [B, H, n_px, 3] scratch                  (device) */
+int ll_clip_preprocess(const uint8_t *img, int64_t B, int H, int W, int layout, const int32_t *coef_h,
+                       const int32_t *bounds_h, int ksize_h, const int32_t *coef_v,
+                       const int32_t *bounds_v, int ksize_v, const float *mean3, const float *std3,
+                       int n_px, uint8_t *tmp, void *out, int out_dtype, ll_stream_t stream);
+
 /* ----------------------------------------------------------- device: distortions */
 
 /* Row-wise L2 normalisation (F.normalize, eps 1e-12) + zs_norm @ zs_norm^T tile, fp32.

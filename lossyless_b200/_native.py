@@ -72,6 +72,8 @@ _SIGNATURES = {
     "ll_gemm": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "ll_gemm_set_tile_n": (c_int, [c_int]),
     "ll_gemm_set_cta_pair": (c_int, [c_int]),
+    "ll_clip_preprocess": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, POINTER(c_float), POINTER(c_float),
+                                  c_int, _P, _P, c_int, _P]),
     "ll_contrastive_logits": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int, _P]),
     "ll_contrastive_logits_backward": (c_int, [_P, c_int, _P, _P, c_int, c_int, _P, _P]),
     "ll_contrastive_ce_forward": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, _P, _P, _P]),

@@ -171,14 +171,27 @@ class ClipCompressor(nn.Module):
 
     def compress_batch_to_host(self, X_host, out_host=None, sub_batch=378):
         """One step of the encode hot path with HOST buffers: (pinned) host images -> H2D -> ViT ->
-        quantise + rANS -> container records -> D2H.  The batch is walked in sub-batches whose H2D
+        quantise + rANS -> container records -> D2H.  ``X_host`` is either CLIP-normalised
+        [B,3,224,224] (fp16 / fp32, what the reference's transform yields) or raw uint8 pixels
+        [B,H,W,3] / [B,3,H,W], in which case resize + crop + normalise also run on the GPU
+        (bit-identical to the PIL / torchvision transform, lossyless_b200/preprocess.py).  The batch is walked in sub-batches whose H2D
         copies run on a side stream, double-buffered against the ViT of the previous sub-batch, so
         PCIe and the tensor cores overlap.  Returns (records: uint8 host view holding the batch's
         ``>I len + bytes`` records, n_images, the pinned output buffer for reuse)."""
         dev = torch.device(self.device)
         B = X_host.shape[0]
+        is_raw = X_host.dtype == torch.uint8  # raw pixels: CLIP preprocessing runs on the GPU as well
+        if is_raw:
+            chw = X_host.shape[1] == 3 and X_host.shape[-1] != 3
+            if getattr(self, "_gpu_preprocess", None) is None:
+                from ..preprocess import GpuClipPreprocess
+
+                self._gpu_preprocess = GpuClipPreprocess(224)
         if X_host.is_cuda:
-            X = X_host.half() if X_host.dtype == torch.float32 else X_host
+            if is_raw:
+                X = self._gpu_preprocess(X_host, chw=chw)
+            else:
+                X = X_host.half() if X_host.dtype == torch.float32 else X_host
             packed, offsets, _ = self._compress_records(X, mode=1)
         else:
             pipe = self._h2d_pipe(dev, X_host, sub_batch)
@@ -193,7 +206,10 @@ class ClipCompressor(nn.Module):
                     pipe["buf"][slot][: i1 - i0].copy_(X_host[i0:i1], non_blocking=True)
                     pipe["ready"][slot].record(pipe["stream"])
                 main.wait_event(pipe["ready"][slot])
-                self.clip(pipe["buf"][slot][: i1 - i0], out=z[i0:i1])
+                xs = pipe["buf"][slot][: i1 - i0]
+                if is_raw:
+                    xs = self._gpu_preprocess(xs, chw=chw)
+                self.clip(xs, out=z[i0:i1])
                 ev = torch.cuda.Event()
                 ev.record(main)
                 pipe["consumed"][slot] = ev
