@@ -89,6 +89,16 @@ int ll_eb_rans_encode(const void *z, int z_dtype, int64_t rows, int C, const flo
                       int cdf_stride, const int32_t *cdf_len, const int32_t *offset,
                       uint8_t *scratch, int32_t *lens, int32_t *symbols_out, ll_stream_t stream);
 
+/* Same kernel with a per-element table index and mean, for conditional priors:
+ * sym = rint(z_in - means[r,c]) coded with CDF row indexes[r,c] (indexes / means NULL: channel c / medians[c]).
+ * replaces compressai GaussianConditional.compress = EntropyModel.compress(inputs, indexes, means)
+ * (lossyless/rates.py:705: `self.gaussian_conditional.compress(z_in, indexes, means=means_hat)`). */
+int ll_rans_encode_indexed(const void *z, int z_dtype, int64_t rows, int C, const float *bias,
+                           const float *exp_scale, const float *medians, const int32_t *indexes,
+                           const float *means, const void *enc_table, int cdf_stride,
+                           const int32_t *cdf_len, const int32_t *offset, uint8_t *scratch,
+                           int32_t *lens, int32_t *symbols_out, ll_stream_t stream);
+
 /* Compacts the per-row streams into one buffer.  mode 0: raw concatenation (what
  * ClipCompressor.compress returns, one bytes object per row, hub/compressor.py:117-119);
  * mode 1: container records ">I len" + bytes exactly as compress_dataset writes them
@@ -112,6 +122,14 @@ int ll_rans_decode(const uint8_t *data, const int64_t *offsets, const int32_t *l
                    const int32_t *offset, const float *medians, const float *bias,
                    const float *exp_scale, float *z_hat, int32_t *symbols_out, int32_t *status,
                    ll_stream_t stream);
+
+/* per-element table index / mean variant (GaussianConditional.decompress, lossyless/rates.py:716-718) */
+int ll_rans_decode_indexed(const uint8_t *data, const int64_t *offsets, const int32_t *lens,
+                           int64_t rows, int C, const int32_t *cdf, int cdf_stride,
+                           const int32_t *cdf_len, const int32_t *offset, const float *medians,
+                           const int32_t *indexes, const float *means, const float *bias,
+                           const float *exp_scale, float *z_hat, int32_t *symbols_out,
+                           int32_t *status, ll_stream_t stream);
 
 /* ------------------------------------------------------- device: EntropyBottleneck */
 

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "ll_rans_stream_cap_bytes": (c_int, [c_int]),
     "ll_rans_build_enc_table": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "ll_eb_rans_encode": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
+    "ll_rans_encode_indexed": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
+    "ll_rans_decode_indexed": (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ll_rans_pack": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "ll_rans_decode": (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ll_eb_pack_params": (c_int, [POINTER(_P), POINTER(_P), POINTER(_P), c_int, _P, _P]),

@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from . import _native as N
 
-__all__ = ["EntropyBottleneck", "EntropyModel", "LowerBound", "update_registered_buffers"]
+__all__ = ["EntropyBottleneck", "GaussianConditional", "EntropyModel", "LowerBound", "update_registered_buffers"]
 
 
 class LowerBound(nn.Module):
@@ -140,6 +140,123 @@ class EntropyModel(nn.Module):
         return cdf
 
 
+    # -- entropy coding -----------------------------------------------------------------
+    def _coder_tables(self, device):
+        """Device-resident tables for the rANS kernels, cached until the CDF buffers change."""
+        self._check_cdf_size()
+        self._check_cdf_length()
+        self._check_offsets_size()
+        key = (self._quantized_cdf.data_ptr(), self._quantized_cdf._version, str(device))
+        if self._enc_cache is not None and self._enc_cache[0] == key:
+            return self._enc_cache[1]
+        cdf = self._quantized_cdf.to(device=device, dtype=torch.int32).contiguous()
+        cdf_len = self._cdf_length.to(device=device, dtype=torch.int32).contiguous()
+        offset = self._offset.to(device=device, dtype=torch.int32).contiguous()
+        C, stride = cdf.shape
+        enc = torch.empty(C * stride * 16, dtype=torch.uint8, device=device)
+        N.call("ll_rans_build_enc_table", N.ptr(cdf), N.ptr(cdf_len), C, stride, N.ptr(enc), N.stream())
+        tabs = dict(cdf=cdf, cdf_len=cdf_len, offset=offset, enc=enc, stride=stride)
+        self._enc_cache = (key, tabs)
+        return tabs
+
+    def _channel_means(self, device):
+        """Per-channel mean of the prior (the bottleneck's medians); conditional priors pass `means`."""
+        raise ValueError("this entropy model has no per-channel means: pass `means`")
+
+    def compress_to_device(self, z, bias=None, exp_scale=None, mode=0, want_symbols=False, indexes=None, means=None):
+        """Fused (process_z_in +) quantise + rANS encode + pack of z [rows, C] on the GPU.
+        Returns (packed uint8 [total], offsets int64 [rows+1], lens int32 [rows], symbols|None),
+        all device tensors.  mode 0 = raw concatenation, 1 = container records (">I len" + bytes).
+        ``indexes`` int32 [rows, C] / ``means`` float32 [rows, C] select a CDF row and a mean per element
+        (conditional priors); by default element c uses CDF row c and the prior's per-channel mean."""
+        N.require_cuda(z, "z")
+        if self.entropy_coder is None:
+            self.entropy_coder = _RansCoder()
+        z = z.contiguous()
+        rows, C = z.shape
+        if indexes is None and C != getattr(self, "channels", C):
+            raise ValueError(f"expected {self.channels} channels, got {C}")
+        t = self._coder_tables(z.device)
+        med = self._channel_means(z.device) if means is None else None
+        idx = indexes.to(torch.int32).contiguous() if indexes is not None else None
+        mu = means.detach().float().contiguous() if means is not None else None
+        if rows == 0:
+            return (torch.empty(0, dtype=torch.uint8, device=z.device), torch.zeros(1, dtype=torch.int64, device=z.device),
+                    torch.empty(0, dtype=torch.int32, device=z.device),
+                    torch.empty((0, C), dtype=torch.int32, device=z.device) if want_symbols else None)
+        cap = N.load().ll_rans_stream_cap_bytes(C)
+        scratch = torch.empty((rows, cap), dtype=torch.uint8, device=z.device)
+        lens = torch.empty(rows, dtype=torch.int32, device=z.device)
+        symbols = torch.empty((rows, C), dtype=torch.int32, device=z.device) if want_symbols else None
+        b = bias.detach().float().contiguous() if bias is not None else None
+        es = exp_scale.detach().float().contiguous() if exp_scale is not None else None
+        N.call("ll_rans_encode_indexed", N.ptr(z), N.dtype_code(z), rows, C, N.ptr(b), N.ptr(es), N.ptr(med), N.ptr(idx), N.ptr(mu),
+               N.ptr(t["enc"]), t["stride"], N.ptr(t["cdf_len"]), N.ptr(t["offset"]), N.ptr(scratch), N.ptr(lens),
+               N.ptr(symbols), N.stream())
+        packed = torch.empty(rows * (cap + 4) + 16, dtype=torch.uint8, device=z.device)
+        offsets = torch.empty(rows + 1, dtype=torch.int64, device=z.device)
+        N.call("ll_rans_pack", N.ptr(scratch), N.ptr(lens), rows, cap, mode, N.ptr(packed), N.ptr(offsets), N.stream())
+        return packed, offsets, lens, symbols
+
+    def decompress_from_device(self, data, offsets, lens, bias=None, exp_scale=None, want_symbols=False, indexes=None, means=None):
+        """Batched decode of streams stored in a device byte buffer -> (z_hat [rows,C] fp32,
+        symbols|None).  Raises ValueError if any stream is malformed."""
+        N.require_cuda(data, "data")
+        if self.entropy_coder is None:
+            self.entropy_coder = _RansCoder()
+        t = self._coder_tables(data.device)
+        rows = lens.numel()
+        C = indexes.shape[1] if indexes is not None else self.channels
+        med = self._channel_means(data.device) if means is None else None
+        idx = indexes.to(torch.int32).contiguous() if indexes is not None else None
+        mu = means.detach().float().contiguous() if means is not None else None
+        if rows == 0:
+            return torch.empty((0, C), dtype=torch.float32, device=data.device), None
+        z_hat = torch.empty((rows, C), dtype=torch.float32, device=data.device)
+        status = torch.empty(rows, dtype=torch.int32, device=data.device)
+        symbols = torch.empty((rows, C), dtype=torch.int32, device=data.device) if want_symbols else None
+        b = bias.detach().float().contiguous() if bias is not None else None
+        es = exp_scale.detach().float().contiguous() if exp_scale is not None else None
+        N.call("ll_rans_decode_indexed", N.ptr(data), N.ptr(offsets), N.ptr(lens), rows, C, N.ptr(t["cdf"]), t["stride"],
+               N.ptr(t["cdf_len"]), N.ptr(t["offset"]), N.ptr(med), N.ptr(idx), N.ptr(mu), N.ptr(b), N.ptr(es), N.ptr(z_hat),
+               N.ptr(symbols), N.ptr(status), N.stream())
+        bad = int(status.sum().item())
+        if bad:
+            raise ValueError(f"{bad} of {rows} rANS streams are truncated or corrupt")
+        return z_hat, symbols
+
+    @staticmethod
+    def _strings_to_device(strings, device):
+        """list of bytes -> (device byte buffer, offsets int64 [n+1], lens int32 [n]); validates lengths."""
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        lens_np = np.fromiter((len(s) for s in strings), dtype=np.int32, count=len(strings))
+        if (lens_np % 4 != 0).any() or (lens_np < 8).any():
+            raise ValueError("rANS streams must be >= 8 bytes and a multiple of 4 bytes long")
+        off_np = np.zeros(len(strings) + 1, dtype=np.int64)
+        np.cumsum(lens_np, out=off_np[1:])
+        data = torch.frombuffer(bytearray(b"".join(strings)) + bytearray(16), dtype=torch.uint8).to(device)
+        return data, torch.from_numpy(off_np).to(device), torch.from_numpy(lens_np).to(device)
+
+    @staticmethod
+    def _device_to_strings(packed, offsets):
+        off = offsets.cpu().numpy()
+        buf = packed[: int(off[-1])].cpu().numpy().tobytes()
+        return [buf[off[i]: off[i + 1]] for i in range(len(off) - 1)]
+
+
+    # -- checkpoint compatibility ---------------------------------------------------------
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # the CDF buffers are dynamically sized: adopt the checkpoint's shapes (policy "resize")
+        for name in ("_quantized_cdf", "_offset", "_cdf_length", "scale_table"):
+            key = prefix + name
+            if key in state_dict and hasattr(self, name):
+                cur = getattr(self, name)
+                setattr(self, name, torch.empty(state_dict[key].shape, dtype=cur.dtype, device=cur.device))
+        self._enc_cache = None
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
 class EntropyBottleneck(EntropyModel):
     """compressai.entropy_models.EntropyBottleneck (Balle et al. 2018 factorised prior)."""
 
@@ -174,6 +291,9 @@ class EntropyBottleneck(EntropyModel):
 
     def _get_medians(self):
         return self.quantiles[:, :, 1:2]
+
+    def _channel_means(self, device):
+        return self._get_medians().detach().reshape(-1).float().to(device).contiguous()
 
     def _logits_cumulative(self, inputs, stop_gradient):
         """Plain torch: used by update() (load time) and loss() (3 points per channel)."""
@@ -255,56 +375,6 @@ class EntropyBottleneck(EntropyModel):
             out, lik = out.reshape(shape), lik.reshape(shape)
         return out, lik
 
-    # -- entropy coding -----------------------------------------------------------------
-    def _coder_tables(self, device):
-        """Device-resident tables for the rANS kernels, cached until the CDF buffers change."""
-        self._check_cdf_size()
-        self._check_cdf_length()
-        self._check_offsets_size()
-        key = (self._quantized_cdf.data_ptr(), self._quantized_cdf._version, str(device))
-        if self._enc_cache is not None and self._enc_cache[0] == key:
-            return self._enc_cache[1]
-        cdf = self._quantized_cdf.to(device=device, dtype=torch.int32).contiguous()
-        cdf_len = self._cdf_length.to(device=device, dtype=torch.int32).contiguous()
-        offset = self._offset.to(device=device, dtype=torch.int32).contiguous()
-        C, stride = cdf.shape
-        enc = torch.empty(C * stride * 16, dtype=torch.uint8, device=device)
-        N.call("ll_rans_build_enc_table", N.ptr(cdf), N.ptr(cdf_len), C, stride, N.ptr(enc), N.stream())
-        tabs = dict(cdf=cdf, cdf_len=cdf_len, offset=offset, enc=enc, stride=stride,
-                    medians=self._get_medians().detach().reshape(-1).float().to(device).contiguous())
-        self._enc_cache = (key, tabs)
-        return tabs
-
-    def compress_to_device(self, z, bias=None, exp_scale=None, mode=0, want_symbols=False):
-        """Fused (process_z_in +) quantise + rANS encode + pack of z [rows, C] on the GPU.
-        Returns (packed uint8 [total], offsets int64 [rows+1], lens int32 [rows], symbols|None),
-        all device tensors.  mode 0 = raw concatenation, 1 = container records (">I len" + bytes)."""
-        N.require_cuda(z, "z")
-        if self.entropy_coder is None:
-            self.entropy_coder = _RansCoder()
-        z = z.contiguous()
-        rows, C = z.shape
-        if C != self.channels:
-            raise ValueError(f"expected {self.channels} channels, got {C}")
-        t = self._coder_tables(z.device)
-        if rows == 0:
-            return (torch.empty(0, dtype=torch.uint8, device=z.device), torch.zeros(1, dtype=torch.int64, device=z.device),
-                    torch.empty(0, dtype=torch.int32, device=z.device),
-                    torch.empty((0, C), dtype=torch.int32, device=z.device) if want_symbols else None)
-        cap = N.load().ll_rans_stream_cap_bytes(C)
-        scratch = torch.empty((rows, cap), dtype=torch.uint8, device=z.device)
-        lens = torch.empty(rows, dtype=torch.int32, device=z.device)
-        symbols = torch.empty((rows, C), dtype=torch.int32, device=z.device) if want_symbols else None
-        b = bias.detach().float().contiguous() if bias is not None else None
-        es = exp_scale.detach().float().contiguous() if exp_scale is not None else None
-        N.call("ll_eb_rans_encode", N.ptr(z), N.dtype_code(z), rows, C, N.ptr(b), N.ptr(es), N.ptr(t["medians"]),
-               N.ptr(t["enc"]), t["stride"], N.ptr(t["cdf_len"]), N.ptr(t["offset"]), N.ptr(scratch), N.ptr(lens),
-               N.ptr(symbols), N.stream())
-        packed = torch.empty(rows * (cap + 4) + 16, dtype=torch.uint8, device=z.device)
-        offsets = torch.empty(rows + 1, dtype=torch.int64, device=z.device)
-        N.call("ll_rans_pack", N.ptr(scratch), N.ptr(lens), rows, cap, mode, N.ptr(packed), N.ptr(offsets), N.stream())
-        return packed, offsets, lens, symbols
-
     def compress(self, x, bias=None, exp_scale=None):
         """x: [B, C, 1, 1] or [B, C] (already ``process_z_in``-ed unless bias / exp_scale are
         given, in which case that affine map is fused into the kernel) -> list of B bytes."""
@@ -315,62 +385,137 @@ class EntropyBottleneck(EntropyModel):
         elif x.dim() != 2:
             raise ValueError("Invalid `inputs` size. Expected a 4-D tensor.")
         packed, offsets, _, _ = self.compress_to_device(x, bias, exp_scale, mode=0)
-        off = offsets.cpu().numpy()
-        buf = packed[: int(off[-1])].cpu().numpy().tobytes()
-        return [buf[off[i]: off[i + 1]] for i in range(len(off) - 1)]
-
-    def decompress_from_device(self, data, offsets, lens, bias=None, exp_scale=None, want_symbols=False):
-        """Batched decode of streams stored in a device byte buffer -> (z_hat [rows,C] fp32,
-        symbols|None).  Raises ValueError if any stream is malformed."""
-        N.require_cuda(data, "data")
-        if self.entropy_coder is None:
-            self.entropy_coder = _RansCoder()
-        t = self._coder_tables(data.device)
-        rows, C = lens.numel(), self.channels
-        if rows == 0:
-            return torch.empty((0, C), dtype=torch.float32, device=data.device), None
-        z_hat = torch.empty((rows, C), dtype=torch.float32, device=data.device)
-        status = torch.empty(rows, dtype=torch.int32, device=data.device)
-        symbols = torch.empty((rows, C), dtype=torch.int32, device=data.device) if want_symbols else None
-        b = bias.detach().float().contiguous() if bias is not None else None
-        es = exp_scale.detach().float().contiguous() if exp_scale is not None else None
-        N.call("ll_rans_decode", N.ptr(data), N.ptr(offsets), N.ptr(lens), rows, C, N.ptr(t["cdf"]), t["stride"],
-               N.ptr(t["cdf_len"]), N.ptr(t["offset"]), N.ptr(t["medians"]), N.ptr(b), N.ptr(es), N.ptr(z_hat),
-               N.ptr(symbols), N.ptr(status), N.stream())
-        bad = int(status.sum().item())
-        if bad:
-            raise ValueError(f"{bad} of {rows} rANS streams are truncated or corrupt")
-        return z_hat, symbols
+        return self._device_to_strings(packed, offsets)
 
     def decompress(self, strings, size=(1, 1), bias=None, exp_scale=None):
         """list of bytes -> [B, C, 1, 1] float32 (compressai layout)."""
         if tuple(size) != (1, 1):
             raise ValueError("only 1x1 spatial latents are supported")
-        if not isinstance(strings, (tuple, list)):
-            raise ValueError("Invalid `strings` parameter type.")
         device = self._quantized_cdf.device
         if device.type != "cuda":
             raise N.NativeError("EntropyBottleneck.decompress needs the module on a B200 (cuda); there is no CPU path")
-        lens_np = np.fromiter((len(s) for s in strings), dtype=np.int32, count=len(strings))
-        if (lens_np % 4 != 0).any() or (lens_np < 8).any():
-            raise ValueError("rANS streams must be >= 8 bytes and a multiple of 4 bytes long")
-        off_np = np.zeros(len(strings) + 1, dtype=np.int64)
-        np.cumsum(lens_np, out=off_np[1:])
-        data = torch.frombuffer(bytearray(b"".join(strings)) + bytearray(16), dtype=torch.uint8).to(device)
-        z_hat, _ = self.decompress_from_device(data, torch.from_numpy(off_np).to(device),
-                                               torch.from_numpy(lens_np).to(device), bias, exp_scale)
+        data, off, lens = self._strings_to_device(strings, device)
+        z_hat, _ = self.decompress_from_device(data, off, lens, bias, exp_scale)
         return z_hat.reshape(len(strings), self.channels, 1, 1)
 
-    # -- checkpoint compatibility ---------------------------------------------------------
-    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
-        # the CDF buffers are dynamically sized: adopt the checkpoint's shapes (policy "resize")
-        for name in ("_quantized_cdf", "_offset", "_cdf_length"):
-            key = prefix + name
-            if key in state_dict:
-                setattr(self, name, torch.empty(state_dict[key].shape, dtype=torch.int32,
-                                                device=getattr(self, name).device))
+
+
+class GaussianConditional(EntropyModel):
+    """compressai.entropy_models.GaussianConditional: Gaussian prior whose per-element scale (and mean)
+    is predicted from side information (Balle et al. 2018 / Minnen et al. 2018).  Used by the reference's
+    scale-hyperprior rate (lossyless/rates.py:571-756).
+
+    ``update_scale_table`` builds one integer CDF per scale level at load time (float32 CPU ops in
+    compressai's op order + the library's host pmf->CDF function); ``compress`` / ``decompress`` are the
+    batched rANS kernels with a per-element table index and mean.  The likelihood is a handful of
+    elementwise torch ops (erfc), differentiable by autograd -- it is not on the encode path."""
+
+    def __init__(self, scale_table, *args, scale_bound=0.11, tail_mass=1e-9, **kwargs):
+        super().__init__(*args, **kwargs)
+        if not isinstance(scale_table, (type(None), list, tuple)):
+            raise ValueError(f'Invalid type for scale_table "{type(scale_table)}"')
+        if isinstance(scale_table, (list, tuple)) and len(scale_table) < 1:
+            raise ValueError(f'Invalid scale_table length "{len(scale_table)}"')
+        if scale_table and (scale_table != sorted(scale_table) or any(s <= 0 for s in scale_table)):
+            raise ValueError(f'Invalid scale_table "({scale_table})"')
+        self.tail_mass = float(tail_mass)
+        if scale_bound is None and scale_table:
+            scale_bound = scale_table[0]
+        if scale_bound <= 0:
+            raise ValueError("Invalid parameters")
+        self.lower_bound_scale = LowerBound(scale_bound)
+        self.register_buffer("scale_table", self._prepare_scale_table(scale_table) if scale_table else torch.Tensor())
+        self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]) if scale_bound is not None else None)
+
+    @staticmethod
+    def _prepare_scale_table(scale_table):
+        return torch.Tensor(tuple(float(s) for s in scale_table))
+
+    @staticmethod
+    def _standardized_cumulative(inputs):
+        # the complementary error function maximises numerical precision
+        return 0.5 * torch.erfc(-(2 ** -0.5) * inputs)
+
+    @staticmethod
+    def _standardized_quantile(quantile):
+        import scipy.stats
+
+        return scipy.stats.norm.ppf(quantile)
+
+    def update_scale_table(self, scale_table, force=False):
+        if self._offset.numel() > 0 and not force:
+            return False
+        device = self.scale_table.device
+        self.scale_table = self._prepare_scale_table(scale_table).to(device)
+        self.update()
+        return True
+
+    def update(self):
+        dev = self.scale_table.device
+        with torch.no_grad():
+            table = self.scale_table.detach().float().cpu()
+            multiplier = -self._standardized_quantile(self.tail_mass / 2)
+            pmf_center = torch.ceil(table * multiplier).int()
+            pmf_length = 2 * pmf_center + 1
+            max_length = int(torch.max(pmf_length).item())
+            samples = torch.abs(torch.arange(max_length).int() - pmf_center[:, None]).float()
+            samples_scale = table.unsqueeze(1).float()
+            upper = self._standardized_cumulative((0.5 - samples) / samples_scale)
+            lower = self._standardized_cumulative((-0.5 - samples) / samples_scale)
+            pmf = upper - lower
+            tail_mass = 2 * lower[:, :1]
+            cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
+        self._quantized_cdf = cdf.to(dev)
+        self._offset = (-pmf_center).to(dev)
+        self._cdf_length = (pmf_length + 2).to(dev)
         self._enc_cache = None
-        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def _likelihood(self, inputs, scales, means=None):
+        values = inputs - means if means is not None else inputs
+        scales = self.lower_bound_scale(scales)
+        values = torch.abs(values)
+        upper = self._standardized_cumulative((0.5 - values) / scales)
+        lower = self._standardized_cumulative((-0.5 - values) / scales)
+        return upper - lower
+
+    def forward(self, inputs, scales, means=None, training=None, noise=None):
+        if training is None:
+            training = self.training
+        if training:
+            outputs = inputs + (noise if noise is not None else torch.empty_like(inputs).uniform_(-0.5, 0.5))
+        else:
+            outputs = self.quantize(inputs, "dequantize", means)
+        likelihood = self._likelihood(outputs, scales, means)
+        if self.use_likelihood_bound:
+            likelihood = self.likelihood_lower_bound(likelihood)
+        return outputs, likelihood
+
+    def build_indexes(self, scales):
+        scales = self.lower_bound_scale(scales)
+        indexes = scales.new_full(scales.size(), len(self.scale_table) - 1).int()
+        for s in self.scale_table[:-1]:
+            indexes -= (scales <= s).int()
+        return indexes
+
+    def compress(self, inputs, indexes, means=None, bias=None, exp_scale=None):
+        """inputs / indexes / means: [B, C, 1, 1] or [B, C] -> list of B bytes."""
+        B = inputs.shape[0]
+        x, idx = inputs.reshape(B, -1), indexes.reshape(B, -1)
+        mu = means.reshape(B, -1) if means is not None else torch.zeros_like(x, dtype=torch.float32)
+        packed, offsets, _, _ = self.compress_to_device(x, bias, exp_scale, mode=0, indexes=idx, means=mu)
+        return self._device_to_strings(packed, offsets)
+
+    def decompress(self, strings, indexes, means=None, bias=None, exp_scale=None):
+        """-> float32 tensor shaped like ``indexes`` (symbols + means)."""
+        device = self._quantized_cdf.device
+        if device.type != "cuda":
+            raise N.NativeError("GaussianConditional.decompress needs the module on a B200 (cuda); there is no CPU path")
+        B = len(strings)
+        idx = indexes.reshape(B, -1)
+        mu = means.reshape(B, -1) if means is not None else torch.zeros(idx.shape, dtype=torch.float32, device=device)
+        data, off, lens = self._strings_to_device(strings, device)
+        z_hat, _ = self.decompress_from_device(data, off, lens, bias, exp_scale, indexes=idx, means=mu)
+        return z_hat.reshape(indexes.shape)
 
 
 class _CpuParams:

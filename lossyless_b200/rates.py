@@ -4,8 +4,9 @@ On the hot path (SURVEY.md section 8a-4/4'/5/6): ``get_rate_estimator`` (:29-49)
 ``EntropyBottleneck`` wrapper (:55-71), ``RateEstimator`` (:75-314), ``HRateEstimator``
 (:398-506) and ``HRateFactorizedPrior`` (:509-564).  ``forward`` is one fused launch
 (process_z_in -> noise/round -> likelihood -> -log q row sum -> process_z_out) with a fused
-backward; ``compress`` / ``decompress`` are the batched rANS kernels.  ``lossless``, ``H_hyper``,
-``H_spatial`` and ``MI`` are "next" rows (section 8f) and raise NotImplementedError.
+backward; ``compress`` / ``decompress`` are the batched rANS kernels.  ``HRateHyperprior`` (:571-756, the
+first "next" row of section 8f) is built on the same kernels (side bottleneck + indexed rANS for the
+Gaussian conditional).  ``lossless``, ``H_spatial`` and ``MI`` raise NotImplementedError.
 """
 import math
 
@@ -15,15 +16,18 @@ import torch.nn as nn
 from . import entropy_models as em
 from .helpers import BASE_LOG, OrderedSet, Timer, atleast_ndim, mean, weights_init
 
-__all__ = ["get_rate_estimator", "EntropyBottleneck", "RateEstimator", "HRateEstimator", "HRateFactorizedPrior"]
+__all__ = ["get_rate_estimator", "EntropyBottleneck", "RateEstimator", "HRateEstimator", "HRateFactorizedPrior",
+           "HRateHyperprior", "get_scale_table"]
 
 
 def get_rate_estimator(mode, z_dim=None, p_ZlX=None, **kwargs):
     """Return the correct entropy coder."""
     if mode == "H_factorized":
         return HRateFactorizedPrior(z_dim, **kwargs)
-    if mode in ("lossless", "H_hyper", "H_spatial", "MI"):
-        raise NotImplementedError(f"rate estimator {mode!r} is a 'next' row of SURVEY.md section 8f; only H_factorized is built")
+    if mode == "H_hyper":
+        return HRateHyperprior(z_dim, **kwargs)
+    if mode in ("lossless", "H_spatial", "MI"):
+        raise NotImplementedError(f"rate estimator {mode!r} is a 'next' row of SURVEY.md section 8f; H_factorized and H_hyper are built")
     raise ValueError(f"Unkown rate estimator={mode}.")
 
 
@@ -108,6 +112,8 @@ class RateEstimator(nn.Module):
         for m in self.children():
             if isinstance(m, em.EntropyBottleneck):
                 updated &= m.update(force=force)
+            elif isinstance(m, em.GaussianConditional):
+                updated &= m.update_scale_table(get_scale_table().tolist(), force=force)
         return updated
 
     def prepare_compressor_(self):
@@ -199,3 +205,86 @@ class HRateFactorizedPrior(HRateEstimator):
     def decompress(self, all_strings):
         assert isinstance(all_strings, list) and len(all_strings) == 1
         return self.entropy_bottleneck.decompress(all_strings[0], bias=self.biasing, exp_scale=self.codec_exp_scale())
+
+
+def get_scale_table(min=0.11, max=256, levels=64):
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+class HRateHyperprior(HRateEstimator):
+    """Scale (and mean) hyperprior rate (Balle et al. 2018; Minnen et al. 2018), reference
+    lossyless/rates.py:571-756: side information ``s = side_encoder(z_in)`` is coded with a factorised
+    bottleneck, ``z_encoder(s_hat)`` predicts per-dimension Gaussian scales (and means) under which z is
+    coded; the rate is ``-log q(s) - log q(z|s)``.  Two rANS streams per image.
+
+    The reference's compress path overwrites ``means_hat`` with ``scales_hat`` (rates.py:691-692), which
+    makes its real bit-rate far larger than its entropy estimate; that defect is not reproduced: the
+    predicted means are used for coding exactly as in ``forward_help``."""
+
+    def __init__(self, z_dim, factor_dim=5, side_z_dim=None, is_pred_mean=True, **kwargs):
+        super().__init__(z_dim, **kwargs)
+        if side_z_dim is None:
+            side_z_dim = max(10, self.z_dim // factor_dim)
+        self.side_z_dim, self.is_pred_mean = side_z_dim, is_pred_mean
+        self.entropy_bottleneck = EntropyBottleneck(side_z_dim, **self.kwargs_ent_bottleneck)
+        self.gaussian_conditional = em.GaussianConditional(None)
+        self.side_encoder, self.z_encoder = self.get_encoders()
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.side_encoder.reset_parameters()
+        self.z_encoder.reset_parameters()
+        self.scaling = torch.nn.Parameter(torch.ones(self.z_dim))
+        self.biasing = torch.nn.Parameter(torch.zeros(self.z_dim))
+
+    def get_encoders(self):
+        from .architectures import MLP
+
+        kwargs_mlp = dict(n_hid_layers=2, hid_dim=max(self.z_dim, 256))
+        side_encoder = MLP(self.z_dim, self.side_z_dim, **kwargs_mlp)
+        z_encoder = MLP(self.side_z_dim, self.z_dim * (2 if self.is_pred_mean else 1), **kwargs_mlp)
+        return side_encoder, z_encoder
+
+    def chunk_params(self, gaussian_params):
+        if self.is_pred_mean:
+            return gaussian_params.chunk(2, -1)
+        return gaussian_params, None
+
+    def forward_help(self, z, _, __, noise=None):
+        z_in = self.process_z_in(z)
+        side_z = self.side_encoder(z_in)
+        nz_side = noise[1] if noise is not None else None
+        side_z_hat, q_s = self.entropy_bottleneck(side_z, noise=nz_side)
+        scales_hat, means_hat = self.chunk_params(self.z_encoder(side_z_hat))
+        z_hat, q_zls = self.gaussian_conditional(z_in, scales_hat, means=means_hat, noise=noise[0] if noise is not None else None)
+        neg_log_q_s = -torch.log(q_s).sum(-1)
+        neg_log_q_zls = -torch.log(q_zls).sum(-1)
+        neg_log_q_zs = neg_log_q_s + neg_log_q_zls
+        logs = dict(H_q_ZlS=neg_log_q_zls.mean() / math.log(BASE_LOG), H_q_Z=neg_log_q_zs.mean() / math.log(BASE_LOG),
+                    H_q_S=neg_log_q_s.mean() / math.log(BASE_LOG), H_ZlX=0)
+        if self.is_compute_real_rate:
+            n_bits, logs2 = self.real_rate(z, is_return_logs=True)
+            logs.update(logs2)
+            logs["n_bits"] = n_bits
+        return self.process_z_out(z_hat), neg_log_q_zs, logs, dict()
+
+    def get_indexes_means_hat(self, side_z_strings):
+        side_z_hat = self.entropy_bottleneck.decompress(side_z_strings)
+        scales_hat, means_hat = self.chunk_params(self.z_encoder(side_z_hat))
+        return self.gaussian_conditional.build_indexes(scales_hat), means_hat
+
+    @torch.no_grad()
+    def compress(self, z, parent=None):
+        z_in = self.process_z_in(z)
+        side_z_strings = self.entropy_bottleneck.compress(self.side_encoder(z_in))
+        indexes, means_hat = self.get_indexes_means_hat(side_z_strings)
+        z_strings = self.gaussian_conditional.compress(z_in, indexes, means=means_hat)
+        return [z_strings, side_z_strings]
+
+    @torch.no_grad()
+    def decompress(self, all_strings):
+        assert isinstance(all_strings, list) and len(all_strings) == 2
+        z_strings, side_z_strings = all_strings
+        indexes, means_hat = self.get_indexes_means_hat(side_z_strings)
+        z_hat = self.gaussian_conditional.decompress(z_strings, indexes, means=means_hat)
+        return self.process_z_out(z_hat)

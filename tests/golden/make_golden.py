@@ -110,3 +110,27 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def gaussian_golden():
+    """GaussianConditional tables for the reference's 64-level scale table + an indexed-rANS vector."""
+    from oracle import gaussian as og
+
+    tab = og.update(og.get_scale_table())
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(6, 512, generator=g) * 6
+    means = torch.randn(6, 512, generator=g)
+    scales = torch.rand(6, 512, generator=g) * 5 + 0.02
+    x[4] *= 40  # escapes far outside the narrow tables
+    scales[5] = 200.0  # widest tables (3133 entries)
+    idx = og.build_indexes(scales, og.get_scale_table())
+    strings, sym = og.compress(x, idx, means, tab)
+    np.savez_compressed(os.path.join(OUT, "gaussian_conditional.npz"), cdf=tab["cdf"], cdf_length=tab["cdf_length"], offset=tab["offset"],
+                        x=x.numpy(), means=means.numpy(), scales=scales.numpy(), indexes=idx.numpy(), symbols=sym,
+                        lens=np.array([len(s) for s in strings], dtype=np.int32), bytes=np.frombuffer(b"".join(strings), dtype=np.uint8))
+
+
+if __name__ == "__main__":
+    gaussian_golden()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -20,6 +20,7 @@ for s in $STAGES; do
     vit)   run vit 300 python -m pytest tests/test_vit_gpu.py -m gpu -q ;;
     eb)    run eb 300 python -m pytest tests/test_eb_gpu.py -m gpu -q ;;
     dist)  run dist 300 python -m pytest tests/test_distortion_gpu.py tests/test_training_gpu.py -m gpu -q ;;
+    hyper) run hyper 300 python -m pytest tests/test_hyperprior.py -m gpu -q ;;
     prep)  run prep 300 python -m pytest tests/test_preprocess_gpu.py -m gpu -q ;;
     hub)   run hub 300 python -m pytest tests/test_hub_gpu.py -m gpu -q ;;
     all)   run all 900 python -m pytest tests -m gpu -x -q ;;
