@@ -108,10 +108,6 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
-if __name__ == "__main__":
-    main()
-
-
 def gaussian_golden():
     """GaussianConditional tables for the reference's 64-level scale table + an indexed-rANS vector."""
     from oracle import gaussian as og
@@ -132,5 +128,4 @@ def gaussian_golden():
 
 if __name__ == "__main__":
     gaussian_golden()
-    for f in sorted(os.listdir(OUT)):
-        print(f, os.path.getsize(os.path.join(OUT, f)))
+    main()
