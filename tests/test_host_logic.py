@@ -80,3 +80,18 @@ def test_vit_requires_cuda(native_lib):
     vit = VisionTransformer(224, 32, 768, 2, 12, 512)
     with pytest.raises(NativeError, match="no CPU fallback"):
         vit(torch.zeros(1, 3, 224, 224))
+
+
+def test_downstream_linear_eval_runs():
+    """tools/z_linear_eval.py (README.md:66-74 / utils/Z_linear_eval.py recipe) on separable synthetic Z."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("z_linear_eval", os.path.join(ROOT, "tools", "z_linear_eval.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(0)
+    centers = rng.normal(size=(5, 512)) * 2
+    Y = rng.integers(0, 5, 600)
+    Z = (centers[Y] + rng.normal(size=(600, 512))).astype(np.float32)
+    res = mod.linear_eval(Z[:400], Y[:400], Z[400:], Y[400:])
+    assert res["test/pred/acc"] > 0.95 and abs(res["test/pred/err"] - (1 - res["test/pred/acc"])) < 1e-12
