@@ -37,6 +37,7 @@ for s in $STAGES; do
              run pair756_bn256 200 env LL_PAIR=1 LL_BN=256 LL_GEMM_ONLY=1 python tools/gemm_bench.py 756 ;;
     epidbg) for d in 0 0x100 0x1100 0x300 0x700 0xf00 0x1f00; do run epidbg_$d 200 env LL_DBG=$d LL_PAIR=1 LL_BN=256 LL_GEMM_ONLY=1 python tools/gemm_bench.py 378; done ;;
     bnsweep) for bn in 128 192; do run pair378_bn$bn 200 env LL_PAIR=1 LL_BN=$bn LL_GEMM_ONLY=1 python tools/gemm_bench.py 378; done ;;
+    ncu_vit) run ncu_vit 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 50 -c 50 -f -o gpurun_out/prof_vit_gemms python tools/vit_once.py ;;
     ncu_small) run ncu_small 600 ncu --set full --clock-control none --import-source on -k regex:"attention" -s 10 -c 2 -f -o gpurun_out/prof_small python tools/gemm_bench.py 378 ;;
     ncu_gemm) run ncu_gemm 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 8 -c 5 -f -o gpurun_out/prof_gemm python tools/gemm_bench.py 256 ;;
     ncu_list) run ncu_list 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --batch 378 --no-cpu-baseline ;;
