@@ -8,7 +8,7 @@ One "step" = one batch of synthetic CLIP-normalised 3x224x224 fp16 images throug
 i.e. the body of the reference's ``compress_dataset`` loop (hub/compressor.py:186-189).
 Prints ONE JSON line on rank 0 (contract in the task statement):
   value     images/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e       same metric through ``ClipCompressor.compress_batch_to_host`` with pinned HOST
+  e2e       same metric through ``ClipCompressor.compress_stream`` (compress_dataset's loop) with pinned HOST
             buffers: H2D of the images and D2H of the records inside the timed region
   roofline  the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / event-timed GEMM time,
             against the measured bf16 peak in MEASURED_PEAKS.json
@@ -170,6 +170,17 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (average over one block's four GEMMs) from the
+    committed ncu --set full capture; None if the summary is not in the tree."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_vit_gemms_dram_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["per_launch_dram_bytes_layer_average"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,6 +191,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="images per internal ViT pass (0 = library default)")
     ap.add_argument("--cpu-images", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse-ln", action="store_true", help="A/B: run ln_1 / ln_2 as separate kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -224,6 +236,8 @@ def main():
     comp, _ = hubconf.clip_compressor_b005(device=f"cuda:{local_rank}")
     if args.chunk:
         comp.clip.set_chunk(args.chunk)
+    if args.no_fuse_ln:
+        comp.clip.set_fuse_layernorm(False)
     B = args.batch
     # encode shards by image: every rank codes its own independent batch, no collective on the path
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -251,27 +265,40 @@ def main():
         ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- e2e: pinned host images in, container records out, per step
+    # ---- e2e: pinned host images in, container records out, per step, through compress_dataset's own loop
+    # (ClipCompressor.compress_stream: batch i+1 is enqueued before the host waits for batch i's records; every
+    # step's H2D copy and records D2H happen inside the timed region)
+    def e2e_run(x_host, steps):
+        n = 0
+        for rec, b in comp.compress_stream(x_host for _ in range(steps)):
+            n += b
+        return n
+
+    e2e_run(X_host, 2)
+    barrier()
+    t0 = time.perf_counter()
+    n_done = e2e_run(X_host, args.steps)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert n_done == B * args.steps
+    e2e = world * B * args.steps / e2e_s
+    # the same, one blocking call per batch (no overlap across batches)
     pinned_out = None
-    for _ in range(2):
-        _, _, pinned_out = comp.compress_batch_to_host(X_host, pinned_out)
+    _, _, pinned_out = comp.compress_batch_to_host(X_host, pinned_out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         rec, _, pinned_out = comp.compress_batch_to_host(X_host, pinned_out)
     barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = world * B * args.steps / e2e_s
+    e2e_blocking = world * B * args.steps / max_over_ranks(time.perf_counter() - t0)
 
     # ---- e2e from raw pixels: STL10-shaped uint8 images (BASELINE config 2) -> H2D of the bytes -> GPU CLIP
     # preprocessing (PIL-exact bicubic 96 -> 224, normalise) -> ViT -> codec -> records D2H
     raw_host = torch.randint(0, 256, (B, 96, 96, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(rank)).pin_memory()
-    for _ in range(2):
-        _, _, pinned_out = comp.compress_batch_to_host(raw_host, pinned_out)
+    e2e_run(raw_host, 2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        _, _, pinned_out = comp.compress_batch_to_host(raw_host, pinned_out)
+    e2e_run(raw_host, args.steps)
     barrier()
     e2e_raw = world * B * args.steps / max_over_ranks(time.perf_counter() - t0)
 
@@ -292,12 +319,14 @@ def main():
                    "l2": f"inputs {B * 3 * 224 * 224 * 2 / 1e6:.0f} MB/step > 126 MB L2, no flush needed",
                    "bits_per_img": bits_per_img, "sharding": "independent images per rank, no collective"},
         "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 2, "d2h_bytes_per_step": total_bytes + 8,
-                "input": "pinned host fp16 [B,3,224,224] CLIP-normalised tensors (what the reference's loop body receives)"},
+                "input": "pinned host fp16 [B,3,224,224] CLIP-normalised tensors (what the reference's loop body receives)",
+                "api": "ClipCompressor.compress_stream (compress_dataset's loop)", "blocking_per_batch_call": e2e_blocking},
         "e2e_raw_uint8": {"value": e2e_raw, "unit": "img/s", "h2d_bytes_per_step": B * 96 * 96 * 3,
                           "input": "pinned host uint8 [B,96,96,3] STL10-shaped images; resize/crop/normalise on the GPU"},
         "gpu_launches": args.steps * (vit_launches + 1 + 2),
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all ViT linears)", "achieved": achieved,
-                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": ncu_traffic(),
+                     "traffic_unit": "bytes of DRAM read + write per GEMM launch (ncu --set full capture, profiles/r01_ncu_vit_gemms_dram_traffic.json)",
                      "peak_source": pk["source"], "gemm_ms_per_step": gemm_ms / max(2, min(args.steps, 5)),
                      "gemm_launches_per_step": gemm_launches // max(2, min(args.steps, 5)),
                      "algorithmic_gflop_per_img": GFLOP_GEMM_PER_IMG,

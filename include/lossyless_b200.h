@@ -209,6 +209,10 @@ int64_t ll_vit_launches(const ll_vit_t *v, int64_t batch);
 /* max images per internal pass (default 378 = one full round of 74 CTA pairs x 256 token rows);
  * a batch is split into near-equal passes */
 int ll_vit_set_chunk(ll_vit_t *v, int64_t chunk);
+/* ln_1 / ln_2 of every ResidualAttentionBlock (clip/model.py) are by default folded into the GEMMs either
+ * side of them (ll_vit_create folds gamma/beta into library-owned copies of in_proj / c_fc; the producing
+ * GEMM epilogues leave per-row statistics, see ll_gemm_ln).  on = 0 runs the separate LayerNorm kernels. */
+int ll_vit_set_fuse_layernorm(ll_vit_t *v, int on);
 
 /* Per-GEMM device timing for the roofline report: between begin and end every GEMM launch of
  * ll_vit_forward is bracketed by cudaEvents on the launch stream; end synchronises and returns
@@ -236,6 +240,18 @@ int ll_attention_set_impl(int impl);
  * 1 = QuickGELU x*sigmoid(1.702x).  K % 64 == 0, N % 64 == 0. */
 int ll_gemm(const void *A, const void *W, const float *bias, const void *residual, void *D,
             int64_t M, int N, int K, int dtype, int act, ll_stream_t stream);
+/* GEMM with the fused-LayerNorm epilogue operands the encoder uses (nn.LayerNorm of
+ * clip/model.py ResidualAttentionBlock.ln_1 / ln_2 folded into the neighbouring GEMMs):
+ *   row_stats_in  float2 [stats_in_parts][M] partial (sum, sum of squares) over stat_width columns of each
+ *                 A row, summed in order: every accumulator row is multiplied by rsqrt(var + 1e-5) before
+ *                 the bias.  With W row-centred and pre-scaled by gamma and bias' = bias + W beta (host,
+ *                 load time) this is LN(A) W^T + bias.
+ *   row_stats_out float2 [N / 64][M]: the same partials of the D rows as stored, one part per 64 columns;
+ *                 one writer per slot and a tile-independent order, so results are reproducible.
+ * Either may be NULL (both NULL == ll_gemm). */
+int ll_gemm_ln(const void *A, const void *W, const float *bias, const void *residual, void *D,
+               int64_t M, int N, int K, int dtype, int act, const void *row_stats_in,
+               int stats_in_parts, void *row_stats_out, int stat_width, ll_stream_t stream);
 /* Force the GEMM's tile width (64/128/192/256; 0 = automatic wave-aware choice). Tests, tuning. */
 int ll_gemm_set_tile_n(int bn);
 /* CTA-pair (tcgen05 cta_group::2, 256-row tiles) policy: -1 automatic, 0 never, 1 always. */

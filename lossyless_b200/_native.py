@@ -65,6 +65,7 @@ _SIGNATURES = {
     "ll_vit_forward": (c_int, [_P, _P, c_int, c_int64, _P, _P, c_int64, _P]),
     "ll_vit_launches": (c_int64, [_P, c_int64]),
     "ll_vit_set_chunk": (c_int, [_P, c_int64]),
+    "ll_vit_set_fuse_layernorm": (c_int, [_P, c_int]),
     "ll_vit_profile_begin": (c_int, [_P]),
     "ll_vit_profile_end": (c_int, [_P, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_int64)]),
     "ll_vit_profile_breakdown": (c_int, [_P, POINTER(ctypes.c_double)]),
@@ -72,6 +73,7 @@ _SIGNATURES = {
     "ll_attention": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P]),
     "ll_attention_set_impl": (c_int, [c_int]),
     "ll_gemm": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "ll_gemm_ln": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
     "ll_gemm_set_tile_n": (c_int, [c_int]),
     "ll_gemm_set_cta_pair": (c_int, [c_int]),
     "ll_clip_preprocess": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, POINTER(c_float), POINTER(c_float),

@@ -183,6 +183,11 @@ class VisionTransformer(nn.Module):
         N.call("ll_vit_set_chunk", nat["handle"], int(images_per_pass))
         nat["ws"] = None
 
+    def set_fuse_layernorm(self, on):
+        """ln_1 / ln_2 folded into the neighbouring GEMMs (default) or run as separate kernels."""
+        nat = self._native or self._build_native()
+        N.call("ll_vit_set_fuse_layernorm", nat["handle"], int(bool(on)))
+
     def launches(self, batch):
         nat = self._native or self._build_native()
         return int(N.load().ll_vit_launches(nat["handle"], int(batch)))

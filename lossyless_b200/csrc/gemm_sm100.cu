@@ -119,7 +119,9 @@ template <typename T, int BN, int kCtas>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
-                    const float *__restrict__ bias, int has_residual, int M, int N, int K, int act)
+                    const float *__restrict__ bias, int has_residual, int M, int N, int K, int act,
+                    const float2 *__restrict__ stats_in, int stats_in_parts, float2 *__restrict__ stats_out,
+                    float inv_stat_width)
 {
     using S = GemmShape<BN, kCtas>;
     extern __shared__ uint8_t smem_raw[];
@@ -277,6 +279,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ptx::tma_load_2d(buf0 + g * kEpiBufBytes, &tmap_r, &rbar[g], n0 + g * kEpiCols, m0);
                 }
             }
+            // fused LayerNorm, consumer side: the weights were row-centred and scaled by gamma on the host, so
+            // LN(x) W^T + b = rstd(x) * (x W''^T) + b' -- only the row's 1/std is needed here, from the
+            // (sum, sum of squares) partials the producing kernel's epilogue left, one [M] plane per part, added in
+            // a fixed order (no atomics: the encoder's bytes stay reproducible run to run)
+            float row_scale = 1.f;
+            if (stats_in != nullptr) {
+                const int r = m0 + lane;
+                if (r < M) {
+                    // all (<= 16) part loads in flight together, then a fixed-order sum
+                    float2 st[16];
+#pragma unroll
+                    for (int p = 0; p < 16; ++p)
+                        st[p] = p < stats_in_parts ? __ldg(&stats_in[(size_t)p * M + r]) : make_float2(0.f, 0.f);
+                    float sx = 0.f, sq = 0.f;
+#pragma unroll
+                    for (int p = 0; p < 16; ++p) sx += st[p].x, sq += st[p].y;
+                    const float mu = sx * inv_stat_width;
+                    row_scale = rsqrtf(fmaxf(sq * inv_stat_width - mu * mu, 0.f) + 1e-5f);
+                }
+            }
             ptx::mbar_wait(&tfull_bar[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * S::kAccStride;
@@ -293,6 +315,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int q = 0; q < 16; ++q) bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+                float st_sum = 0.f, st_sq = 0.f;
                 uint32_t r0[32], r1[32];
                 if (!(act & 0x800)) {
                     ptx::tmem_ld_32x32(taddr + g * kEpiCols, r0);
@@ -330,8 +353,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(j < 4 ? r0[j * 8 + e] : r1[(j - 4) * 8 + e]);
                     {
                         const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
-                        f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
-                        f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+                        f[0] = fmaf(f[0], row_scale, b0.x), f[1] = fmaf(f[1], row_scale, b0.y);
+                        f[2] = fmaf(f[2], row_scale, b0.z), f[3] = fmaf(f[3], row_scale, b0.w);
+                        f[4] = fmaf(f[4], row_scale, b1.x), f[5] = fmaf(f[5], row_scale, b1.y);
+                        f[6] = fmaf(f[6], row_scale, b1.z), f[7] = fmaf(f[7], row_scale, b1.w);
                     }
                     if ((act & 0xff) == 1) {
 #pragma unroll
@@ -344,7 +369,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] += rf[e];
                     }
-                    if (!(act & 0x200)) *slot = Pack8<T>::pack(f);
+                    const uint4 packed = Pack8<T>::pack(f);
+                    if (!(act & 0x200)) *slot = packed;
+                    if (stats_out != nullptr) {
+                        // fused LayerNorm, producer side.  Taken from the fp32 values before the 16-bit rounding: the
+                        // rounding errors average out over the row (mean moves by ~1e-5 sigma, 1/std by ~1e-7
+                        // relative), far below the 16-bit rounding of the consumer's own output
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            st_sum += f[e];
+                            st_sq = fmaf(f[e], f[e], st_sq);
+                        }
+                    }
+                }
+                if (stats_out != nullptr && m0 + lane < M) {
+                    // one part per 64-column group -- a single writer per slot and a summation order that does not
+                    // depend on the tile shape, so the encoder's bits are reproducible and batch-size invariant
+                    stats_out[(size_t)((n0 >> 6) + g) * M + m0 + lane] = make_float2(st_sum, st_sq);
                 }
                 if (!(act & 0x1000)) ptx::fence_proxy_async_smem();
                 __syncwarp();
@@ -467,6 +508,12 @@ int make_tmap_3d(CUtensorMap *map, const void *base, int dtype, int64_t batch, i
     return LL_OK;
 }
 
+// optional fused-LayerNorm epilogue operands of the next gemm_launch on this thread
+static thread_local const float2 *t_stats_in = nullptr;
+static thread_local float2 *t_stats_out = nullptr;
+static thread_local int t_stats_in_parts = 0;
+static thread_local int t_stat_width = 1;
+
 template <typename T, int BN, int kCtas>
 static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr,
                        const float *bias, int has_residual, int64_t M, int N, int K, int act, cudaStream_t stream)
@@ -495,7 +542,8 @@ static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    LL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, td, tr, bias, has_residual, (int)M, N, K, act));
+    LL_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tw, td, tr, bias, has_residual, (int)M, N, K, act, t_stats_in, t_stats_in_parts,
+                                     t_stats_out, 1.f / (float)t_stat_width));
     return LL_OK;
 }
 
@@ -559,6 +607,21 @@ int gemm_launch_tmaps(const CUtensorMap &ta, const CUtensorMap &tw, const CUtens
 }
 
 
+int gemm_launch_ln(const void *A, const void *W, const float *bias, const void *residual, void *D, int64_t M, int N, int K,
+                   int dtype, int act, const void *stats_in, int stats_in_parts, void *stats_out, int stat_width,
+                   cudaStream_t stream)
+{
+    LL_REQUIRE(stats_in == nullptr || (stats_in_parts > 0 && stats_in_parts <= 16), "gemm_ln: stats_in needs 1 <= stats_in_parts <= 16");
+    t_stats_in = static_cast<const float2 *>(stats_in);
+    t_stats_in_parts = stats_in_parts;
+    t_stats_out = static_cast<float2 *>(stats_out);
+    t_stat_width = stat_width > 0 ? stat_width : 1;
+    const int rc = gemm_launch(A, W, bias, residual, D, M, N, K, dtype, act, stream);
+    t_stats_in = nullptr;
+    t_stats_out = nullptr;
+    return rc;
+}
+
 int gemm_launch(const void *A, const void *W, const float *bias, const void *residual, void *D, int64_t M, int N,
                 int K, int dtype, int act, cudaStream_t stream)
 {
@@ -599,6 +662,14 @@ extern "C" int ll_gemm_set_cta_pair(int mode)
     if (mode < -1 || mode > 1) return ll::fail(LL_ERR_INVALID, "gemm_set_cta_pair: mode must be -1 (auto), 0 (off) or 1 (on)");
     ll::g_pair_mode = mode;
     return LL_OK;
+}
+
+extern "C" int ll_gemm_ln(const void *A, const void *W, const float *bias, const void *residual, void *D, int64_t M, int N,
+                          int K, int dtype, int act, const void *row_stats_in, int stats_in_parts, void *row_stats_out,
+                          int stat_width, ll_stream_t stream)
+{
+    return ll::gemm_launch_ln(A, W, bias, residual, D, M, N, K, dtype, act, row_stats_in, stats_in_parts, row_stats_out,
+                              stat_width, ll::as_stream(stream));
 }
 
 extern "C" int ll_gemm(const void *A, const void *W, const float *bias, const void *residual, void *D, int64_t M,

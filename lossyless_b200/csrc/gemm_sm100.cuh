@@ -12,6 +12,13 @@ namespace ll {
 int gemm_launch(const void *A, const void *W, const float *bias, const void *residual, void *D, int64_t M,
                 int N, int K, int dtype, int act, cudaStream_t stream);
 
+// Same with the fused-LayerNorm epilogue operands.  stats_in: float2 [stats_in_parts][M] partial (sum, sum of squares)
+// of the A rows over stat_width columns -- each accumulator row is scaled by 1/std before the bias.  stats_out:
+// float2 [N / 64][M], the same partials of the D rows as stored, one part per 64 columns.  Either may be null.
+int gemm_launch_ln(const void *A, const void *W, const float *bias, const void *residual, void *D, int64_t M, int N, int K,
+                   int dtype, int act, const void *stats_in, int stats_in_parts, void *stats_out, int stat_width,
+                   cudaStream_t stream);
+
 // Encodes a 2-D K-major tensor map: tensor [rows, K] row-major, box [box_rows, 64], 128B swizzle.
 int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, int64_t rows, int64_t K, int box_rows);
 // 3-D map over [batch, rows, cols] (cols contiguous), box [1, box_rows, 64], 128B swizzle: rows beyond

@@ -43,10 +43,11 @@ patchify_kernel(const TIn *__restrict__ x, T *__restrict__ A, int64_t B, int R, 
 // ------------------------------------------------------------------------- LayerNorm family
 // One warp per row of `width` (multiple of 256, <= 1024) 16-bit elements; fp32 statistics
 // (CLIP's LayerNorm subclass computes in fp32 and casts back), eps 1e-5.
+// Returns (sum, sum of squares) of the row as stored, for the next block's fused LayerNorm.
 template <typename T, int kChunks>
-__device__ __forceinline__ void warp_layernorm_store(float (&v)[kChunks][8], const float *__restrict__ gamma,
-                                                     const float *__restrict__ beta, T *__restrict__ dst, int lane,
-                                                     int width)
+__device__ __forceinline__ float2 warp_layernorm_store(float (&v)[kChunks][8], const float *__restrict__ gamma,
+                                                       const float *__restrict__ beta, T *__restrict__ dst, int lane,
+                                                       int width)
 {
     float s = 0.f;
 #pragma unroll
@@ -63,6 +64,7 @@ __device__ __forceinline__ void warp_layernorm_store(float (&v)[kChunks][8], con
             q += d * d;
         }
     const float rstd = rsqrtf(warp_sum(q) / (float)width + 1e-5f);
+    float os = 0.f, oq = 0.f;
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
         const int col = c * 256 + lane * 8;
@@ -74,9 +76,15 @@ __device__ __forceinline__ void warp_layernorm_store(float (&v)[kChunks][8], con
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         T out[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) out[j] = from_float<T>((v[c][j] - mean) * rstd * g[j] + bb[j]);
+        for (int j = 0; j < 8; ++j) {
+            out[j] = from_float<T>((v[c][j] - mean) * rstd * g[j] + bb[j]);
+            const float o = to_float<T>(out[j]);
+            os += o;
+            oq = fmaf(o, o, oq);
+        }
         *reinterpret_cast<uint4 *>(dst + col) = *reinterpret_cast<const uint4 *>(out);
     }
+    return make_float2(warp_sum(os), warp_sum(oq));
 }
 
 template <typename T>
@@ -161,7 +169,7 @@ template <typename T, int kChunks>
 __global__ void __launch_bounds__(256)
 assemble_lnpre_kernel(const T *__restrict__ patch_out, const T *__restrict__ cls, const T *__restrict__ pos,
                       const float *__restrict__ gamma, const float *__restrict__ beta, T *__restrict__ x, int64_t B,
-                      int S)
+                      int S, float2 *__restrict__ row_stats)
 {
     pdl_wait();
     pdl_launch_dependents();
@@ -181,7 +189,33 @@ assemble_lnpre_kernel(const T *__restrict__ patch_out, const T *__restrict__ cls
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[c][j] = to_float<T>(from_float<T>(a[j] + p[j]));
     }
-    warp_layernorm_store<T, kChunks>(v, gamma, beta, x + r * width, lane, width);
+    const float2 st = warp_layernorm_store<T, kChunks>(v, gamma, beta, x + r * width, lane, width);
+    if (row_stats != nullptr && lane == 0) row_stats[r] = st;
+}
+
+// One-time weight fold for the fused LayerNorm (ll_vit_create): for a Linear that consumes LN(x),
+//   LN(x) W^T + b = rstd * (x - mean) (W diag(gamma))^T + (b + W beta)
+// and with every row of W diag(gamma) centred (its mean subtracted) the "- mean" drops out of the product:
+//   = rstd * x W''^T + b'.   One warp per output row; fp32 arithmetic, one rounding to the storage type.
+template <typename T>
+__global__ void __launch_bounds__(256)
+fold_layernorm_kernel(const T *__restrict__ W, const float *__restrict__ bias, const float *__restrict__ gamma,
+                      const float *__restrict__ beta, int N, int K, T *__restrict__ Wf, float *__restrict__ bf)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (n >= N) return;
+    float s = 0.f, bs = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float w = to_float<T>(W[(int64_t)n * K + k]);
+        s += w * gamma[k];
+        bs = fmaf(w, beta[k], bs);
+    }
+    const float mean = warp_sum(s) / (float)K;
+    bs = warp_sum(bs);
+    for (int k = lane; k < K; k += 32)
+        Wf[(int64_t)n * K + k] = from_float<T>(to_float<T>(W[(int64_t)n * K + k]) * gamma[k] - mean);
+    if (lane == 0) bf[n] = (bias ? bias[n] : 0.f) + bs;
 }
 
 // ------------------------------------------------------------------------- attention
@@ -373,14 +407,14 @@ static int launch_layernorm(const T *x, int64_t rows, int64_t row_stride, const 
 }
 
 template <typename T>
-static int launch_assemble(const T *po, const T *cls, const T *pos, const float *g, const float *b, T *x, int64_t B, int S, int width, cudaStream_t s)
+static int launch_assemble(const T *po, const T *cls, const T *pos, const float *g, const float *b, T *x, int64_t B, int S, int width, float2 *st, cudaStream_t s)
 {
     const unsigned grid = (unsigned)((B * S * 32 + 255) / 256);
     switch (width / 256) {
-        case 1: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 1>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S)); break;
-        case 2: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 2>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S)); break;
-        case 3: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 3>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S)); break;
-        case 4: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 4>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S)); break;
+        case 1: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 1>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st)); break;
+        case 2: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 2>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st)); break;
+        case 3: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 3>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st)); break;
+        case 4: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 4>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st)); break;
         default: return fail(LL_ERR_INVALID, "assemble: width %d unsupported", width);
     }
     LL_LAUNCH_CHECK();
@@ -426,6 +460,11 @@ struct ll_vit {
     ll_vit_weights_t w;
     std::vector<const void *> in_proj_w, out_proj_w, fc_w, cproj_w;
     std::vector<const float *> in_proj_b, out_proj_b, fc_b, cproj_b, ln1_w, ln1_b, ln2_w, ln2_b;
+    // fused LayerNorm (default): ln_1 / ln_2 folded into in_proj / c_fc at create time -- library-owned copies
+    bool fuse_ln = true;
+    std::vector<void *> in_proj_wf, fc_wf;
+    std::vector<float *> in_proj_bf, fc_bf;
+    std::vector<void *> owned;
     int tokens, grid, kpatch;
     int64_t chunk;  // images per pass: keeps one pass's activations L2-resident
     // optional per-GEMM timing (bench.py's roofline leg): event pairs on the launch stream
@@ -439,6 +478,7 @@ struct ll_vit {
     ~ll_vit()
     {
         for (auto e : ev_pool) cudaEventDestroy(e);
+        for (auto p : owned) cudaFree(p);
     }
     cudaEvent_t next_event()
     {
@@ -456,7 +496,7 @@ namespace {
 inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
 
 struct Workspace {
-    uint8_t *patch_a, *patch_o, *x, *h, *qkv, *f, *cls;
+    uint8_t *patch_a, *patch_o, *x, *h, *qkv, *f, *cls, *stats1, *stats2;
     int64_t total;
 };
 
@@ -478,6 +518,8 @@ Workspace carve(const ll_vit *v, int64_t n, uint8_t *base)
     ws.qkv = take(M * 3 * W * 2);
     ws.f = take(M * 4 * W * 2);
     ws.cls = take(n * W * 2);
+    ws.stats1 = take((W / 64) * M * (int64_t)sizeof(float2));  // ln_1 / ln_2 row statistics, <= width / 64 parts
+    ws.stats2 = take((W / 64) * M * (int64_t)sizeof(float2));
     ws.total = off;
     return ws;
 }
@@ -508,8 +550,30 @@ int forward_chunk(ll_vit *v, const void *x, int x_dtype, int64_t n, void *z, con
     };
     if ((rc = timed(3, [&] { return launch_patchify<T>(x, x_dtype, (T *)ws.patch_a, n, c.res, c.patch, s); }))) return rc;
     if ((rc = gemm(ws.patch_a, v->w.conv1_w, nullptr, nullptr, ws.patch_o, Mp, W, v->kpatch, 0))) return rc;
-    if ((rc = timed(3, [&] { return launch_assemble<T>((const T *)ws.patch_o, (const T *)v->w.class_emb, (const T *)v->w.pos_emb, v->w.ln_pre_w, v->w.ln_pre_b, (T *)ws.x, n, S, W, s); }))) return rc;
-    for (int l = 0; l < c.layers; ++l) {
+    auto gemm_ln = [&](const void *A, const void *Wt, const float *bias, const void *res, void *D, int64_t m, int N, int K, int act,
+                       const void *st_in, int parts_in, void *st_out) {
+        if (v->profiling) {
+            v->prof_flops += 2.0 * (double)m * N * K;
+            v->prof_launches += 1;
+        }
+        return timed(0, [&] { return gemm_launch_ln(A, Wt, bias, res, D, m, N, K, dt, act, st_in, parts_in, st_out, W, s); });
+    };
+    float2 *st1 = v->fuse_ln ? (float2 *)ws.stats1 : nullptr;
+    if ((rc = timed(3, [&] { return launch_assemble<T>((const T *)ws.patch_o, (const T *)v->w.class_emb, (const T *)v->w.pos_emb, v->w.ln_pre_w, v->w.ln_pre_b, (T *)ws.x, n, S, W, st1, s); }))) return rc;
+    if (v->fuse_ln) {
+        // x -> [rstd(x) * x W''qkv + b'] -> attention -> out-proj (+x, row stats) -> [rstd * x W''fc + b', GELU]
+        //   -> c_proj (+x, row stats): the LayerNorm launches and the h round trip through L2 are gone
+        int parts1 = 1;  // the assemble kernel leaves whole-row statistics, the GEMM epilogues one part per 64 columns
+        for (int l = 0; l < c.layers; ++l) {
+            if ((rc = gemm_ln(ws.x, v->in_proj_wf[l], v->in_proj_bf[l], nullptr, ws.qkv, M, 3 * W, W, 0, ws.stats1, parts1, nullptr))) return rc;
+            if ((rc = timed(1, [&] { return launch_attention<T>((const T *)ws.qkv, (T *)ws.h, n, S, c.heads, s); }))) return rc;
+            if ((rc = gemm_ln(ws.h, v->out_proj_w[l], v->out_proj_b[l], ws.x, ws.x, M, W, W, 0, nullptr, 0, ws.stats2))) return rc;
+            if ((rc = gemm_ln(ws.x, v->fc_wf[l], v->fc_bf[l], nullptr, ws.f, M, 4 * W, W, 1, ws.stats2, W / 64, nullptr))) return rc;
+            if ((rc = gemm_ln(ws.f, v->cproj_w[l], v->cproj_b[l], ws.x, ws.x, M, W, 4 * W, 0, nullptr, 0, ws.stats1))) return rc;
+            parts1 = W / 64;
+        }
+    }
+    for (int l = 0; !v->fuse_ln && l < c.layers; ++l) {
         if ((rc = timed(2, [&] { return launch_layernorm<T>((const T *)ws.x, M, W, v->ln1_w[l], v->ln1_b[l], (T *)ws.h, W, s); }))) return rc;
         if ((rc = gemm(ws.h, v->in_proj_w[l], v->in_proj_b[l], nullptr, ws.qkv, M, 3 * W, W, 0))) return rc;
         if ((rc = timed(1, [&] { return launch_attention<T>((const T *)ws.qkv, (T *)ws.h, n, S, c.heads, s); }))) return rc;
@@ -555,6 +619,34 @@ extern "C" int ll_vit_create(const ll_vit_config_t *cfg, const ll_vit_weights_t 
     v->tokens = g * g + 1;
     v->kpatch = 3 * cfg->patch * cfg->patch;
     v->chunk = 378;  // 74 CTA pairs x 256 rows = 18 944 tokens: every GEMM of a pass is a whole number of rounds
+    // fold ln_1 into in_proj and ln_2 into c_fc (device, once)
+    const int W = cfg->width;
+    auto fold = [&](const void *Wsrc, const float *bias, const float *gamma, const float *beta, int N, void **Wf, float **bf) -> int {
+        LL_CUDA_CHECK(cudaMalloc(Wf, (size_t)N * W * 2));
+        v->owned.push_back(*Wf);
+        LL_CUDA_CHECK(cudaMalloc((void **)bf, (size_t)N * sizeof(float)));
+        v->owned.push_back(*bf);
+        const unsigned grid = (unsigned)((N * 32 + 255) / 256);
+        if (cfg->dtype == LL_F16)
+            fold_layernorm_kernel<__half><<<grid, 256>>>((const __half *)Wsrc, bias, gamma, beta, N, W, (__half *)*Wf, *bf);
+        else
+            fold_layernorm_kernel<__nv_bfloat16><<<grid, 256>>>((const __nv_bfloat16 *)Wsrc, bias, gamma, beta, N, W, (__nv_bfloat16 *)*Wf, *bf);
+        LL_LAUNCH_CHECK();
+        return LL_OK;
+    };
+    v->in_proj_wf.resize(L), v->in_proj_bf.resize(L), v->fc_wf.resize(L), v->fc_bf.resize(L);
+    for (int l = 0; l < L; ++l) {
+        int rc = fold(v->in_proj_w[l], v->in_proj_b[l], v->ln1_w[l], v->ln1_b[l], 3 * W, &v->in_proj_wf[l], &v->in_proj_bf[l]);
+        if (rc == LL_OK) rc = fold(v->fc_w[l], v->fc_b[l], v->ln2_w[l], v->ln2_b[l], 4 * W, &v->fc_wf[l], &v->fc_bf[l]);
+        if (rc != LL_OK) {
+            delete v;
+            return rc;
+        }
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        delete v;
+        return fail(LL_ERR_CUDA, "vit_create: LayerNorm fold failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     *out = v;
     return LL_OK;
 }
@@ -565,6 +657,13 @@ extern "C" int ll_vit_set_chunk(ll_vit_t *v, int64_t chunk)
 {
     LL_REQUIRE(v && chunk > 0, "vit_set_chunk: bad arguments");
     v->chunk = chunk;
+    return LL_OK;
+}
+
+extern "C" int ll_vit_set_fuse_layernorm(ll_vit_t *v, int on)
+{
+    LL_REQUIRE(v != nullptr, "vit_set_fuse_layernorm: null handle");
+    v->fuse_ln = on != 0;
     return LL_OK;
 }
 
@@ -579,7 +678,7 @@ extern "C" int64_t ll_vit_launches(const ll_vit_t *v, int64_t batch)
 {
     if (!v || batch <= 0) return 0;
     const int64_t passes = (batch + v->chunk - 1) / v->chunk;
-    return passes * (5 + 7 * (int64_t)v->cfg.layers);
+    return passes * (5 + (v->fuse_ln ? 5 : 7) * (int64_t)v->cfg.layers);
 }
 
 extern "C" int ll_vit_forward(ll_vit_t *v, const void *x, int x_dtype, int64_t batch, void *z, void *workspace,

@@ -169,15 +169,14 @@ class ClipCompressor(nn.Module):
             z, bias=self.biasing, exp_scale=self._exp_scale(), mode=mode)
         return packed, offsets, lens
 
-    def compress_batch_to_host(self, X_host, out_host=None, sub_batch=378):
-        """One step of the encode hot path with HOST buffers: (pinned) host images -> H2D -> ViT ->
-        quantise + rANS -> container records -> D2H.  ``X_host`` is either CLIP-normalised
-        [B,3,224,224] (fp16 / fp32, what the reference's transform yields) or raw uint8 pixels
-        [B,H,W,3] / [B,3,H,W], in which case resize + crop + normalise also run on the GPU
-        (bit-identical to the PIL / torchvision transform, lossyless_b200/preprocess.py).  The batch is walked in sub-batches whose H2D
-        copies run on a side stream, double-buffered against the ViT of the previous sub-batch, so
-        PCIe and the tensor cores overlap.  Returns (records: uint8 host view holding the batch's
-        ``>I len + bytes`` records, n_images, the pinned output buffer for reuse)."""
+    def _encode_host_batch(self, X_host, sub_batch=378):
+        """Enqueues (no host synchronisation) the whole encode of one batch held in HOST memory: H2D -> [GPU
+        preprocessing] -> ViT -> quantise + rANS -> container records.  ``X_host`` is either CLIP-normalised
+        [B,3,224,224] (fp16 / fp32, what the reference's transform yields) or raw uint8 pixels [B,H,W,3] /
+        [B,3,H,W], in which case resize + crop + normalise also run on the GPU (bit-identical to the PIL /
+        torchvision transform, lossyless_b200/preprocess.py).  The batch is walked in sub-batches whose H2D
+        copies run on a side stream, double-buffered against the ViT of the previous sub-batch, so PCIe and
+        the tensor cores overlap.  Returns device tensors (packed records, offsets int64 [B+1])."""
         dev = torch.device(self.device)
         B = X_host.shape[0]
         is_raw = X_host.dtype == torch.uint8  # raw pixels: CLIP preprocessing runs on the GPU as well
@@ -193,34 +192,90 @@ class ClipCompressor(nn.Module):
             else:
                 X = X_host.half() if X_host.dtype == torch.float32 else X_host
             packed, offsets, _ = self._compress_records(X, mode=1)
-        else:
-            pipe = self._h2d_pipe(dev, X_host, sub_batch)
-            main = torch.cuda.current_stream(dev)
-            z = torch.empty((B, self.z_dim), dtype=torch.float16, device=dev)
-            for k, i0 in enumerate(range(0, B, sub_batch)):
-                i1 = min(B, i0 + sub_batch)
-                slot = k % 2
-                with torch.cuda.stream(pipe["stream"]):
-                    if pipe["consumed"][slot] is not None:
-                        pipe["stream"].wait_event(pipe["consumed"][slot])  # ViT of sub-batch k-2 done with the slot
-                    pipe["buf"][slot][: i1 - i0].copy_(X_host[i0:i1], non_blocking=True)
-                    pipe["ready"][slot].record(pipe["stream"])
-                main.wait_event(pipe["ready"][slot])
-                xs = pipe["buf"][slot][: i1 - i0]
-                if is_raw:
-                    xs = self._gpu_preprocess(xs, chw=chw)
-                self.clip(xs, out=z[i0:i1])
-                ev = torch.cuda.Event()
-                ev.record(main)
-                pipe["consumed"][slot] = ev
-            packed, offsets, _, _ = self.entropy_bottleneck.compress_to_device(
-                z, bias=self.biasing, exp_scale=self._exp_scale(), mode=1)
+            return packed, offsets
+        pipe = self._h2d_pipe(dev, X_host, sub_batch)
+        main = torch.cuda.current_stream(dev)
+        z = torch.empty((B, self.z_dim), dtype=torch.float16, device=dev)
+        for i0 in range(0, B, sub_batch):
+            i1 = min(B, i0 + sub_batch)
+            slot = pipe["next"]
+            pipe["next"] = 1 - slot
+            with torch.cuda.stream(pipe["stream"]):
+                if pipe["consumed"][slot] is not None:
+                    pipe["stream"].wait_event(pipe["consumed"][slot])  # the ViT that last read this slot is done
+                pipe["buf"][slot][: i1 - i0].copy_(X_host[i0:i1], non_blocking=True)
+                pipe["ready"][slot].record(pipe["stream"])
+            main.wait_event(pipe["ready"][slot])
+            xs = pipe["buf"][slot][: i1 - i0]
+            if is_raw:
+                xs = self._gpu_preprocess(xs, chw=chw)
+            self.clip(xs, out=z[i0:i1])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            pipe["consumed"][slot] = ev
+        packed, offsets, _, _ = self.entropy_bottleneck.compress_to_device(
+            z, bias=self.biasing, exp_scale=self._exp_scale(), mode=1)
+        return packed, offsets
+
+    @torch.no_grad()
+    def compress_batch_to_host(self, X_host, out_host=None, sub_batch=378):
+        """One step of the encode hot path with HOST buffers: (pinned) host images -> H2D -> ViT ->
+        quantise + rANS -> container records -> D2H (see ``_encode_host_batch``).  Returns (records: uint8 host
+        view holding the batch's ``>I len + bytes`` records, n_images, the pinned output buffer for reuse)."""
+        dev = torch.device(self.device)
+        packed, offsets = self._encode_host_batch(X_host, sub_batch)
         total = int(offsets[-1].item())  # one 8-byte D2H: size of this batch's records
         if out_host is None or out_host.numel() < total:
             out_host = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
         out_host[:total].copy_(packed[:total], non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        return out_host[:total], B, out_host
+        return out_host[:total], X_host.shape[0], out_host
+
+    @torch.no_grad()
+    def compress_stream(self, host_batches, sub_batch=378):
+        """``compress_dataset``'s loop as a software pipeline: yields ``(records, n_images)`` per batch of
+        ``host_batches`` (same inputs as ``compress_batch_to_host``), in order.  Batch i + 1 is enqueued (its H2D
+        copies start as soon as a staging slot frees up) BEFORE the host waits for batch i, and batch i's records
+        come back on a separate D2H stream, so neither the first H2D copy of a batch nor the read-back of the
+        previous one is exposed.  ``records`` is a view of a pinned buffer that is valid until the generator
+        is resumed."""
+        dev = torch.device(self.device)
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_d2h_stream", None) is None:
+            self._d2h_stream = torch.cuda.Stream(dev)
+        d2h = self._d2h_stream
+
+        def enqueue(X_host):
+            packed, offsets = self._encode_host_batch(X_host, sub_batch)
+            done = torch.cuda.Event()
+            done.record(main)
+            total_host = torch.empty(1, dtype=torch.int64).pin_memory()
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                total_host.copy_(offsets[-1:], non_blocking=True)
+                sized = torch.cuda.Event()
+                sized.record(d2h)
+            return dict(packed=packed, offsets=offsets, total=total_host, sized=sized, n=X_host.shape[0], src=X_host)
+
+        def finish(job):
+            job["sized"].synchronize()
+            total = int(job["total"][0])
+            out = getattr(self, "_stream_out", None)
+            if out is None or out.numel() < total:
+                out = self._stream_out = torch.empty(max(2 * total, 1 << 20), dtype=torch.uint8).pin_memory()
+            with torch.cuda.stream(d2h):
+                out[:total].copy_(job["packed"][:total], non_blocking=True)
+            d2h.synchronize()
+            return out[:total], job["n"]
+
+        pending = None
+        for X_host in host_batches:
+            job = enqueue(X_host)
+            if pending is not None:
+                yield finish(pending)
+            pending = job
+        if pending is not None:
+            yield finish(pending)
 
     def _h2d_pipe(self, dev, X_host, sub_batch):
         """Two device staging slots + a copy stream, created once per (dtype, sub_batch)."""
@@ -229,7 +284,7 @@ class ClipCompressor(nn.Module):
         if pipe is None or pipe["key"] != key:
             pipe = dict(key=key, stream=torch.cuda.Stream(dev),
                         buf=[torch.empty((sub_batch,) + tuple(X_host.shape[1:]), dtype=X_host.dtype, device=dev) for _ in range(2)],
-                        ready=[torch.cuda.Event(), torch.cuda.Event()], consumed=[None, None])
+                        ready=[torch.cuda.Event(), torch.cuda.Event()], consumed=[None, None], next=0)
             self._pipe = pipe
         return pipe
 
@@ -243,15 +298,21 @@ class ClipCompressor(nn.Module):
             raise ValueError("Compression only implemented on GPU (as uses fp16).")
 
         start = time.time()
-        n, Y, pinned = 0, [], None
+        n, Y = 0, []
+        kwargs_dataloader = dict(kwargs_dataloader)
+        kwargs_dataloader.setdefault("pin_memory", True)  # async H2D needs page-locked batches
+
+        def images():
+            for x, *y in _progress(DataLoader(dataset, **kwargs_dataloader)):
+                if label_file is not None:
+                    Y.append(y[0].cpu().numpy().astype(np.uint16))
+                yield x
+
         with Path(file).open("wb") as f:
             write_uints(f, (0,))  # N, patched below once known
-            for x, *y in _progress(DataLoader(dataset, **kwargs_dataloader)):
-                records, b, pinned = self.compress_batch_to_host(x, pinned)
+            for records, b in self.compress_stream(images()):
                 f.write(records.numpy().data)
                 n += b
-                if label_file is not None:
-                    Y += [y[0].cpu().numpy().astype(np.uint16)]
             f.seek(0)
             write_uints(f, (n,))
 

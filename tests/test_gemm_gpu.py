@@ -137,3 +137,46 @@ def test_gemm_cta_pair_long_k(cuda_device):
         nat.call("ll_gemm_set_cta_pair", -1)
     ref = _ref(A, W, None, None, 0)
     assert (D.float() - ref).abs().max().item() < 6e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,Nn,act", [(50, 2304, 0), (6400 + 17, 3072, 1), (18944, 768, 0)])
+def test_gemm_fused_layernorm(cuda_device, dtype, M, Nn, act):
+    """ll_gemm_ln: LN(A) W^T + b from the raw rows, per-row statistics partials and host-folded weights, against
+    torch's layer_norm + matmul in fp32; and the row statistics it leaves for the next LayerNorm."""
+    from lossyless_b200 import _native as nat
+
+    g = torch.Generator(device=cuda_device).manual_seed(M + Nn)
+    K = 768
+    A = (torch.randn(M, K, generator=g, device=cuda_device) * 0.7 + torch.randn(M, 1, generator=g, device=cuda_device)).to(dtype)
+    A[:, 5] *= 30  # an outlier channel like the residual stream's
+    W = (torch.randn(Nn, K, generator=g, device=cuda_device) * K ** -0.5).to(dtype)
+    bias = torch.randn(Nn, generator=g, device=cuda_device)
+    gamma = 1 + 0.2 * torch.randn(K, generator=g, device=cuda_device)
+    beta = 0.2 * torch.randn(K, generator=g, device=cuda_device)
+    ref = _ref(torch.nn.functional.layer_norm(A.float(), (K,), gamma, beta, 1e-5), W, bias, None, act)
+    # the fold ll_vit_create does on the device, here in torch
+    Wg = W.float() * gamma
+    Wf = (Wg - Wg.mean(1, keepdim=True)).to(dtype)
+    bf = bias + W.float() @ beta
+    # statistics of A in three uneven parts, [parts, M] float2
+    cuts = [0, 100, 101, K]
+    parts = torch.stack([torch.stack([A.float()[:, a:b].sum(1), (A.float()[:, a:b] ** 2).sum(1)], -1) for a, b in zip(cuts, cuts[1:])]).contiguous()
+    D = torch.empty((M, Nn), dtype=dtype, device=cuda_device)
+    st_out = torch.full((Nn // 64, M, 2), float("nan"), device=cuda_device)
+    nat.call("ll_gemm_ln", nat.ptr(A), nat.ptr(Wf), nat.ptr(bf), None, nat.ptr(D), M, Nn, K, nat.dtype_code(A), act,
+             nat.ptr(parts), 3, nat.ptr(st_out), K, nat.stream())
+    tol = 6e-3 if dtype == torch.float16 else 3e-2
+    err = (D.float() - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), err
+    # row statistics for the next LayerNorm (taken before the 16-bit rounding): mean and variance of the stored rows
+    got = st_out.sum(0)
+    mean, var = got[:, 0] / Nn, got[:, 1] / Nn - (got[:, 0] / Nn) ** 2
+    eps = 1e-3 if dtype == torch.float16 else 8e-3
+    assert (mean - D.float().mean(1)).abs().max().item() < eps
+    assert ((var - D.float().var(1, unbiased=False)).abs() / D.float().var(1, unbiased=False)).max().item() < eps
+    # reproducible: a second launch gives the same bits (no atomics in the statistics)
+    D2, st2 = torch.empty_like(D), torch.empty_like(st_out)
+    nat.call("ll_gemm_ln", nat.ptr(A), nat.ptr(Wf), nat.ptr(bf), None, nat.ptr(D2), M, Nn, K, nat.dtype_code(A), act,
+             nat.ptr(parts), 3, nat.ptr(st2), K, nat.stream())
+    assert torch.equal(D, D2) and torch.equal(st_out, st2)

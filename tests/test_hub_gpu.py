@@ -74,3 +74,21 @@ def test_compress_dataset_file_format(compressor, tmp_path, capsys):
     (tmp_path / "bad.bin").write_bytes(blob[:-5])
     with pytest.raises(ValueError):
         comp.decompress_dataset(tmp_path / "bad.bin")
+
+
+def test_compress_stream_matches_blocking_calls(compressor):
+    """compress_dataset's pipelined loop (batch i+1 enqueued before batch i is read back, staging slots shared
+    across batches) returns, batch by batch, the bytes of the one-call-per-batch path -- ragged batch sizes,
+    fp16 / fp32 / raw uint8 inputs."""
+    comp, _ = compressor
+    g = torch.Generator().manual_seed(11)
+    batches = [torch.randn(n, 3, 224, 224, generator=g).half().pin_memory() for n in (5, 400, 1, 379)]
+    batches.append(torch.randn(7, 3, 224, 224, generator=g).pin_memory())
+    want = [bytes(comp.compress_batch_to_host(b)[0].numpy().data) for b in batches]
+    got = [(bytes(rec.numpy().data), n) for rec, n in comp.compress_stream(iter(batches), sub_batch=128)]
+    assert [n for _, n in got] == [b.shape[0] for b in batches]
+    assert [r for r, _ in got] == want
+    raw = [torch.randint(0, 256, (n, 96, 96, 3), dtype=torch.uint8, generator=g).pin_memory() for n in (3, 130)]
+    want = [bytes(comp.compress_batch_to_host(b)[0].numpy().data) for b in raw]
+    assert [bytes(rec.numpy().data) for rec, _ in comp.compress_stream(iter(raw))] == want
+    assert list(comp.compress_stream(iter([]))) == []

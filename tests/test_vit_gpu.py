@@ -85,6 +85,23 @@ def test_vit_b32_vs_golden(cuda_device, golden_dir):
     xb = x.repeat(200, 1, 1, 1)  # 400 images: two internal passes (378-image limit) of 200
     zb = vit(xb).float().cpu().numpy()
     assert np.array_equal(zb[0::2], np.repeat(z[:1], 200, 0)) and np.array_equal(zb[1::2], np.repeat(z[1:], 200, 0))
-    assert vit.launches(400) == 2 * (5 + 7 * 12)
+    assert vit.launches(400) == 2 * (5 + 5 * 12)  # ln_1 / ln_2 are fused into the GEMMs
     vit.set_chunk(64)  # many small passes give the same bits
     assert np.array_equal(vit(xb[:130]).float().cpu().numpy(), zb[:130])
+
+
+def test_vit_fused_layernorm_matches_separate_kernels(cuda_device, golden_dir):
+    """The default path folds ln_1 / ln_2 into the GEMMs; the separate LayerNorm kernels are the same function."""
+    g = np.load(os.path.join(golden_dir, "vit_b32.npz"))
+    vit, sd, cfg = _product_vit(cuda_device)
+    x = torch.from_numpy(g["x_f16"]).to(cuda_device).repeat(3, 1, 1, 1)
+    z_fused = vit(x).float().cpu().numpy()
+    assert np.array_equal(z_fused, vit(x).float().cpu().numpy())  # reproducible
+    vit.set_fuse_layernorm(False)
+    assert vit.launches(6) == 5 + 7 * 12
+    z_sep = vit(x).float().cpu().numpy()
+    for z in (z_fused, z_sep):
+        err = np.abs(z[:2] - g["z"])
+        assert err.max() < 5e-2 and err.mean() < 8e-3, (err.max(), err.mean())
+    d = np.abs(z_fused - z_sep)
+    assert d.max() < 4e-2 and d.mean() < 6e-3, (d.max(), d.mean())

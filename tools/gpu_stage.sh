@@ -26,6 +26,12 @@ for s in $STAGES; do
     all)   run all 900 python -m pytest tests -m gpu -x -q ;;
     smoke) run smoke 200 python __graft_entry__.py smoke ;;
     bench) run bench 400 python bench.py --steps 10 --warmup 3 ;;
+    ab_ln) for i in 1 2; do
+             run ab_sep$i 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-fuse-ln
+             run ab_fused$i 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+           done ;;
+    sweep) run sweep 600 python tools/sweep.py --out gpurun_out/sweep.txt ;;
+    trainbench) run trainbench 600 python tools/train_bench.py --out gpurun_out/trainbench.txt ;;
     gemmbench) run gemmbench 200 python tools/gemm_bench.py 256 ;;
     pairbench) run pairbench0 200 env LL_PAIR=0 LL_GEMM_ONLY=1 python tools/gemm_bench.py 256
                run pairbench1 200 env LL_PAIR=1 LL_GEMM_ONLY=1 python tools/gemm_bench.py 256
@@ -37,7 +43,9 @@ for s in $STAGES; do
              run pair756_bn256 200 env LL_PAIR=1 LL_BN=256 LL_GEMM_ONLY=1 python tools/gemm_bench.py 756 ;;
     epidbg) for d in 0 0x100 0x1100 0x300 0x700 0xf00 0x1f00; do run epidbg_$d 200 env LL_DBG=$d LL_PAIR=1 LL_BN=256 LL_GEMM_ONLY=1 python tools/gemm_bench.py 378; done ;;
     bnsweep) for bn in 128 192; do run pair378_bn$bn 200 env LL_PAIR=1 LL_BN=$bn LL_GEMM_ONLY=1 python tools/gemm_bench.py 378; done ;;
-    ncu_vit) run ncu_vit 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 50 -c 50 -f -o gpurun_out/prof_vit_gemms python tools/vit_once.py ;;
+    ncu_vit) run ncu_vit 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 50 -c 10 -f -o gpurun_out/prof_vit_gemms python tools/vit_once.py
+             ncu -i gpurun_out/prof_vit_gemms.ncu-rep --page raw --csv > gpurun_out/prof_vit_gemms_raw.csv 2>/dev/null
+             [ "$(stat -c %s gpurun_out/prof_vit_gemms.ncu-rep 2>/dev/null || echo 0)" -gt 40000000 ] && rm -f gpurun_out/prof_vit_gemms.ncu-rep ;;
     ncu_small) run ncu_small 600 ncu --set full --clock-control none --import-source on -k regex:"attention" -s 10 -c 2 -f -o gpurun_out/prof_small python tools/gemm_bench.py 378 ;;
     ncu_gemm) run ncu_gemm 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 8 -c 5 -f -o gpurun_out/prof_gemm python tools/gemm_bench.py 256 ;;
     ncu_list) run ncu_list 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --batch 378 --no-cpu-baseline ;;
