@@ -302,6 +302,17 @@ def main():
     barrier()
     e2e_raw = world * B * args.steps / max_over_ranks(time.perf_counter() - t0)
 
+    # ---- what the host link gives: a bare pinned H2D copy of one 378-image sub-batch, nothing else running
+    probe_dst = torch.empty_like(X[:378])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe_dst.copy_(X_host[:378], non_blocking=True)
+    ev0.record()
+    for _ in range(4):
+        probe_dst.copy_(X_host[:378], non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_gbps = 4 * probe_dst.numel() * 2 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+
     # ---- roofline leg: same steps with every GEMM launch bracketed by events
     comp.clip.profile_begin()
     for _ in range(max(2, min(args.steps, 5))):
@@ -320,7 +331,7 @@ def main():
                    "bits_per_img": bits_per_img, "sharding": "independent images per rank, no collective"},
         "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 2, "d2h_bytes_per_step": total_bytes + 8,
                 "input": "pinned host fp16 [B,3,224,224] CLIP-normalised tensors (what the reference's loop body receives)",
-                "api": "ClipCompressor.compress_stream (compress_dataset's loop)", "blocking_per_batch_call": e2e_blocking},
+                "api": "ClipCompressor.compress_stream (compress_dataset's loop)", "h2d_link_gbps": h2d_gbps, "blocking_per_batch_call": e2e_blocking},
         "e2e_raw_uint8": {"value": e2e_raw, "unit": "img/s", "h2d_bytes_per_step": B * 96 * 96 * 3,
                           "input": "pinned host uint8 [B,96,96,3] STL10-shaped images; resize/crop/normalise on the GPU"},
         "gpu_launches": args.steps * (vit_launches + 1 + 2),

@@ -272,6 +272,9 @@ int ll_clip_preprocess(const uint8_t *img, int64_t B, int H, int W, int layout, 
                        const int32_t *bounds_h, int ksize_h, const int32_t *coef_v,
                        const int32_t *bounds_v, int ksize_v, const float *mean3, const float *std3,
                        int n_px, uint8_t *tmp, void *out, int out_dtype, ll_stream_t stream);
+/* 0 (default): images whose pixels + intermediate fit shared memory take a fused one-CTA-per-image kernel;
+ * 1: always the general two-pass kernels.  Same bits either way (tests/test_preprocess_gpu.py). */
+int ll_clip_preprocess_set_impl(int impl);
 
 /* ----------------------------------------------------------- device: distortions */
 

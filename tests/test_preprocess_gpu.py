@@ -7,7 +7,9 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-SIZES = [(96, 96), (32, 32), (224, 224), (375, 500), (500, 375), (600, 300), (225, 224), (1000, 40)]
+# (96,96) .. (97,101) take the fused shared-memory kernel (odd byte counts: every image at a different 16-byte
+# phase), the rest the general two-pass kernels
+SIZES = [(96, 96), (32, 32), (100, 150), (97, 101), (28, 28), (224, 224), (375, 500), (500, 375), (600, 300), (225, 224), (1000, 40)]
 
 
 def _cpu_transform(arr):
@@ -35,6 +37,16 @@ def test_matches_pil_torchvision(cuda_device, h, w):
     assert out16.dtype == torch.float16 and torch.equal(out16.cpu(), ref.half())
     out_chw = pre(x.permute(0, 3, 1, 2).contiguous(), chw=True, dtype=torch.float32)
     assert torch.equal(out_chw.cpu(), ref)
+    # the general two-pass kernels give the same bits as whatever was chosen above
+    from lossyless_b200 import _native as nat
+
+    nat.call("ll_clip_preprocess_set_impl", 1)
+    try:
+        assert torch.equal(pre(x, dtype=torch.float32).cpu(), ref) and torch.equal(pre(x).cpu(), ref.half())
+        assert torch.equal(pre(x, dtype=torch.bfloat16), out32.bfloat16())
+    finally:
+        nat.call("ll_clip_preprocess_set_impl", 0)
+    assert torch.equal(pre(x, dtype=torch.bfloat16), out32.bfloat16())
 
 
 def test_compress_dataset_from_raw_pixels(cuda_device, tmp_path):

@@ -30,6 +30,7 @@ for s in $STAGES; do
              run ab_sep$i 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-fuse-ln
              run ab_fused$i 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
            done ;;
+    e2eprobe) run e2eprobe 300 python tools/e2e_probe.py ;;
     sweep) run sweep 600 python tools/sweep.py --out gpurun_out/sweep.txt ;;
     trainbench) run trainbench 600 python tools/train_bench.py --out gpurun_out/trainbench.txt ;;
     gemmbench) run gemmbench 200 python tools/gemm_bench.py 256 ;;
