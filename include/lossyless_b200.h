@@ -63,6 +63,12 @@ int ll_container_index(const uint8_t *buf, int64_t size, int64_t pos, int64_t n,
 
 /* ------------------------------------------------------------------ device: rANS codec */
 
+/* Kernel selection for the factorised-prior codec: 0 = by row count (default: one stream per
+ * warp below 8192 rows -- latency matters; one stream per lane above -- throughput matters),
+ * 1 = always one stream per warp, 2 = always one stream per lane.  Both produce the same
+ * bytes (tests/test_codec_gpu.py); the knob exists for tests and benchmarks.  Process-wide. */
+int ll_rans_set_impl(int impl);
+
 /* bytes of per-row scratch ll_eb_rans_encode needs for C symbols (worst case, escapes
  * included); always a multiple of 4. */
 int ll_rans_stream_cap_bytes(int C);

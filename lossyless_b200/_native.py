@@ -50,6 +50,7 @@ _SIGNATURES = {
     "ll_build_cdf_tables": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "ll_container_index": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),
     "ll_rans_stream_cap_bytes": (c_int, [c_int]),
+    "ll_rans_set_impl": (c_int, [c_int]),
     "ll_rans_build_enc_table": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "ll_eb_rans_encode": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),
     "ll_rans_encode_indexed": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P, _P]),

@@ -114,3 +114,94 @@ def test_full_size_roundtrip_property(cuda_device, weights_dir):
     bits = 8 * lens.float().mean().item()
     assert 1950 < bits < 2150, bits  # ~2055 bits/img for b005 on N(0, 0.45^2)
     assert int(offsets[-1]) == int(lens.sum())
+
+
+@pytest.fixture
+def codec_impl():
+    """Sets the codec kernel choice (include/lossyless_b200.h: ll_rans_set_impl) and restores 'auto'."""
+    from lossyless_b200 import _native as N
+
+    yield lambda impl: N.call("ll_rans_set_impl", impl)
+    N.call("ll_rans_set_impl", 0)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_stream_per_lane_kernels_vs_oracle(cuda_device, weights_dir, codec_impl, tag, dtype):
+    """The throughput kernels (one stream per lane) forced on at a ragged row count: bytes, symbols and
+    decoded values identical to the oracle's, i.e. to the stream-per-warp kernels'."""
+    eb, sd, b, es = _module(weights_dir, tag, cuda_device)
+    gen = torch.Generator().manual_seed(5)
+    z = (torch.randn(3 * 128 + 32 + 5, 512, generator=gen) * 0.6).to(dtype)  # full CTAs, a full warp, a ragged warp
+    z[7] *= 30   # a row of escapes
+    z[40, ::3] = -200.0
+    codec_impl(2)
+    packed, offsets, lens, sym = eb.compress_to_device(z.to(cuda_device), b, es, mode=1, want_symbols=True)
+    strings = eb.compress(z.to(cuda_device), bias=b, exp_scale=es)
+    ebo = oeb.split_state_dict(sd)
+    tab = oeb.update(ebo)
+    ref, rsym = oeb.compress(ebo, tab, oeb.process_z_in(z, sd["biasing"], sd["scaling"]))
+    assert strings == ref
+    assert np.array_equal(sym.cpu().numpy(), rsym)
+    rec = packed[: int(offsets[-1])].cpu().numpy().tobytes()
+    assert rec == b"".join(struct.pack(">I", len(s)) + s for s in ref)
+    z_hat, dsym = eb.decompress_from_device(*_to_dev(ref, cuda_device), bias=b, exp_scale=es, want_symbols=True)
+    assert np.array_equal(dsym.cpu().numpy(), rsym)
+    zh_ref, _ = oeb.decompress(ebo, tab, ref)
+    assert torch.equal(z_hat.cpu(), oeb.process_z_out(zh_ref, sd["biasing"], sd["scaling"]))
+    # same through the stream-per-warp kernels
+    codec_impl(1)
+    assert eb.compress(z.to(cuda_device), bias=b, exp_scale=es) == ref
+
+
+def test_stream_per_lane_edge_cases(cuda_device, weights_dir, codec_impl):
+    eb, sd, b, es = _module(weights_dir, "beta5e-02", cuda_device)
+    codec_impl(2)
+    one = eb.compress(torch.zeros(1, 512, device=cuda_device), bias=b, exp_scale=es)
+    codec_impl(1)
+    assert one == eb.compress(torch.zeros(1, 512, device=cuda_device), bias=b, exp_scale=es)
+    codec_impl(2)
+    big = torch.full((3, 512), 65504.0, dtype=torch.float16, device=cuda_device)
+    big[1] = -65504.0
+    s = eb.compress(big, bias=b, exp_scale=es)
+    ebo = oeb.split_state_dict(sd)
+    ref, _ = oeb.compress(ebo, oeb.update(ebo), oeb.process_z_in(big.cpu(), sd["biasing"], sd["scaling"]))
+    assert s == ref
+    assert torch.equal(eb.decompress(s, [1, 1], bias=b, exp_scale=es).reshape(3, 512).cpu(),
+                       oeb.process_z_out(oeb.decompress(ebo, oeb.update(ebo), ref)[0], sd["biasing"], sd["scaling"]))
+    with pytest.raises(ValueError):
+        eb.decompress([one[0][:8]], [1, 1], bias=b, exp_scale=es)
+    with pytest.raises(ValueError):
+        eb.decompress([one[0][:-2]], [1, 1], bias=b, exp_scale=es)
+    # a channel count that is not a multiple of the 64-channel chunk (config 4: C = 128 is; 102 is not)
+    from lossyless_b200.entropy_models import EntropyBottleneck
+
+    torch.manual_seed(0)
+    small = EntropyBottleneck(102, init_scale=10, filters=[3, 3, 3, 3])
+    small.update(force=True)
+    small = small.to(cuda_device)
+    z = torch.randn(77, 102, device=cuda_device) * 4
+    got = small.compress(z)
+    codec_impl(1)
+    assert got == small.compress(z)
+    codec_impl(2)
+    assert torch.equal(small.decompress(got, [1, 1]).reshape(77, 102), small.quantize(z, "dequantize", small._get_medians().reshape(1, -1)))
+
+
+def test_large_pack_matches_single_cta_pack(cuda_device, weights_dir, codec_impl):
+    """> 4096 rows take the three-launch pack (block sums in the offsets array): identical records."""
+    eb, sd, b, es = _module(weights_dir, "beta1e-02", cuda_device)
+    gen = torch.Generator(device=cuda_device).manual_seed(2)
+    z = (torch.randn(4096 + 1024 + 17, 512, generator=gen, device=cuda_device) * 0.45).half()
+    codec_impl(2)
+    packed, offsets, lens, _ = eb.compress_to_device(z, b, es, mode=1)
+    codec_impl(1)
+    total = 0
+    for lo, hi in ((0, 4096), (4096, z.shape[0])):  # pieces small enough for the single-CTA pack
+        p2, o2, l2, _ = eb.compress_to_device(z[lo:hi], b, es, mode=1)
+        n = int(o2[-1])
+        assert torch.equal(packed[total: total + n], p2[:n])
+        assert torch.equal(offsets[lo:hi] - total, o2[:-1])
+        assert torch.equal(lens[lo:hi], l2)
+        total += n
+    assert int(offsets[-1]) == total

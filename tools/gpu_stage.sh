@@ -31,6 +31,10 @@ for s in $STAGES; do
              run ab_fused$i 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
            done ;;
     e2eprobe) run e2eprobe 300 python tools/e2e_probe.py ;;
+    codecbench) run codecbench 600 python tools/codec_bench.py --out gpurun_out/codecbench.txt ;;
+    ncu_codec) run ncu_codec 600 ncu --set full --clock-control none --import-source on -k regex:lanes -s 8 -c 2 -f -o gpurun_out/prof_codec python tools/codec_bench.py --rows 131072
+               ncu -i gpurun_out/prof_codec.ncu-rep --page raw --csv > gpurun_out/prof_codec_raw.csv 2>/dev/null
+               ncu -i gpurun_out/prof_codec.ncu-rep --page source --csv > gpurun_out/prof_codec_source.csv 2>/dev/null ;;
     sweep) run sweep 600 python tools/sweep.py --out gpurun_out/sweep.txt ;;
     trainbench) run trainbench 600 python tools/train_bench.py --out gpurun_out/trainbench.txt ;;
     gemmbench) run gemmbench 200 python tools/gemm_bench.py 256 ;;
