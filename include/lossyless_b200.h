@@ -263,6 +263,33 @@ int ll_gemm_set_tile_n(int bn);
 /* CTA-pair (tcgen05 cta_group::2, 256-row tiles) policy: -1 automatic, 0 never, 1 always. */
 int ll_gemm_set_cta_pair(int mode);
 
+/* ----------------------------------------- device: ViT encoder backward (fine-tuning) */
+
+/* The reference fine-tunes through `clip.load(...).visual.float()` with torch autograd under AMP
+ * (lossyless/architectures.py:351-376, lossyless/learnable_compressors.py:277-303).  Here every dense
+ * contraction of the backward pass (dX = dY W, dW = dY^T X) is an ll_gemm call on transposed 16-bit
+ * copies; the entry points below are the rest of that backward pass (lossyless_b200/clip_vit.py drives
+ * them).  All tensors device, row-major, `dtype` LL_F16 or LL_BF16 unless stated. */
+
+/* dst [C, Rpad] = src [R, C]^T, columns R..Rpad-1 zero (2-byte elements; Rpad >= R).  The token count
+ * becomes the K of a weight-gradient GEMM and must be a multiple of 64. */
+int ll_transpose_pad(const void *src, void *dst, int64_t R, int C, int64_t Rpad, ll_stream_t stream);
+/* out[c] += sum_r src[r, c] (float32 accumulate: bias gradients).  out must be initialised. */
+int ll_colsum(const void *src, int64_t R, int C, int dtype, float *out, ll_stream_t stream);
+/* clip/model.py QuickGELU: f = u * sigmoid(1.702 u);  g_u = g_f * d f / d u.  n elements. */
+int ll_quickgelu_forward(const void *u, void *f, int64_t n, int dtype, ll_stream_t stream);
+int ll_quickgelu_backward(const void *u, const void *g_f, void *g_u, int64_t n, int dtype, ll_stream_t stream);
+/* Backward of ll_layernorm (clip/model.py LayerNorm, eps 1e-5), statistics recomputed from x:
+ *   g_x = (g_res or 0) + dLN(x)^T g_h;   g_gamma, g_beta float32 [width], ACCUMULATED (atomics).
+ * width in {512, 768, 1024}; g_res may be NULL; g_x must not alias the inputs. */
+int ll_layernorm_backward(const void *x, const void *g_h, const float *gamma, const void *g_res, void *g_x,
+                          float *g_gamma, float *g_beta, int64_t rows, int width, int dtype,
+                          ll_stream_t stream);
+/* Backward of ll_attention: qkv [batch*S, 3*H*64], g_out [batch*S, H*64] -> g_qkv [batch*S, 3*H*64].
+ * The probabilities are recomputed from qkv.  S <= 64. */
+int ll_attention_backward(const void *qkv, const void *g_out, void *g_qkv, int64_t batch, int S, int H,
+                          int dtype, ll_stream_t stream);
+
 /* ------------------------------------------------------ device: CLIP preprocessing */
 
 /* uint8 images -> bicubic resize (Pillow's 8-bit ImagingResample, bit-exact) -> centre crop n_px ->

@@ -94,12 +94,15 @@ class PretrainedSSL(nn.Module):
     """Pretrained SSL encoder; only ``model="clip_vit"`` (CLIP ViT-B/32, 3x224x224 -> 512).
 
     The reference calls ``clip.load`` (a download) and ``.float()``s the tower for AMP training;
-    here the weights come from ``clip_state_dict`` (dict or path; default: seeded random init) and
-    the tower runs frozen in fp16 through ``ll_vit_forward`` -- the reference's shipped CLIP
-    recipe (bin/clip/clip_hub.sh, config/finetune/freezer.yaml) keeps it frozen as well.  The
-    output is returned as float32 and carries no gradient."""
+    here the weights come from ``clip_state_dict`` (dict or path; default: seeded random init).
+    ``is_frozen=True`` (default; the reference's shipped CLIP recipe, bin/clip/clip_hub.sh +
+    config/finetune/freezer.yaml): the tower runs in fp16 through ``ll_vit_forward`` and the float32
+    output carries no gradient.  ``is_frozen=False`` (the reference's ``PretrainedSSL`` without the
+    ``Freezer`` callback, lossyless/architectures.py:351-376): float32 master parameters, 16-bit
+    ``compute_dtype`` kernels, and a backward pass through the whole tower (``clip_vit._VitTrainFn``)."""
 
-    def __init__(self, in_shape, out_shape, model="clip_vit", clip_state_dict=None):
+    def __init__(self, in_shape, out_shape, model="clip_vit", clip_state_dict=None, is_frozen=True,
+                 compute_dtype=torch.bfloat16):
         super().__init__()
         if model != "clip_vit":
             raise NotImplementedError(f"PretrainedSSL model {model!r} is outside the B200 hot path; only clip_vit")
@@ -113,9 +116,13 @@ class PretrainedSSL(nn.Module):
             if not isinstance(clip_state_dict, dict):
                 clip_state_dict = torch.load(clip_state_dict, map_location="cpu", weights_only=True)
             self.encoder.load_state_dict(load_visual_state_dict(clip_state_dict))
-        self.encoder.half()
-        for p in self.encoder.parameters():
-            p.requires_grad_(False)
+        self.is_frozen = is_frozen
+        if is_frozen:
+            self.encoder.half()
+            for p in self.encoder.parameters():
+                p.requires_grad_(False)
+        else:
+            self.encoder.unfreeze_(compute_dtype)
 
     def forward(self, X):
         z = self.encoder(X).float()

@@ -8,8 +8,17 @@ lossyless/architectures.py:367-376): same constructor, same state-dict key names
 mlp.c_fc.*, mlp.c_proj.*, ln_2.*}``, ``ln_post.*``, ``proj``), so a CLIP checkpoint's ``visual.*``
 tensors load with ``load_state_dict``.  The forward pass is one native call
 (``ll_vit_forward``: tcgen05 GEMMs + fused kernels); the torch modules below only hold
-parameters.  Inference only (the reference's shipped CLIP recipe freezes the encoder,
-bin/clip/clip_hub.sh / config/finetune/freezer.yaml).  No CPU path.
+parameters.  Two execution paths, no CPU path:
+
+* frozen / inference (default; the reference's shipped CLIP recipe freezes the encoder,
+  bin/clip/clip_hub.sh / config/finetune/freezer.yaml): one ``ll_vit_forward`` call per batch;
+* fine-tuning (``VisionTransformer.unfreeze_()``; the reference trains through
+  ``clip.load(...).visual.float()`` with torch autograd under AMP, lossyless/architectures.py:351-376):
+  float32 master parameters, 16-bit (bf16 by default) compute copies, a layer-by-layer forward that keeps
+  the activations, and a hand-written backward (``_VitTrainFn``) whose contractions all run on the tcgen05
+  GEMM (``ll_gemm`` on transposed copies) plus the kernels of csrc/vit_train.cu.  torch is used there for
+  allocation, reshapes / slices (data movement) and the three tiny batch reductions of the embedding
+  gradients only.
 """
 import ctypes
 import math
@@ -88,6 +97,9 @@ class VisionTransformer(nn.Module):
         self.ln_post = _LayerNorm(width)
         self.proj = nn.Parameter(torch.empty(width, output_dim))
         self._native = None
+        self._trainable = False
+        self._train_dtype = torch.bfloat16
+        self._train_cache = None
         self.initialize_parameters()
 
     @torch.no_grad()
@@ -209,11 +221,41 @@ class VisionTransformer(nn.Module):
         N.call("ll_vit_profile_breakdown", self._native["handle"], arr)
         return dict(gemm=arr[0], attention=arr[1], layernorm=arr[2], patchify_assemble=arr[3])
 
-    @torch.no_grad()
+    # -- fine-tuning ---------------------------------------------------------------------
+    def unfreeze_(self, compute_dtype=torch.bfloat16):
+        """Make the encoder trainable: float32 master parameters (``clip.load(...).float()``,
+        lossyless/architectures.py:376), ``requires_grad``, 16-bit compute in ``compute_dtype``
+        (the AMP autocast dtype).  ``forward`` then records a backward pass whenever grad is enabled."""
+        if compute_dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError("compute_dtype must be torch.bfloat16 or torch.float16")
+        self.float()
+        for p in self.parameters():
+            p.requires_grad_(True)
+        self._trainable, self._train_dtype, self._train_cache = True, compute_dtype, None
+        return self
+
+    def freeze_(self):
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self._trainable, self._train_cache = False, None
+        return self
+
     def forward(self, x, out=None):
-        """x [B,3,R,R] (fp16 / bf16 / fp32, cuda, CLIP-normalised) -> z [B, output_dim] in the
-        model's 16-bit dtype (the reference's fp16 ``self.clip(X)``).  ``out`` optionally receives
-        the result (a contiguous [B, output_dim] view of a larger buffer, for pipelined callers)."""
+        """x [B,3,R,R] (fp16 / bf16 / fp32, cuda, CLIP-normalised) -> z [B, output_dim].
+        Frozen encoder / no grad: the model's 16-bit dtype (the reference's fp16 ``self.clip(X)``);
+        ``out`` optionally receives the result (a contiguous [B, output_dim] view of a larger buffer, for
+        pipelined callers).  Unfrozen encoder with grad enabled: float32 z carrying the backward pass."""
+        if self._trainable and torch.is_grad_enabled():
+            if out is not None:
+                raise ValueError("out= is not supported on the fine-tuning path")
+            names, params = zip(*self.named_parameters())
+            return _VitTrainFn.apply(self, x, names, *params)
+        if self._native is not None and self._native.get("stale"):
+            self._native = None  # parameters were updated by an optimiser step since the views were made
+        with torch.no_grad():
+            return self._forward_frozen(x, out)
+
+    def _forward_frozen(self, x, out=None):
         N.require_cuda(x, "x")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.input_resolution or x.shape[3] != self.input_resolution:
             raise ValueError(f"expected [B,3,{self.input_resolution},{self.input_resolution}] images, got {tuple(x.shape)}")
@@ -234,6 +276,189 @@ class VisionTransformer(nn.Module):
         N.call("ll_vit_forward", nat["handle"], N.ptr(x), N.dtype_code(x), B, N.ptr(z), N.ptr(nat["ws"]),
                nat["ws"].numel(), N.stream())
         return z
+
+
+# ------------------------------------------------------------------------------ fine-tuning path
+def _gemm(A, W, bias=None, residual=None, act=0):
+    """D[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual) on the tcgen05 GEMM; 16-bit operands."""
+    M, K = A.shape
+    Nn = W.shape[0]
+    D = torch.empty((M, Nn), dtype=A.dtype, device=A.device)
+    N.call("ll_gemm", N.ptr(A), N.ptr(W), N.ptr(bias), N.ptr(residual), N.ptr(D), M, Nn, K, N.dtype_code(A), act, N.stream())
+    return D
+
+
+def _ln(x, w, b):
+    h = torch.empty_like(x)
+    N.call("ll_layernorm", N.ptr(x), x.shape[0], x.shape[1], N.ptr(w), N.ptr(b), N.ptr(h), N.dtype_code(x), N.stream())
+    return h
+
+
+def _transpose_pad(t):
+    """[R, C] -> [C, ceil64(R)] zero padded (R becomes the K of a weight-gradient GEMM)."""
+    R, C = t.shape
+    Rp = (R + 63) // 64 * 64
+    out = torch.empty((C, Rp), dtype=t.dtype, device=t.device)
+    N.call("ll_transpose_pad", N.ptr(t), N.ptr(out), R, C, Rp, N.stream())
+    return out
+
+
+def _wgrad(gy, x):
+    """dW [N, K] = gy[M, N]^T @ x[M, K] (16-bit result, as autocast produces it)."""
+    return _gemm(_transpose_pad(gy), _transpose_pad(x))
+
+
+def _colsum(t):
+    out = torch.zeros(t.shape[1], dtype=torch.float32, device=t.device)
+    N.call("ll_colsum", N.ptr(t), t.shape[0], t.shape[1], N.dtype_code(t), N.ptr(out), N.stream())
+    return out
+
+
+def _ln_backward(x, g_h, gamma, g_res=None):
+    g_x = torch.empty_like(x)
+    g_w = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
+    g_b = torch.zeros_like(g_w)
+    N.call("ll_layernorm_backward", N.ptr(x), N.ptr(g_h), N.ptr(gamma), N.ptr(g_res), N.ptr(g_x), N.ptr(g_w), N.ptr(g_b),
+           x.shape[0], x.shape[1], N.dtype_code(x), N.stream())
+    return g_x, g_w, g_b
+
+
+class _VitTrainFn(torch.autograd.Function):
+    """forward = clip.model.VisionTransformer.forward layer by layer (activations kept);
+    backward = its hand-written adjoint.  Replaces torch autograd through the reference's unfrozen
+    ``PretrainedSSL`` encoder (lossyless/architectures.py:351-376)."""
+
+    @staticmethod
+    def forward(ctx, vit, x, names, *params):
+        N.require_cuda(x, "x")
+        R, P, Wd = vit.input_resolution, vit.patch_size, vit.width
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != R or x.shape[3] != R:
+            raise ValueError(f"expected [B,3,{R},{R}] images, got {tuple(x.shape)}")
+        if x.shape[0] == 0:
+            raise ValueError("the fine-tuning path needs a non-empty batch")
+        dt = vit._train_dtype
+        w = vit._train_weights(dt)
+        B, g = x.shape[0], R // P
+        S = g * g + 1
+        M = B * S
+        # im2col is pure data movement: [B,3,g,P,g,P] -> [B*g*g, 3*P*P]
+        a_patch = x.to(dt).reshape(B, 3, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(B * g * g, 3 * P * P).contiguous()
+        patch = _gemm(a_patch, w["conv1.weight"])
+        tok = (torch.cat([w["class_embedding"].expand(B, 1, Wd), patch.view(B, g * g, Wd)], 1) + w["positional_embedding"]).reshape(M, Wd)
+        xs = _ln(tok, w["ln_pre.weight"], w["ln_pre.bias"])
+        saved = []
+        for i in range(vit.layers):
+            p = f"transformer.resblocks.{i}."
+            h1 = _ln(xs, w[p + "ln_1.weight"], w[p + "ln_1.bias"])
+            qkv = _gemm(h1, w[p + "attn.in_proj_weight"], w[p + "attn.in_proj_bias"])
+            a = torch.empty((M, Wd), dtype=dt, device=x.device)
+            N.call("ll_attention", N.ptr(qkv), N.ptr(a), B, S, vit.heads, N.dtype_code(qkv), N.stream())
+            x1 = _gemm(a, w[p + "attn.out_proj.weight"], w[p + "attn.out_proj.bias"], residual=xs)
+            h2 = _ln(x1, w[p + "ln_2.weight"], w[p + "ln_2.bias"])
+            u = _gemm(h2, w[p + "mlp.c_fc.weight"], w[p + "mlp.c_fc.bias"])
+            f = torch.empty_like(u)
+            N.call("ll_quickgelu_forward", N.ptr(u), N.ptr(f), u.numel(), N.dtype_code(u), N.stream())
+            x2 = _gemm(f, w[p + "mlp.c_proj.weight"], w[p + "mlp.c_proj.bias"], residual=x1)
+            saved.append((xs, h1, qkv, a, x1, h2, u, f))
+            xs = x2
+        xc = xs.view(B, S, Wd)[:, 0].contiguous()
+        hc = _ln(xc, w["ln_post.weight"], w["ln_post.bias"])
+        z = _gemm(hc, w["proj_t"])
+        ctx.vit, ctx.names, ctx.w = vit, names, w
+        ctx.state = dict(a_patch=a_patch, tok=tok, saved=saved, xc=xc, hc=hc, B=B, S=S, M=M)
+        ctx.needs = [p.requires_grad for p in params]
+        return z.float()
+
+    @staticmethod
+    def backward(ctx, g_z):
+        vit, w, st = ctx.vit, ctx.w, ctx.state
+        dt = vit._train_dtype
+        B, S, M, Wd = st["B"], st["S"], st["M"], vit.width
+        dev = g_z.device
+        G = {}
+        gz = g_z.to(dt).contiguous()
+        # z = hc @ proj
+        g_hc = _gemm(gz, w["proj"])                      # [B, 768] = gz [B,512] @ proj[768,512]^T
+        G["proj"] = _wgrad(st["hc"], gz)                 # [768, 512]
+        g_xc, G["ln_post.weight"], G["ln_post.bias"] = _ln_backward(st["xc"], g_hc, w["ln_post.weight"])
+        g_x = torch.zeros((B, S, Wd), dtype=dt, device=dev)
+        g_x[:, 0] = g_xc
+        g_x = g_x.view(M, Wd)
+        for i in reversed(range(vit.layers)):
+            p = f"transformer.resblocks.{i}."
+            xs, h1, qkv, a, x1, h2, u, f = st["saved"][i]
+            wt = vit._train_weights_t(dt, i)
+            # x2 = x1 + f @ c_proj^T + b
+            g_f = _gemm(g_x, wt["c_proj"])
+            G[p + "mlp.c_proj.weight"] = _wgrad(g_x, f)
+            G[p + "mlp.c_proj.bias"] = _colsum(g_x)
+            g_u = torch.empty_like(u)
+            N.call("ll_quickgelu_backward", N.ptr(u), N.ptr(g_f), N.ptr(g_u), u.numel(), N.dtype_code(u), N.stream())
+            del g_f
+            g_h2 = _gemm(g_u, wt["c_fc"])
+            G[p + "mlp.c_fc.weight"] = _wgrad(g_u, h2)
+            G[p + "mlp.c_fc.bias"] = _colsum(g_u)
+            del g_u
+            g_x1, G[p + "ln_2.weight"], G[p + "ln_2.bias"] = _ln_backward(x1, g_h2, w[p + "ln_2.weight"], g_res=g_x)
+            # x1 = x + a @ out_proj^T + b
+            g_a = _gemm(g_x1, wt["out_proj"])
+            G[p + "attn.out_proj.weight"] = _wgrad(g_x1, a)
+            G[p + "attn.out_proj.bias"] = _colsum(g_x1)
+            g_qkv = torch.empty_like(qkv)
+            N.call("ll_attention_backward", N.ptr(qkv), N.ptr(g_a), N.ptr(g_qkv), B, S, vit.heads, N.dtype_code(qkv), N.stream())
+            g_h1 = _gemm(g_qkv, wt["in_proj"])
+            G[p + "attn.in_proj_weight"] = _wgrad(g_qkv, h1)
+            G[p + "attn.in_proj_bias"] = _colsum(g_qkv)
+            del g_qkv, g_a
+            g_x, G[p + "ln_1.weight"], G[p + "ln_1.bias"] = _ln_backward(xs, g_h1, w[p + "ln_1.weight"], g_res=g_x1)
+            st["saved"][i] = None
+        g_tok, G["ln_pre.weight"], G["ln_pre.bias"] = _ln_backward(st["tok"], g_x, w["ln_pre.weight"])
+        g_tok = g_tok.view(B, S, Wd)
+        G["positional_embedding"] = g_tok.sum(0, dtype=torch.float32)
+        G["class_embedding"] = g_tok[:, 0].sum(0, dtype=torch.float32)
+        g_patch = g_tok[:, 1:].reshape(B * (S - 1), Wd).contiguous()
+        G["conv1.weight"] = _wgrad(g_patch, st["a_patch"]).view(vit.conv1.weight.shape)
+        if vit._native is not None:
+            vit._native["stale"] = True  # an optimiser step is about to change the parameters
+        grads = tuple(G[n].float() if need else None for n, need in zip(ctx.names, ctx.needs))
+        ctx.state = None
+        return (None, None, None) + grads
+
+
+def _train_weights(self, dt):
+    """16-bit compute copies of the float32 master parameters (the autocast casts), rebuilt when an
+    optimiser step bumped a parameter's version.  LayerNorm gains / biases and linear biases stay fp32."""
+    key = (dt, tuple(p._version for p in self.parameters()), self.proj.device)
+    if self._train_cache is not None and self._train_cache["key"] == key:
+        return self._train_cache["w"]
+    w = {}
+    with torch.no_grad():
+        for n, p in self.named_parameters():
+            if n.endswith("bias") or "ln_" in n:
+                w[n] = p.detach().float().contiguous()
+            else:
+                w[n] = p.detach().to(dt).contiguous()
+        w["conv1.weight"] = w["conv1.weight"].reshape(self.width, -1)
+        w["proj_t"] = w["proj"].t().contiguous()
+    self._train_cache = dict(key=key, w=w, wt={})
+    return w
+
+
+def _train_weights_t(self, dt, i):
+    """Transposed 16-bit copies of block i's four matrices: the W operands of the data-gradient GEMMs
+    (dX = dY @ W is D = A W'^T with W' = W^T stored row-major)."""
+    cache = self._train_cache["wt"]
+    if i not in cache:
+        w = self._train_cache["w"]
+        p = f"transformer.resblocks.{i}."
+        tr = lambda t: _transpose_pad(t)[:, : t.shape[0]].contiguous() if t.shape[0] % 64 else _transpose_pad(t)
+        cache[i] = dict(in_proj=tr(w[p + "attn.in_proj_weight"]), out_proj=tr(w[p + "attn.out_proj.weight"]),
+                        c_fc=tr(w[p + "mlp.c_fc.weight"]), c_proj=tr(w[p + "mlp.c_proj.weight"]))
+    return cache[i]
+
+
+VisionTransformer._train_weights = _train_weights
+VisionTransformer._train_weights_t = _train_weights_t
 
 
 def load_visual_state_dict(sd):

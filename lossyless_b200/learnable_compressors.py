@@ -235,10 +235,12 @@ def allreduce_mean_(params, group=None):
         o += n
 
 
-def default_clip_hparams(distortion="lossy_Z", beta=5e-2, max_steps=1000, n_data=50000, clip_state_dict=None):
+def default_clip_hparams(distortion="lossy_Z", beta=5e-2, max_steps=1000, n_data=50000, clip_state_dict=None,
+                         is_frozen=True, compute_dtype=torch.bfloat16):
     """hparams of the reference's CLIP bottleneck recipe (config/featurizer/bottleneck_clip_lossyZ.yaml,
     bin/clip/clip_hub.sh) with ``rate=H_factorized`` and either the lossy-Z or the BINCE
-    (contrastive, config/distortion/BINCE.yaml) distortion."""
+    (contrastive, config/distortion/BINCE.yaml) distortion.  ``is_frozen=False`` fine-tunes the CLIP tower
+    as well (the reference's recipe without the ``Freezer`` callback of config/finetune/freezer.yaml)."""
     if distortion == "lossy_Z":
         dist = dict(mode="lossy_Z", factor_beta=1, kwargs=dict(p_norm=1))
     elif distortion == "BINCE":
@@ -250,7 +252,7 @@ def default_clip_hparams(distortion="lossy_Z", beta=5e-2, max_steps=1000, n_data
     return NamespaceMap(
         stage="feat",
         data=dict(shape=(3, 224, 224), mode="image", max_steps=max_steps, length=n_data),
-        encoder=dict(z_dim=512, fam="deterministic", fam_kwargs={}, arch="clip", arch_kwargs=dict(clip_state_dict=clip_state_dict)),
+        encoder=dict(z_dim=512, fam="deterministic", fam_kwargs={}, arch="clip", arch_kwargs=dict(clip_state_dict=clip_state_dict, is_frozen=is_frozen, compute_dtype=compute_dtype)),
         rate=dict(mode="H_factorized", factor_beta=1,
                   kwargs=dict(z_dim=512, is_endToEnd=False, warmup_k_epoch=0,
                               kwargs_ent_bottleneck=dict(init_scale=10, filters=[3, 3, 3, 3]))),

@@ -22,6 +22,7 @@ for s in $STAGES; do
     dist)  run dist 300 python -m pytest tests/test_distortion_gpu.py tests/test_training_gpu.py -m gpu -q ;;
     hyper) run hyper 300 python -m pytest tests/test_hyperprior.py -m gpu -q ;;
     prep)  run prep 300 python -m pytest tests/test_preprocess_gpu.py -m gpu -q ;;
+    vittrain) run vittrain 600 python -m pytest tests/test_vit_train_gpu.py -m gpu -q -x ;;
     hub)   run hub 300 python -m pytest tests/test_hub_gpu.py -m gpu -q ;;
     all)   run all 900 python -m pytest tests -m gpu -x -q ;;
     smoke) run smoke 200 python __graft_entry__.py smoke ;;
