@@ -79,6 +79,7 @@ _SIGNATURES = {
     "ll_quickgelu_backward": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
     "ll_layernorm_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "ll_attention_backward": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "ll_attention_backward_set_impl": (c_int, [c_int]),
     "ll_gemm": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "ll_clip_preprocess_set_impl": (c_int, [c_int]),
     "ll_gemm_ln": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),

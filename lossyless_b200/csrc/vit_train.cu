@@ -11,18 +11,51 @@
 //   attention_backward  softmax(q k^T / 8) v per (image, head), S <= 64, d = 64, probabilities recomputed
 // All HBM-bound elementwise / row-wise work except the attention backward (small fp32 tiles in shared
 // memory, one CTA per (image, head)).
+#include <algorithm>
+
 #include "ll_common.cuh"
 
 namespace ll {
 
 // ------------------------------------------------------------------------- transpose (2-byte elements)
+// 64 x 64 tiles, 4-byte global accesses on both sides (a warp moves one 128-byte row segment per access).
+// Needs C even and Rpad even (true for every caller: widths and padded token counts are multiples of 64);
+// odd shapes take the scalar kernel below.
 __global__ void __launch_bounds__(256)
 transpose_pad_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int64_t R, int C, int64_t Rpad)
+{
+    __shared__ uint16_t tile[64][66];
+    const int64_t r0 = (int64_t)blockIdx.y * 64;
+    const int c0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int64_t r = r0 + ty + 8 * k;
+        const int c = c0 + 2 * tx;
+        uint32_t v = 0;
+        if (r < R && c < C) v = *reinterpret_cast<const uint32_t *>(src + r * C + c);  // C even: c + 1 < C too
+        *reinterpret_cast<uint32_t *>(&tile[ty + 8 * k][2 * tx]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int cl = ty + 8 * k;
+        const int c = c0 + cl;
+        const int64_t r = r0 + 2 * tx;
+        if (c < C && r < Rpad) {
+            const uint32_t v = (uint32_t)tile[2 * tx][cl] | ((uint32_t)tile[2 * tx + 1][cl] << 16);
+            *reinterpret_cast<uint32_t *>(dst + (int64_t)c * Rpad + r) = v;  // Rpad even: r + 1 < Rpad too
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+transpose_pad_scalar_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int64_t R, int C, int64_t Rpad)
 {
     __shared__ uint16_t tile[32][33];
     const int64_t r0 = (int64_t)blockIdx.y * 32;
     const int c0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int64_t r = r0 + ty + 8 * k;
@@ -56,31 +89,6 @@ colsum_kernel(const T *__restrict__ src, int64_t R, int C, int64_t rows_per_cta,
     if (rg == 0 && c < C) atomicAdd(out + c, part[0][cx] + part[1][cx] + part[2][cx] + part[3][cx]);
 }
 
-// ------------------------------------------------------------------------- QuickGELU
-template <typename T>
-__global__ void __launch_bounds__(256)
-quickgelu_forward_kernel(const T *__restrict__ u, T *__restrict__ f, int64_t n)
-{
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float x = to_float<T>(u[i]);
-        f[i] = from_float<T>(x / (1.f + __expf(-1.702f * x)));
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256)
-quickgelu_backward_kernel(const T *__restrict__ u, const T *__restrict__ g_f, T *__restrict__ g_u, int64_t n)
-{
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float x = to_float<T>(u[i]);
-        const float s = 1.f / (1.f + __expf(-1.702f * x));
-        // d/dx [x s(1.702 x)] = s + 1.702 x s (1 - s)
-        g_u[i] = from_float<T>(to_float<T>(g_f[i]) * (s + 1.702f * x * s * (1.f - s)));
-    }
-}
-
 // 8 contiguous 16-bit elements <-> 8 floats through one 16-byte access (pointers 16-byte aligned)
 template <typename T>
 __device__ __forceinline__ void load8(const T *p, float *out)
@@ -98,6 +106,54 @@ __device__ __forceinline__ void store8(T *p, const float *v)
 #pragma unroll
     for (int k = 0; k < 8; ++k) e[k] = from_float<T>(v[k]);
     *reinterpret_cast<uint4 *>(p) = raw;
+}
+
+// ------------------------------------------------------------------------- QuickGELU
+// 8 elements (16 bytes) per thread per step; the tail (n % 8) is handled by the last thread scalar-wise.
+template <typename T>
+__global__ void __launch_bounds__(256)
+quickgelu_forward_kernel(const T *__restrict__ u, T *__restrict__ f, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n8 = n / 8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        float x[8];
+        load8<T>(u + 8 * i, x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = x[k] / (1.f + __expf(-1.702f * x[k]));
+        store8<T>(f + 8 * i, x);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = 8 * n8; i < n; ++i) {
+            const float x = to_float<T>(u[i]);
+            f[i] = from_float<T>(x / (1.f + __expf(-1.702f * x)));
+        }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+quickgelu_backward_kernel(const T *__restrict__ u, const T *__restrict__ g_f, T *__restrict__ g_u, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n8 = n / 8;
+    // d/dx [x s(1.702 x)] = s + 1.702 x s (1 - s)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        float x[8], g[8];
+        load8<T>(u + 8 * i, x);
+        load8<T>(g_f + 8 * i, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float sg = 1.f / (1.f + __expf(-1.702f * x[k]));
+            g[k] *= sg + 1.702f * x[k] * sg * (1.f - sg);
+        }
+        store8<T>(g_u + 8 * i, g);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = 8 * n8; i < n; ++i) {
+            const float x = to_float<T>(u[i]);
+            const float sg = 1.f / (1.f + __expf(-1.702f * x));
+            g_u[i] = from_float<T>(to_float<T>(g_f[i]) * (sg + 1.702f * x * sg * (1.f - sg)));
+        }
 }
 
 // ------------------------------------------------------------------------- LayerNorm backward
@@ -286,6 +342,199 @@ attention_backward_kernel(const T *__restrict__ qkv, const T *__restrict__ g_out
 
 constexpr size_t kAbSmem = 4 * 64 * kAbPitch * 2 + 2 * 64 * kAbPPitch * 4;
 
+// Tensor-core variant (default): the five products of the backward pass on mma.sync.m16n8k16 with fp32
+// accumulation, S padded to 64.  Four warps; warp w owns rows 16w..16w+15 of every product's M dimension.
+// Operands live in shared memory in both orientations ([s][d] and [d][s]; P and dS as [i][j] and [j][i],
+// rounded to the 16-bit type as flash-attention backward does) so that every fragment is two plain 32-bit
+// loads per register pair with the reduction index contiguous; the 72-element pitch makes them conflict-free.
+template <typename T>
+struct MmaOp;
+template <>
+struct MmaOp<__half> {
+    static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+    {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+};
+template <>
+struct MmaOp<__nv_bfloat16> {
+    static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+    {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    }
+};
+
+constexpr int kAmP = 72;  // elements per shared-memory row (144 B: rows g = 0..7 land on banks 4g + t)
+constexpr size_t kAmSmem = 11 * 64 * kAmP * 2;
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi)
+{
+    T v[2] = {from_float<T>(lo), from_float<T>(hi)};
+    return *reinterpret_cast<uint32_t *>(v);
+}
+
+// acc[nt] (16 x 8 tiles, nt = 0..7) += A[m0.., :] * B^T with A = [m][k] and B = [n][k], k = 0..63
+template <typename T>
+__device__ __forceinline__ void warp_mma_64(float (&acc)[8][4], const T *A, const T *B, int m0, int g, int t)
+{
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4];
+        a[0] = *reinterpret_cast<const uint32_t *>(A + (m0 + g) * kAmP + 16 * kk + 2 * t);
+        a[1] = *reinterpret_cast<const uint32_t *>(A + (m0 + g + 8) * kAmP + 16 * kk + 2 * t);
+        a[2] = *reinterpret_cast<const uint32_t *>(A + (m0 + g) * kAmP + 16 * kk + 2 * t + 8);
+        a[3] = *reinterpret_cast<const uint32_t *>(A + (m0 + g + 8) * kAmP + 16 * kk + 2 * t + 8);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t *>(B + (8 * nt + g) * kAmP + 16 * kk + 2 * t);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t *>(B + (8 * nt + g) * kAmP + 16 * kk + 2 * t + 8);
+            MmaOp<T>::mma(acc[nt], a, b0, b1);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+attention_backward_mma_kernel(const T *__restrict__ qkv, const T *__restrict__ g_out, T *__restrict__ g_qkv, int S, int H)
+{
+    extern __shared__ __align__(16) uint8_t ab_smem[];
+    T *sQ = reinterpret_cast<T *>(ab_smem);
+    T *sK = sQ + 64 * kAmP, *sV = sK + 64 * kAmP, *sG = sV + 64 * kAmP;          // [s][d]
+    T *sQt = sG + 64 * kAmP, *sKt = sQt + 64 * kAmP, *sGt = sKt + 64 * kAmP;     // [d][s]
+    T *sP = sGt + 64 * kAmP, *sPt = sP + 64 * kAmP, *sS = sPt + 64 * kAmP, *sSt = sS + 64 * kAmP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int img = blockIdx.x / H, head = blockIdx.x % H;
+    const int64_t row0 = (int64_t)img * S;
+    const int ld = 3 * H * kAbD, ldo = H * kAbD;
+    const float scale = 0.125f;
+
+    for (int i = tid; i < 64 * 32; i += 128) {
+        const int r = i >> 5, w = i & 31;
+        uint32_t q = 0, k = 0, v = 0, o = 0;
+        if (r < S) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(qkv + (row0 + r) * ld + head * kAbD);
+            q = src[w];
+            k = src[w + (H * kAbD) / 2];
+            v = src[w + H * kAbD];
+            o = reinterpret_cast<const uint32_t *>(g_out + (row0 + r) * ldo + head * kAbD)[w];
+        }
+        *reinterpret_cast<uint32_t *>(sQ + r * kAmP + 2 * w) = q;
+        *reinterpret_cast<uint32_t *>(sK + r * kAmP + 2 * w) = k;
+        *reinterpret_cast<uint32_t *>(sV + r * kAmP + 2 * w) = v;
+        *reinterpret_cast<uint32_t *>(sG + r * kAmP + 2 * w) = o;
+        const T *qe = reinterpret_cast<const T *>(&q), *ke = reinterpret_cast<const T *>(&k), *oe = reinterpret_cast<const T *>(&o);
+        sQt[(2 * w) * kAmP + r] = qe[0];
+        sQt[(2 * w + 1) * kAmP + r] = qe[1];
+        sKt[(2 * w) * kAmP + r] = ke[0];
+        sKt[(2 * w + 1) * kAmP + r] = ke[1];
+        sGt[(2 * w) * kAmP + r] = oe[0];
+        sGt[(2 * w + 1) * kAmP + r] = oe[1];
+    }
+    __syncthreads();
+
+    const int m0 = 16 * warp;
+    {
+        // scores and dP for rows m0 .. m0+15
+        float sc[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f, dp[nt][e] = 0.f;
+        warp_mma_64<T>(sc, sQ, sK, m0, g, t);
+        warp_mma_64<T>(dp, sG, sV, m0, g, t);
+        // element e of tile nt: row m0 + g + 8 * (e >> 1), column 8 nt + 2 t + (e & 1)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * nt + 2 * t + e;
+                    float &x = sc[nt][2 * h + e];
+                    x = col < S ? x * scale : -INFINITY;
+                    mx = fmaxf(mx, x);
+                }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float &x = sc[nt][2 * h + e];
+                    x = __expf(x - mx);  // exp(-inf) = 0 for the padded columns
+                    sum += x;
+                }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = 1.f / sum;
+            float delta = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    sc[nt][2 * h + e] *= inv;
+                    delta += sc[nt][2 * h + e] * dp[nt][2 * h + e];
+                }
+            delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+            delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+            const int row = m0 + g + 8 * h;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int col = 8 * nt + 2 * t;
+                const float p0 = sc[nt][2 * h], p1 = sc[nt][2 * h + 1];
+                const float d0 = p0 * (dp[nt][2 * h] - delta) * scale, d1 = p1 * (dp[nt][2 * h + 1] - delta) * scale;
+                *reinterpret_cast<uint32_t *>(sP + row * kAmP + col) = pack2<T>(p0, p1);
+                *reinterpret_cast<uint32_t *>(sS + row * kAmP + col) = pack2<T>(d0, d1);
+                sPt[col * kAmP + row] = from_float<T>(p0);
+                sPt[(col + 1) * kAmP + row] = from_float<T>(p1);
+                sSt[col * kAmP + row] = from_float<T>(d0);
+                sSt[(col + 1) * kAmP + row] = from_float<T>(d1);
+            }
+        }
+    }
+    __syncthreads();
+
+    // dQ = dS K, dK = dS^T Q, dV = P^T dO for rows m0 .. m0+15
+    float acc[8][4];
+    auto store = [&](int which) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = m0 + g + 8 * h;
+            if (row < S) {
+                T *dst = g_qkv + (row0 + row) * ld + which * H * kAbD + head * kAbD;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+                    *reinterpret_cast<uint32_t *>(dst + 8 * nt + 2 * t) = pack2<T>(acc[nt][2 * h], acc[nt][2 * h + 1]);
+            }
+        }
+    };
+    auto clear = [&]() {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+    };
+    clear();
+    warp_mma_64<T>(acc, sS, sKt, m0, g, t);
+    store(0);
+    clear();
+    warp_mma_64<T>(acc, sSt, sQt, m0, g, t);
+    store(1);
+    clear();
+    warp_mma_64<T>(acc, sPt, sGt, m0, g, t);
+    store(2);
+}
+
+static int g_attention_bwd_impl = 0;  // 0 = mma.sync kernel, 1 = fp32 CUDA-core kernel
+
 }  // namespace ll
 
 using namespace ll;
@@ -300,8 +549,14 @@ using namespace ll;
 extern "C" int ll_transpose_pad(const void *src, void *dst, int64_t R, int C, int64_t Rpad, ll_stream_t stream)
 {
     LL_REQUIRE(src && dst && R > 0 && C > 0 && Rpad >= R, "transpose_pad: bad arguments");
-    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((Rpad + 31) / 32));
-    transpose_pad_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), R, C, Rpad);
+    const bool fast = (C % 2 == 0) && (Rpad % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0;
+    if (fast) {
+        dim3 grid((unsigned)((C + 63) / 64), (unsigned)((Rpad + 63) / 64));
+        transpose_pad_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), R, C, Rpad);
+    } else {
+        dim3 grid((unsigned)((C + 31) / 32), (unsigned)((Rpad + 31) / 32));
+        transpose_pad_scalar_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), R, C, Rpad);
+    }
     LL_LAUNCH_CHECK();
     return LL_OK;
 }
@@ -321,7 +576,8 @@ extern "C" int ll_colsum(const void *src, int64_t R, int C, int dtype, float *ou
 extern "C" int ll_quickgelu_forward(const void *u, void *f, int64_t n, int dtype, ll_stream_t stream)
 {
     LL_REQUIRE(u && f && n > 0, "quickgelu_forward: bad arguments");
-    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
+    LL_REQUIRE(((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(f)) & 15) == 0, "quickgelu_forward: tensors must be 16-byte aligned");
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n / 8 + 255) / 256, (int64_t)num_sms() * 16));
     cudaStream_t s = as_stream(stream);
     LL_DISPATCH_16(dtype, (quickgelu_forward_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half *>(u), static_cast<__half *>(f), n)),
                    (quickgelu_forward_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(u), static_cast<__nv_bfloat16 *>(f), n)), "quickgelu_forward");
@@ -332,7 +588,8 @@ extern "C" int ll_quickgelu_forward(const void *u, void *f, int64_t n, int dtype
 extern "C" int ll_quickgelu_backward(const void *u, const void *g_f, void *g_u, int64_t n, int dtype, ll_stream_t stream)
 {
     LL_REQUIRE(u && g_f && g_u && n > 0, "quickgelu_backward: bad arguments");
-    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
+    LL_REQUIRE(((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(g_f) | reinterpret_cast<uintptr_t>(g_u)) & 15) == 0, "quickgelu_backward: tensors must be 16-byte aligned");
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n / 8 + 255) / 256, (int64_t)num_sms() * 16));
     cudaStream_t s = as_stream(stream);
     LL_DISPATCH_16(dtype, (quickgelu_backward_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half *>(u), static_cast<const __half *>(g_f), static_cast<__half *>(g_u), n)),
                    (quickgelu_backward_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(u), static_cast<const __nv_bfloat16 *>(g_f), static_cast<__nv_bfloat16 *>(g_u), n)), "quickgelu_backward");
@@ -382,8 +639,27 @@ extern "C" int ll_attention_backward(const void *qkv, const void *g_out, void *g
     }
     const unsigned grid = (unsigned)(batch * H);
     cudaStream_t s = as_stream(stream);
+    if (g_attention_bwd_impl == 0) {
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            LL_CUDA_CHECK(cudaFuncSetAttribute(attention_backward_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAmSmem));
+            LL_CUDA_CHECK(cudaFuncSetAttribute(attention_backward_mma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAmSmem));
+            attr2_set = true;
+        }
+        LL_DISPATCH_16(dtype, (attention_backward_mma_kernel<__half><<<grid, 128, kAmSmem, s>>>(static_cast<const __half *>(qkv), static_cast<const __half *>(g_out), static_cast<__half *>(g_qkv), S, H)),
+                       (attention_backward_mma_kernel<__nv_bfloat16><<<grid, 128, kAmSmem, s>>>(static_cast<const __nv_bfloat16 *>(qkv), static_cast<const __nv_bfloat16 *>(g_out), static_cast<__nv_bfloat16 *>(g_qkv), S, H)), "attention_backward");
+        LL_LAUNCH_CHECK();
+        return LL_OK;
+    }
     LL_DISPATCH_16(dtype, (attention_backward_kernel<__half><<<grid, 128, kAbSmem, s>>>(static_cast<const __half *>(qkv), static_cast<const __half *>(g_out), static_cast<__half *>(g_qkv), S, H)),
                    (attention_backward_kernel<__nv_bfloat16><<<grid, 128, kAbSmem, s>>>(static_cast<const __nv_bfloat16 *>(qkv), static_cast<const __nv_bfloat16 *>(g_out), static_cast<__nv_bfloat16 *>(g_qkv), S, H)), "attention_backward");
     LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+extern "C" int ll_attention_backward_set_impl(int impl)
+{
+    LL_REQUIRE(impl == 0 || impl == 1, "attention_backward_set_impl: 0 = mma.sync kernel, 1 = fp32 CUDA-core kernel");
+    g_attention_bwd_impl = impl;
     return LL_OK;
 }

@@ -58,6 +58,18 @@ def _worker(rank, world, port, tmp):
         lin.weight.fill_(0.5), lin.bias.zero_()
     lin(torch.full((4, 3), float(rank + 1))).sum().backward()
     allreduce_mean_(list(lin.parameters()))
+    # several buckets (bucket_bytes smaller than the gradients) and a 16-bit wire dtype give the same mean
+    big = [torch.nn.Parameter(torch.zeros(n)) for n in (300, 7, 1200, 64)]
+    for i, p in enumerate(big):
+        p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+    allreduce_mean_(big, bucket_bytes=2048)
+    for i, p in enumerate(big):
+        assert torch.equal(p.grad, torch.full_like(p, 1.5 * (i + 1)))
+    for i, p in enumerate(big):
+        p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+    allreduce_mean_(big, comm_dtype=torch.float16, bucket_bytes=1024)
+    for i, p in enumerate(big):
+        assert p.grad.dtype == torch.float32 and torch.equal(p.grad, torch.full_like(p, 1.5 * (i + 1)))
     assert torch.allclose(lin.weight.grad, torch.full((2, 3), 4 * 1.5))
     assert torch.allclose(lin.bias.grad, torch.full((2,), 4.0))
     dist.barrier()

@@ -77,6 +77,28 @@ def _worker(rank, world, port, tmp):
         dist.all_reduce(t)
         g.copy_(t / world)
     assert all(torch.allclose(p.grad, g) for p, g in zip(params, g0))
+
+    # unfrozen CLIP tower (2 blocks to keep it short), data parallel: different data per rank, bf16 gradient
+    # buckets; after one fit() step every rank holds the same parameters, and they moved
+    from lossyless_b200.learnable_compressors import LearnableCompressor, default_clip_hparams
+
+    hp = default_clip_hparams(distortion="BINCE", beta=1e-2, max_steps=100, n_data=5000, is_frozen=False)
+    torch.manual_seed(0)
+    model = LearnableCompressor(hp)
+    enc = model.p_ZlX.mapper.encoder
+    del enc.transformer.resblocks[2:]
+    enc.layers = 2
+    model = model.cuda().train()
+    w0 = enc.transformer.resblocks[1].mlp.c_fc.weight.detach().clone()
+    g = torch.Generator().manual_seed(50 + rank)
+    batch = (torch.randn(4, 3, 224, 224, generator=g).cuda(), (None, torch.randn(4, 3, 224, 224, generator=g).cuda()))
+    torch.manual_seed(9 + rank)
+    model.fit([batch], grad_comm_dtype=torch.bfloat16)
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    other_flat = flat.clone()
+    dist.broadcast(other_flat, src=0)
+    assert torch.equal(flat, other_flat), "ranks diverged after the gradient all-reduce"
+    assert (enc.transformer.resblocks[1].mlp.c_fc.weight.detach() - w0).abs().max().item() > 0
     dist.barrier()
     dist.destroy_process_group()
 

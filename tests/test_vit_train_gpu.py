@@ -50,6 +50,10 @@ def test_quickgelu(cuda_device, dtype):
     tol = 1e-2 if dtype == torch.bfloat16 else 2e-3
     assert (f.float() - fr).abs().max().item() < tol * fr.abs().max().item()
     assert (gu.float() - ur.grad).abs().max().item() < tol * ur.grad.abs().max().item()
+    # a length that is not a multiple of the 8-element vector
+    f2 = torch.empty(13, dtype=dtype, device=cuda_device)
+    N.call("ll_quickgelu_forward", N.ptr(u), N.ptr(f2), 13, N.dtype_code(u), N.stream())
+    assert torch.equal(f2, f.reshape(-1)[:13])
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -73,9 +77,11 @@ def test_layernorm_backward(cuda_device, dtype, with_res):
     assert _rel(gw, wr.grad) < 1e-4 and _rel(gb, br.grad) < 1e-4  # fp32 accumulation of the 16-bit inputs
 
 
+@pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("S,B,H", [(50, 5, 12), (64, 2, 3), (17, 3, 2)])
-def test_attention_backward(cuda_device, dtype, S, B, H):
+def test_attention_backward(cuda_device, dtype, S, B, H, impl):
+    """impl 0 = mma.sync kernel (P / dS rounded to the 16-bit type between the products), 1 = fp32 kernel"""
     from lossyless_b200 import _native as N
 
     d = 64
@@ -83,7 +89,11 @@ def test_attention_backward(cuda_device, dtype, S, B, H):
     qkv = torch.randn(B * S, 3 * H * d, generator=g, device=cuda_device).to(dtype)
     go = torch.randn(B * S, H * d, generator=g, device=cuda_device).to(dtype)
     gqkv = torch.full_like(qkv, float("nan"))
-    N.call("ll_attention_backward", N.ptr(qkv), N.ptr(go), N.ptr(gqkv), B, S, H, N.dtype_code(qkv), N.stream())
+    N.call("ll_attention_backward_set_impl", impl)
+    try:
+        N.call("ll_attention_backward", N.ptr(qkv), N.ptr(go), N.ptr(gqkv), B, S, H, N.dtype_code(qkv), N.stream())
+    finally:
+        N.call("ll_attention_backward_set_impl", 0)
     ref_in = qkv.float().requires_grad_(True)
     q, k, v = ref_in.reshape(B, S, 3, H, d).permute(2, 0, 3, 1, 4)
     att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1)

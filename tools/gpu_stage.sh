@@ -36,8 +36,10 @@ for s in $STAGES; do
     ncu_codec) run ncu_codec 600 ncu --set full --clock-control none --import-source on -k regex:lanes -s 8 -c 2 -f -o gpurun_out/prof_codec python tools/codec_bench.py --rows 131072
                ncu -i gpurun_out/prof_codec.ncu-rep --page raw --csv > gpurun_out/prof_codec_raw.csv 2>/dev/null
                ncu -i gpurun_out/prof_codec.ncu-rep --page source --csv > gpurun_out/prof_codec_source.csv 2>/dev/null ;;
+    ncu_train) run ncu_train 800 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches_train.csv python tools/train_bench.py --only unfrozen --batches 256 --steps 1 --warmup 1 ;;
     sweep) run sweep 600 python tools/sweep.py --out gpurun_out/sweep.txt ;;
     trainbench) run trainbench 600 python tools/train_bench.py --out gpurun_out/trainbench.txt ;;
+    trainbench_unfrozen) run trainbench_unfrozen 600 python tools/train_bench.py --only unfrozen --steps 10 --out gpurun_out/trainbench_unfrozen.txt ;;
     gemmbench) run gemmbench 200 python tools/gemm_bench.py 256 ;;
     pairbench) run pairbench0 200 env LL_PAIR=0 LL_GEMM_ONLY=1 python tools/gemm_bench.py 256
                run pairbench1 200 env LL_PAIR=1 LL_GEMM_ONLY=1 python tools/gemm_bench.py 256
