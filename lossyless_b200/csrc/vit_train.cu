@@ -348,9 +348,9 @@ constexpr size_t kAbSmem = 4 * 64 * kAbPitch * 2 + 2 * 64 * kAbPPitch * 4;
 // rounded to the 16-bit type as flash-attention backward does) so that every fragment is two plain 32-bit
 // loads per register pair with the reduction index contiguous; the 72-element pitch makes them conflict-free.
 template <typename T>
-struct MmaOp;
+struct TrainMma;
 template <>
-struct MmaOp<__half> {
+struct TrainMma<__half> {
     static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
     {
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -359,7 +359,7 @@ struct MmaOp<__half> {
     }
 };
 template <>
-struct MmaOp<__nv_bfloat16> {
+struct TrainMma<__nv_bfloat16> {
     static __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
     {
         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -393,7 +393,7 @@ __device__ __forceinline__ void warp_mma_64(float (&acc)[8][4], const T *A, cons
         for (int nt = 0; nt < 8; ++nt) {
             const uint32_t b0 = *reinterpret_cast<const uint32_t *>(B + (8 * nt + g) * kAmP + 16 * kk + 2 * t);
             const uint32_t b1 = *reinterpret_cast<const uint32_t *>(B + (8 * nt + g) * kAmP + 16 * kk + 2 * t + 8);
-            MmaOp<T>::mma(acc[nt], a, b0, b1);
+            TrainMma<T>::mma(acc[nt], a, b0, b1);
         }
     }
 }

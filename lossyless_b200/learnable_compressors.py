@@ -248,15 +248,17 @@ def allreduce_mean_(params, group=None, comm_dtype=None, bucket_bytes=32 << 20):
     buckets.append(cur)
     pending = []
     for bucket in buckets:
-        flat = torch.cat([p.grad.reshape(-1).to(dt) for p in bucket])
+        flat = torch.cat([p.grad.reshape(-1) for p in bucket]).to(dt)  # one batched gather + one cast per bucket
         pending.append((bucket, flat, torch.distributed.all_reduce(flat, group=group, async_op=True)))
     for bucket, flat, work in pending:
         work.wait()
-        o = 0
+        mean = flat.to(bucket[0].grad.dtype).div_(world)
+        views, o = [], 0
         for p in bucket:
             n = p.grad.numel()
-            p.grad.copy_(flat[o:o + n].view_as(p.grad).to(p.grad.dtype) / world)
+            views.append(mean[o:o + n].view_as(p.grad))
             o += n
+        torch._foreach_copy_([p.grad for p in bucket], views)  # one multi-tensor scatter per bucket
 
 
 def default_clip_hparams(distortion="lossy_Z", beta=5e-2, max_steps=1000, n_data=50000, clip_state_dict=None,
