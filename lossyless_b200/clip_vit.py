@@ -245,7 +245,7 @@ class VisionTransformer(nn.Module):
         Frozen encoder / no grad: the model's 16-bit dtype (the reference's fp16 ``self.clip(X)``);
         ``out`` optionally receives the result (a contiguous [B, output_dim] view of a larger buffer, for
         pipelined callers).  Unfrozen encoder with grad enabled: float32 z carrying the backward pass."""
-        if self._trainable and torch.is_grad_enabled():
+        if self._trainable and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             if out is not None:
                 raise ValueError("out= is not supported on the fine-tuning path")
             names, params = zip(*self.named_parameters())

@@ -26,6 +26,22 @@ __device__ constexpr int kMOff[4] = {kM0, kM1, kM2, kM3};
 __device__ constexpr int kBOff[4] = {kB0, kB1, kB2, kB3};
 __device__ constexpr int kFOff[4] = {kF0, kF1, kF2, kF3};
 
+// tanh and sigmoid on two MUFU operations each (ex2.approx: relative error 2^-22; approximate division:
+// 2 ulp): absolute error <= ~2e-7, i.e. at the rounding level of the float32 activations they feed.  The
+// full-precision libdevice versions cost ~25 instructions apiece and made the kernel 3x slower; the per-
+// element budget is 24 tanh + 2 sigmoid + 1 log, so these two functions ARE the kernel.
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float tanh_fast(float a)
+{
+    // 1 - 2 / (1 + e^{2a});  e -> inf gives 1, e -> 0 gives -1
+    return 1.f - __fdividef(2.f, 1.f + ex2_approx(a * 2.8853900817779268f));
+}
+
 // logits_cumulative for one scalar; keeps gated activations g[k][j] and tanh values t[k][j]
 struct Trace {
     float g[4][3];
@@ -37,7 +53,7 @@ __device__ __forceinline__ float logits_fwd(const float (&P)[kNP], float v, Trac
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const float a = fmaf(P[kM0 + j], v, P[kB0 + j]);
-        const float t = tanhf(a);
+        const float t = tanh_fast(a);
         tr.t[0][j] = t;
         tr.g[0][j] = fmaf(P[kF0 + j], t, a);
     }
@@ -48,7 +64,7 @@ __device__ __forceinline__ float logits_fwd(const float (&P)[kNP], float v, Trac
             float a = P[kBOff[k] + j];
 #pragma unroll
             for (int i = 0; i < 3; ++i) a = fmaf(P[kMOff[k] + 3 * j + i], tr.g[k - 1][i], a);
-            const float t = tanhf(a);
+            const float t = tanh_fast(a);
             tr.t[k][j] = t;
             tr.g[k][j] = fmaf(P[kFOff[k] + j], t, a);
         }
@@ -103,7 +119,7 @@ __device__ __forceinline__ float logits_bwd(const float (&P)[kNP], float v, cons
     return gv;
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + ex2_approx(-1.4426950408889634f * x)); }
 
 __global__ void eb_pack_params_kernel(const float *m0, const float *m1, const float *m2, const float *m3, const float *m4,
                                       const float *b0, const float *b1, const float *b2, const float *b3, const float *b4,

@@ -335,12 +335,19 @@ attention_kernel(const T *__restrict__ qkv, T *__restrict__ out, int S, int H, f
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
+    // exp2((s - max) * c) as one FFMA + one MUFU per score (ex2.approx.ftz: -inf -> +0 for the masked keys)
+    const float m0s = mx0 * scale_log2e, m1s = mx1 * scale_log2e;
+    auto ex2 = [](float x) {
+        float y;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    };
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        sc[j][0] = exp2f((sc[j][0] - mx0) * scale_log2e);
-        sc[j][1] = exp2f((sc[j][1] - mx0) * scale_log2e);
-        sc[j][2] = exp2f((sc[j][2] - mx1) * scale_log2e);
-        sc[j][3] = exp2f((sc[j][3] - mx1) * scale_log2e);
+        sc[j][0] = ex2(fmaf(sc[j][0], scale_log2e, -m0s));
+        sc[j][1] = ex2(fmaf(sc[j][1], scale_log2e, -m0s));
+        sc[j][2] = ex2(fmaf(sc[j][2], scale_log2e, -m1s));
+        sc[j][3] = ex2(fmaf(sc[j][3], scale_log2e, -m1s));
         sum0 += sc[j][0] + sc[j][1];
         sum1 += sc[j][2] + sc[j][3];
     }

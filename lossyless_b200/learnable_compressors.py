@@ -19,7 +19,7 @@ from .distributions import CondDist
 from .helpers import BASE_LOG, Annealer, NamespaceMap, OrderedSet, Timer, append_optimizer_scheduler_
 from .rates import get_rate_estimator
 
-__all__ = ["LearnableCompressor", "default_clip_hparams"]
+__all__ = ["LearnableCompressor", "default_clip_hparams", "allreduce_mean_"]
 
 
 class LearnableCompressor(nn.Module):
@@ -197,11 +197,41 @@ class LearnableCompressor(nn.Module):
         self.rate_estimator.make_pickable_()
 
     # -- minimal trainer -----------------------------------------------------------------
-    def fit(self, batches, max_steps=None, grad_clip=3.0, process_group=None, grad_comm_dtype=None):
+    # -- checkpoints (Lightning's file layout, reference main.py:516-547) ------------------
+    def save_checkpoint(self, path, weights_only=True):
+        """``trainer.save_checkpoint(path, weights_only=True)``: ``state_dict`` + ``hyper_parameters`` +
+        step counters under Lightning's key names, so the reference's ``load_from_checkpoint`` and this
+        class's read each other's files (the module / parameter names are the reference's)."""
+        self.rate_estimator.make_pickable_()
+        ckpt = dict(state_dict=self.state_dict(), hyper_parameters=_plain(self.hparams), global_step=self.global_step,
+                    epoch=self.current_epoch)
+        ckpt["pytorch-lightning_version"] = "1.1.5"  # what requirements/environment.yaml pins; informational
+        torch.save(ckpt, path)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location="cpu", strict=True, **kwargs):
+        """``LightningModule.load_from_checkpoint``: rebuild from ``hyper_parameters`` (``kwargs`` override
+        top-level entries, as Lightning's do) and load ``state_dict``.  Accepts a path or an already loaded
+        checkpoint dict."""
+        ckpt = checkpoint_path if isinstance(checkpoint_path, dict) else torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        if "state_dict" not in ckpt or "hyper_parameters" not in ckpt:
+            raise KeyError("not a Lightning checkpoint: need 'state_dict' and 'hyper_parameters'")
+        hp = dict(ckpt["hyper_parameters"])
+        hp.update(kwargs)
+        model = cls(NamespaceMap(hp))
+        model.load_state_dict(ckpt["state_dict"], strict=strict)
+        model.global_step = int(ckpt.get("global_step", 0))
+        model.current_epoch = int(ckpt.get("epoch", 0))
+        return model
+
+    def fit(self, batches, max_steps=None, grad_clip=3.0, process_group=None, grad_comm_dtype=None, callbacks=()):
         """Lightning-free ``Trainer.fit``: per batch, one pass per optimiser ("main" then "coder");
         ``gradient_clip_val=3`` as config/main.yaml; with ``torch.distributed`` initialised the
         trainable gradients are all-reduced (mean) in flat buckets per pass (``allreduce_mean_``;
         ``grad_comm_dtype=torch.bfloat16`` for the bf16 buckets of an unfrozen encoder)."""
+        for cb in callbacks:  # BaseFinetuning hooks run before the optimisers see the parameters
+            if hasattr(cb, "freeze_before_training"):
+                cb.freeze_before_training(self)
         optimizers, schedulers = self.configure_optimizers()
         is_dist = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.train()
@@ -222,6 +252,15 @@ class LearnableCompressor(nn.Module):
         for s in schedulers:
             s["scheduler"].step()
         return self.logged
+
+
+def _plain(d):
+    """NamespaceMap -> nested plain dicts (what ends up under 'hyper_parameters'); dtypes become strings."""
+    if isinstance(d, dict):
+        return {k: _plain(v) for k, v in d.items()}
+    if isinstance(d, (list, tuple)):
+        return type(d)(_plain(v) for v in d)
+    return d
 
 
 def allreduce_mean_(params, group=None, comm_dtype=None, bucket_bytes=32 << 20):

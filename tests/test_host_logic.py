@@ -95,3 +95,67 @@ def test_downstream_linear_eval_runs():
     Z = (centers[Y] + rng.normal(size=(600, 512))).astype(np.float32)
     res = mod.linear_eval(Z[:400], Y[:400], Z[400:], Y[400:])
     assert res["test/pred/acc"] > 0.95 and abs(res["test/pred/err"] - (1 - res["test/pred/acc"])) < 1e-12
+
+
+def _banana_hparams():
+    from lossyless_b200.helpers import NamespaceMap
+
+    return NamespaceMap(
+        stage="feat", data=dict(shape=(2,), mode="distribution", max_steps=50, length=1024000),
+        encoder=dict(z_dim=2, fam="deterministic", fam_kwargs={}, arch="mlp", arch_kwargs=dict(hid_dim=32, n_hid_layers=1, activation="Softplus")),
+        rate=dict(mode="H_factorized", factor_beta=1, kwargs=dict(z_dim=2, kwargs_ent_bottleneck=dict(init_scale=10, filters=[3, 3, 3, 3]))),
+        distortion=dict(mode="direct", factor_beta=1, kwargs=dict(z_dim=2, y_shape=(2,), arch="mlp", arch_kwargs=dict(hid_dim=32, n_hid_layers=1, activation="Softplus"))),
+        featurizer=dict(is_features=True, loss=dict(beta=0.07, beta_anneal="constant")),
+        evaluation=dict(featurizer=dict(is_online=False)),
+        optimizer_feat=dict(mode="Adam", kwargs=dict(lr=3e-3)), optimizer_coder=dict(mode="Adam", kwargs=dict(lr=3e-3)),
+        scheduler_feat=None, scheduler_coder=None)
+
+
+def test_checkpoint_layout_roundtrip(tmp_path):
+    """save_checkpoint writes Lightning's layout (main.py:516-547: state_dict + hyper_parameters);
+    load_from_checkpoint rebuilds the module from it, keyword overrides included."""
+    import torch
+
+    from lossyless_b200.learnable_compressors import LearnableCompressor
+
+    torch.manual_seed(0)
+    model = LearnableCompressor(_banana_hparams())
+    model.global_step = 17
+    path = tmp_path / "best_feat.ckpt"
+    model.save_checkpoint(path)
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert {"state_dict", "hyper_parameters", "global_step", "epoch"} <= set(raw)
+    assert any(k.startswith("p_ZlX.mapper.") for k in raw["state_dict"])
+    assert any(k.startswith("rate_estimator.entropy_bottleneck.") for k in raw["state_dict"])
+    assert isinstance(raw["hyper_parameters"], dict) and type(raw["hyper_parameters"]["rate"]) is dict
+    back = LearnableCompressor.load_from_checkpoint(path, stage="comm")
+    assert back.global_step == 17 and back.stage == "comm"
+    for (k, a), (_, b) in zip(model.state_dict().items(), back.state_dict().items()):
+        assert torch.equal(a, b), k
+    with pytest.raises(KeyError):
+        LearnableCompressor.load_from_checkpoint({"weights": {}})
+
+
+def test_freezer_callback():
+    """Freezer("p_ZlX.mapper") (config/finetune/freezer.yaml): the encoder leaves the optimiser's
+    parameter set; on a CLIP tower it also switches back to the frozen runner."""
+    from lossyless_b200.callbacks import Freezer
+    from lossyless_b200.clip_vit import VisionTransformer
+    from lossyless_b200.learnable_compressors import LearnableCompressor
+
+    model = LearnableCompressor(_banana_hparams())
+    n_all = len(model.get_specific_parameters("main"))
+    cb = Freezer("p_ZlX.mapper")
+    assert cb.get_model(model) is model.p_ZlX.mapper
+    cb.freeze_before_training(model)
+    assert all(not p.requires_grad for p in model.p_ZlX.mapper.parameters())
+    opts, _ = model.configure_optimizers()
+    n_opt = sum(len(g["params"]) for g in opts[0].param_groups)
+    assert n_opt == n_all - len(list(model.p_ZlX.mapper.parameters()))
+
+    vit = VisionTransformer(224, 32, 768, 1, 12, 512).unfreeze_()
+    assert vit._trainable and vit.proj.dtype == torch.float32 and vit.proj.requires_grad
+    holder = torch.nn.Module()
+    holder.enc = vit
+    Freezer("enc").freeze_before_training(holder)
+    assert not vit._trainable and not any(p.requires_grad for p in vit.parameters())

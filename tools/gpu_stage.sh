@@ -33,7 +33,7 @@ for s in $STAGES; do
            done ;;
     e2eprobe) run e2eprobe 300 python tools/e2e_probe.py ;;
     codecbench) run codecbench 600 python tools/codec_bench.py --out gpurun_out/codecbench.txt ;;
-    ncu_codec) run ncu_codec 600 ncu --set full --clock-control none --import-source on -k regex:lanes -s 8 -c 2 -f -o gpurun_out/prof_codec python tools/codec_bench.py --rows 131072
+    ncu_codec) run ncu_codec 600 ncu --set full --clock-control none --import-source on -k regex:lanes -s 17 -c 2 -f -o gpurun_out/prof_codec python tools/codec_bench.py --rows 131072
                ncu -i gpurun_out/prof_codec.ncu-rep --page raw --csv > gpurun_out/prof_codec_raw.csv 2>/dev/null
                ncu -i gpurun_out/prof_codec.ncu-rep --page source --csv > gpurun_out/prof_codec_source.csv 2>/dev/null ;;
     ncu_train) run ncu_train 800 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches_train.csv python tools/train_bench.py --only unfrozen --batches 256 --steps 1 --warmup 1 ;;
