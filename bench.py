@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fuse-ln", action="store_true", help="A/B: run ln_1 / ln_2 as separate kernels")
+    ap.add_argument("--attn-impl", type=int, default=-1, help="A/B: ll_attention_set_impl (0 cp.async, 1 tcgen05, 2 TMA); -1 = library default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -238,6 +239,10 @@ def main():
         comp.clip.set_chunk(args.chunk)
     if args.no_fuse_ln:
         comp.clip.set_fuse_layernorm(False)
+    if args.attn_impl >= 0:
+        from lossyless_b200 import _native as _N
+
+        _N.call("ll_attention_set_impl", args.attn_impl)
     B = args.batch
     # encode shards by image: every rank codes its own independent batch, no collective on the path
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)

@@ -237,8 +237,9 @@ int ll_layernorm(const void *x, int64_t rows, int width, const float *gamma, con
                  void *h, int dtype, ll_stream_t stream);
 int ll_attention(const void *qkv, void *out, int64_t batch, int S, int H, int dtype,
                  ll_stream_t stream);
-/* attention implementation: 0 = mma.sync kernel (default, 1.98 ms vs 2.18 ms per 1512-image step),
- * 1 = persistent tcgen05 kernel (attention_sm100.cu) */
+/* attention implementation: 0 = mma.sync kernel, Q/K/V staged with cp.async; 1 = persistent tcgen05 kernel
+ * (attention_sm100.cu); 2 = the mma.sync kernel with TMA loads / stores (fewer issued instructions; the
+ * kernel is issue-bound, profiles/r01_ncu_attention_fwd_summary.txt).  Same results within rounding. */
 int ll_attention_set_impl(int impl);
 
 /* Stand-alone GEMM entry (tests, micro-benchmarks):  D[M,N] = act(A[M,K] @ W[N,K]^T + bias)

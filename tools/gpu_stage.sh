@@ -31,6 +31,7 @@ for s in $STAGES; do
              run ab_sep$i 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-fuse-ln
              run ab_fused$i 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
            done ;;
+    ab_attn) for i in 0 2 0 2; do run ab_attn$i 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --attn-impl $i; done ;;
     e2eprobe) run e2eprobe 300 python tools/e2e_probe.py ;;
     codecbench) run codecbench 600 python tools/codec_bench.py --out gpurun_out/codecbench.txt ;;
     ncu_codec) run ncu_codec 600 ncu --set full --clock-control none --import-source on -k regex:lanes -s 17 -c 2 -f -o gpurun_out/prof_codec python tools/codec_bench.py --rows 131072
