@@ -187,7 +187,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1512, help="images per step per GPU (4 full 378-image encoder passes)")
+    ap.add_argument("--batch", type=int, default=1512, help="images per step per GPU (one 1512-image encoder pass = 4 full rounds of 74 CTA pairs x 256 token rows)")
     ap.add_argument("--chunk", type=int, default=0, help="images per internal ViT pass (0 = library default)")
     ap.add_argument("--cpu-images", type=int, default=16, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -212,7 +212,7 @@ int ll_vit_forward(ll_vit_t *v, const void *x, int x_dtype, int64_t batch, void 
                    void *workspace, int64_t workspace_bytes, ll_stream_t stream);
 /* number of kernel launches one ll_vit_forward of `batch` images issues */
 int64_t ll_vit_launches(const ll_vit_t *v, int64_t batch);
-/* max images per internal pass (default 378 = one full round of 74 CTA pairs x 256 token rows);
+/* max images per internal pass (default 1512 = four full rounds of 74 CTA pairs x 256 token rows);
  * a batch is split into near-equal passes */
 int ll_vit_set_chunk(ll_vit_t *v, int64_t chunk);
 /* ln_1 / ln_2 of every ResidualAttentionBlock (clip/model.py) are by default folded into the GEMMs either

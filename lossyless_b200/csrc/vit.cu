@@ -767,7 +767,10 @@ extern "C" int ll_vit_create(const ll_vit_config_t *cfg, const ll_vit_weights_t 
     v->grid = g;
     v->tokens = g * g + 1;
     v->kpatch = 3 * cfg->patch * cfg->patch;
-    v->chunk = 378;  // 74 CTA pairs x 256 rows = 18 944 tokens: every GEMM of a pass is a whole number of rounds
+    // 1512 images = 75 600 tokens = 4 full rounds of 74 CTA pairs x 256 rows.  Measured in situ (bench.py, 1512 images per
+    // step): passes of 378 / 756 / 1512 images -> 97.8 / 103.5 / 109.2 k img/s -- the fixed cost of the 50 GEMM launches of a
+    // pass (prologue fill, last-tile drain) is amortised over 4x the work, which outweighs keeping a pass L2-resident.
+    v->chunk = 1512;
     // fold ln_1 into in_proj and ln_2 into c_fc (device, once)
     const int W = cfg->width;
     auto fold = [&](const void *Wsrc, const float *bias, const float *gamma, const float *beta, int N, void **Wf, float **bf) -> int {
@@ -839,7 +842,7 @@ extern "C" int ll_vit_forward(ll_vit_t *v, const void *x, int x_dtype, int64_t b
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
     const int esz_in = x_dtype == LL_F32 ? 4 : 2;
     const int64_t img = 3LL * v->cfg.res * v->cfg.res;
-    // near-equal passes (e.g. 1024 -> 3 x 342 rather than 378 + 378 + 268): no under-filled last pass
+    // near-equal passes (e.g. 2048 -> 2 x 1024 rather than 1512 + 536): no under-filled last pass
     const int64_t passes = (batch + v->chunk - 1) / v->chunk;
     const int64_t per = (batch + passes - 1) / passes;
     for (int64_t b0 = 0; b0 < batch; b0 += per) {

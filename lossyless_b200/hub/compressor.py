@@ -232,12 +232,14 @@ class ClipCompressor(nn.Module):
         return out_host[:total], X_host.shape[0], out_host
 
     @torch.no_grad()
-    def compress_stream(self, host_batches, sub_batch=378):
+    def compress_stream(self, host_batches, sub_batch=1512):
         """``compress_dataset``'s loop as a software pipeline: yields ``(records, n_images)`` per batch of
-        ``host_batches`` (same inputs as ``compress_batch_to_host``), in order.  Batch i + 1 is enqueued (its H2D
+        ``host_batches`` (same inputs as ``compress_batch_to_host``), in order.  With the default ``sub_batch``
+        a batch of up to 1512 images is ONE H2D copy and ONE encoder pass (large passes amortise the per-launch
+        cost of the encoder's 50 GEMMs); the overlap of PCIe and tensor cores then happens across batches.  Batch i + 1 is enqueued (its H2D
         copies start as soon as a staging slot frees up) BEFORE the host waits for batch i, and batch i's records
-        come back on a separate D2H stream, so neither the first H2D copy of a batch nor the read-back of the
-        previous one is exposed.  ``records`` is a view of a pinned buffer that is valid until the generator
+        come back on a separate D2H stream once the host has seen batch i finish, so neither the first H2D copy
+        of a batch nor the read-back of the previous one is exposed.  ``records`` is a view of a pinned buffer that is valid until the generator
         is resumed."""
         dev = torch.device(self.device)
         main = torch.cuda.current_stream(dev)
@@ -245,20 +247,29 @@ class ClipCompressor(nn.Module):
             self._d2h_stream = torch.cuda.Stream(dev)
         d2h = self._d2h_stream
 
+        # a small ring of page-locked size words, allocated once: a page-locked allocation between two launches
+        # forbids their concurrency (CUDA implicit synchronisation), which would serialise batch i+1's H2D copy
+        # behind batch i's kernels
+        if getattr(self, "_size_ring", None) is None:
+            self._size_ring = torch.empty(8, dtype=torch.int64).pin_memory()
+            self._size_next = 0
+
         def enqueue(X_host):
             packed, offsets = self._encode_host_batch(X_host, sub_batch)
             done = torch.cuda.Event()
             done.record(main)
-            total_host = torch.empty(1, dtype=torch.int64).pin_memory()
-            with torch.cuda.stream(d2h):
-                d2h.wait_event(done)
-                total_host.copy_(offsets[-1:], non_blocking=True)
-                sized = torch.cuda.Event()
-                sized.record(d2h)
-            return dict(packed=packed, offsets=offsets, total=total_host, sized=sized, n=X_host.shape[0], src=X_host)
+            total_host = self._size_ring[self._size_next: self._size_next + 1]
+            self._size_next = (self._size_next + 1) % self._size_ring.numel()
+            return dict(packed=packed, offsets=offsets, total=total_host, done=done, n=X_host.shape[0], src=X_host)
 
         def finish(job):
-            job["sized"].synchronize()
+            # Everything batch i needs from the D2H stream is issued HERE, after the host has seen batch i finish:
+            # enqueue(i + 1) runs before finish(i), so a wait for batch i + 1 queued on the D2H stream ahead of
+            # batch i's read-back would hold the host -- and with it the next H2D copy -- until batch i + 1 is done.
+            job["done"].synchronize()
+            with torch.cuda.stream(d2h):
+                job["total"].copy_(job["offsets"][-1:], non_blocking=True)
+            d2h.synchronize()
             total = int(job["total"][0])
             out = getattr(self, "_stream_out", None)
             if out is None or out.numel() < total:
@@ -278,12 +289,16 @@ class ClipCompressor(nn.Module):
             yield finish(pending)
 
     def _h2d_pipe(self, dev, X_host, sub_batch):
-        """Two device staging slots + a copy stream, created once per (dtype, sub_batch)."""
-        key = (str(dev), X_host.dtype, sub_batch, tuple(X_host.shape[1:]))
+        """Two device staging slots + a copy stream per (dtype, image shape); the slots hold
+        ``min(sub_batch, batch)`` images and only ever grow."""
+        key = (str(dev), X_host.dtype, tuple(X_host.shape[1:]))
+        need = min(sub_batch, X_host.shape[0])
         pipe = getattr(self, "_pipe", None)
-        if pipe is None or pipe["key"] != key:
-            pipe = dict(key=key, stream=torch.cuda.Stream(dev),
-                        buf=[torch.empty((sub_batch,) + tuple(X_host.shape[1:]), dtype=X_host.dtype, device=dev) for _ in range(2)],
+        if pipe is None or pipe["key"] != key or pipe["cap"] < need:
+            if pipe is not None:
+                pipe["stream"].synchronize()  # nothing may still be copying into the slots we drop
+            pipe = dict(key=key, cap=need, stream=torch.cuda.Stream(dev),
+                        buf=[torch.empty((need,) + tuple(X_host.shape[1:]), dtype=X_host.dtype, device=dev) for _ in range(2)],
                         ready=[torch.cuda.Event(), torch.cuda.Event()], consumed=[None, None], next=0)
             self._pipe = pipe
         return pipe

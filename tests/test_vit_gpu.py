@@ -83,7 +83,8 @@ def test_vit_b32_vs_golden(cuda_device, golden_dir):
     err = np.abs(z - g["z"])
     assert err.max() < 5e-2 and err.mean() < 8e-3, (err.max(), err.mean())
     assert vit(x.float()).float().cpu().numpy().tolist() == z.tolist()  # fp32 input is cast on load
-    xb = x.repeat(200, 1, 1, 1)  # 400 images: two internal passes (378-image limit) of 200
+    vit.set_chunk(378)
+    xb = x.repeat(200, 1, 1, 1)  # 400 images: two internal passes (378-image limit set above) of 200
     zb = vit(xb).float().cpu().numpy()
     assert np.array_equal(zb[0::2], np.repeat(z[:1], 200, 0)) and np.array_equal(zb[1::2], np.repeat(z[1:], 200, 0))
     assert vit.launches(400) == 2 * (5 + 5 * 12)  # ln_1 / ln_2 are fused into the GEMMs

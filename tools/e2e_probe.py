@@ -85,3 +85,32 @@ for sb in (189, 756, 1512):
         for _ in comp.compress_stream((X_host for _ in range(k)), sub_batch=sb):
             pass
     print(f"compress_stream fp16, sub_batch {sb}: {wall(run):.3f} ms/batch")
+
+# how long the 455 MB H2D copy itself takes while the encoder runs (copy timed with events on its own stream)
+def copy_ms_under_load():
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        c0.record(side)
+        dummy.copy_(X_host, non_blocking=True)
+        c1.record(side)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    return c0.elapsed_time(c1)
+
+
+t = sorted(copy_ms_under_load() for _ in range(5))[2]
+print(f"455 MB pinned H2D while the encoder runs: {t:.3f} ms -> {X_host.numel() * 2 / t / 1e6:.1f} GB/s")
+torch.cuda.synchronize()
+c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+c0.record()
+dummy.copy_(X_host, non_blocking=True)
+c1.record()
+torch.cuda.synchronize()
+print(f"455 MB pinned H2D alone: {c0.elapsed_time(c1):.3f} ms -> {X_host.numel() * 2 / c0.elapsed_time(c1) / 1e6:.1f} GB/s")
+for sb in (378, 504):
+    def run(k, sb=sb):
+        for _ in comp.compress_stream((X_host for _ in range(k)), sub_batch=sb):
+            pass
+    print(f"compress_stream fp16, sub_batch {sb}: {wall(run):.3f} ms/batch")
