@@ -54,10 +54,12 @@ for s in $STAGES; do
     bnsweep) for bn in 128 192; do run pair378_bn$bn 200 env LL_PAIR=1 LL_BN=$bn LL_GEMM_ONLY=1 python tools/gemm_bench.py 378; done ;;
     ncu_vit) run ncu_vit 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 50 -c 10 -f -o gpurun_out/prof_vit_gemms python tools/vit_once.py
              ncu -i gpurun_out/prof_vit_gemms.ncu-rep --page raw --csv > gpurun_out/prof_vit_gemms_raw.csv 2>/dev/null
+             python tools/ncu_gemm_traffic.py gpurun_out/prof_vit_gemms_raw.csv 1512 gpurun_out/ncu_vit_gemms_dram_traffic.json
+             python tools/ncu_summary.py gpurun_out/prof_vit_gemms_raw.csv > gpurun_out/ncu_vit_gemms_summary.txt
              [ "$(stat -c %s gpurun_out/prof_vit_gemms.ncu-rep 2>/dev/null || echo 0)" -gt 40000000 ] && rm -f gpurun_out/prof_vit_gemms.ncu-rep ;;
     ncu_small) run ncu_small 600 ncu --set full --clock-control none --import-source on -k regex:"attention" -s 10 -c 2 -f -o gpurun_out/prof_small python tools/gemm_bench.py 378
                ncu -i gpurun_out/prof_small.ncu-rep --page raw --csv > gpurun_out/prof_attention_raw.csv 2>/dev/null ;;
     ncu_gemm) run ncu_gemm 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 8 -c 5 -f -o gpurun_out/prof_gemm python tools/gemm_bench.py 256 ;;
-    ncu_list) run ncu_list 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --batch 378 --no-cpu-baseline ;;
+    ncu_list) run ncu_list 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline ;;
   esac
 done
