@@ -275,6 +275,10 @@ int ll_gemm_set_cta_pair(int mode);
 /* dst [C, Rpad] = src [R, C]^T, columns R..Rpad-1 zero (2-byte elements; Rpad >= R).  The token count
  * becomes the K of a weight-gradient GEMM and must be a multiple of 64. */
 int ll_transpose_pad(const void *src, void *dst, int64_t R, int C, int64_t Rpad, ll_stream_t stream);
+/* the same plus colsum[c] += sum_r src[r, c] (float32; the bias gradient of the tensor being transposed for
+ * its weight-gradient GEMM, so it is read once).  C and Rpad even, `dtype` LL_F16 / LL_BF16. */
+int ll_transpose_pad_colsum(const void *src, void *dst, int64_t R, int C, int64_t Rpad, int dtype, float *colsum,
+                            ll_stream_t stream);
 /* out[c] += sum_r src[r, c] (float32 accumulate: bias gradients).  out must be initialised. */
 int ll_colsum(const void *src, int64_t R, int C, int dtype, float *out, ll_stream_t stream);
 /* clip/model.py QuickGELU: f = u * sigmoid(1.702 u);  g_u = g_f * d f / d u.  n elements. */

@@ -308,6 +308,17 @@ def _wgrad(gy, x):
     return _gemm(_transpose_pad(gy), _transpose_pad(x))
 
 
+def _wgrad_bias(gy, x):
+    """(dW, db): the weight gradient as above and db = column sums of gy (float32), taken while gy is being
+    transposed so that it is read once."""
+    R, C = gy.shape
+    Rp = (R + 63) // 64 * 64
+    gyt = torch.empty((C, Rp), dtype=gy.dtype, device=gy.device)
+    db = torch.zeros(C, dtype=torch.float32, device=gy.device)
+    N.call("ll_transpose_pad_colsum", N.ptr(gy), N.ptr(gyt), R, C, Rp, N.dtype_code(gy), N.ptr(db), N.stream())
+    return _gemm(gyt, _transpose_pad(x)), db
+
+
 def _colsum(t):
     out = torch.zeros(t.shape[1], dtype=torch.float32, device=t.device)
     N.call("ll_colsum", N.ptr(t), t.shape[0], t.shape[1], N.dtype_code(t), N.ptr(out), N.stream())
@@ -390,25 +401,21 @@ class _VitTrainFn(torch.autograd.Function):
             wt = vit._train_weights_t(dt, i)
             # x2 = x1 + f @ c_proj^T + b
             g_f = _gemm(g_x, wt["c_proj"])
-            G[p + "mlp.c_proj.weight"] = _wgrad(g_x, f)
-            G[p + "mlp.c_proj.bias"] = _colsum(g_x)
+            G[p + "mlp.c_proj.weight"], G[p + "mlp.c_proj.bias"] = _wgrad_bias(g_x, f)
             g_u = torch.empty_like(u)
             N.call("ll_quickgelu_backward", N.ptr(u), N.ptr(g_f), N.ptr(g_u), u.numel(), N.dtype_code(u), N.stream())
             del g_f
             g_h2 = _gemm(g_u, wt["c_fc"])
-            G[p + "mlp.c_fc.weight"] = _wgrad(g_u, h2)
-            G[p + "mlp.c_fc.bias"] = _colsum(g_u)
+            G[p + "mlp.c_fc.weight"], G[p + "mlp.c_fc.bias"] = _wgrad_bias(g_u, h2)
             del g_u
             g_x1, G[p + "ln_2.weight"], G[p + "ln_2.bias"] = _ln_backward(x1, g_h2, w[p + "ln_2.weight"], g_res=g_x)
             # x1 = x + a @ out_proj^T + b
             g_a = _gemm(g_x1, wt["out_proj"])
-            G[p + "attn.out_proj.weight"] = _wgrad(g_x1, a)
-            G[p + "attn.out_proj.bias"] = _colsum(g_x1)
+            G[p + "attn.out_proj.weight"], G[p + "attn.out_proj.bias"] = _wgrad_bias(g_x1, a)
             g_qkv = torch.empty_like(qkv)
             N.call("ll_attention_backward", N.ptr(qkv), N.ptr(g_a), N.ptr(g_qkv), B, S, vit.heads, N.dtype_code(qkv), N.stream())
             g_h1 = _gemm(g_qkv, wt["in_proj"])
-            G[p + "attn.in_proj_weight"] = _wgrad(g_qkv, h1)
-            G[p + "attn.in_proj_bias"] = _colsum(g_qkv)
+            G[p + "attn.in_proj_weight"], G[p + "attn.in_proj_bias"] = _wgrad_bias(g_qkv, h1)
             del g_qkv, g_a
             g_x, G[p + "ln_1.weight"], G[p + "ln_1.bias"] = _ln_backward(xs, g_h1, w[p + "ln_1.weight"], g_res=g_x1)
             st["saved"][i] = None

@@ -21,8 +21,10 @@ namespace ll {
 // 64 x 64 tiles, 4-byte global accesses on both sides (a warp moves one 128-byte row segment per access).
 // Needs C even and Rpad even (true for every caller: widths and padded token counts are multiples of 64);
 // odd shapes take the scalar kernel below.
+template <typename T, bool kColsum>
 __global__ void __launch_bounds__(256)
-transpose_pad_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int64_t R, int C, int64_t Rpad)
+transpose_pad_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int64_t R, int C, int64_t Rpad,
+                     float *__restrict__ colsum)
 {
     __shared__ uint16_t tile[64][66];
     const int64_t r0 = (int64_t)blockIdx.y * 64;
@@ -45,6 +47,12 @@ transpose_pad_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ ds
         if (c < C && r < Rpad) {
             const uint32_t v = (uint32_t)tile[2 * tx][cl] | ((uint32_t)tile[2 * tx + 1][cl] << 16);
             *reinterpret_cast<uint32_t *>(dst + (int64_t)c * Rpad + r) = v;  // Rpad even: r + 1 < Rpad too
+        }
+        if (kColsum) {
+            // bias gradient on the way: the warp holds column c's 64 rows of this tile (zero beyond R)
+            const T *col0 = reinterpret_cast<const T *>(&tile[2 * tx][cl]), *col1 = reinterpret_cast<const T *>(&tile[2 * tx + 1][cl]);
+            const float part = warp_sum(to_float<T>(*col0) + to_float<T>(*col1));
+            if (tx == 0 && c < C) atomicAdd(colsum + c, part);
         }
     }
 }
@@ -546,13 +554,28 @@ using namespace ll;
         default: return fail(LL_ERR_INVALID, name ": dtype must be LL_F16 or LL_BF16");   \
     }
 
+extern "C" int ll_transpose_pad_colsum(const void *src, void *dst, int64_t R, int C, int64_t Rpad, int dtype, float *colsum,
+                                       ll_stream_t stream)
+{
+    LL_REQUIRE(src && dst && colsum && R > 0 && C > 0 && Rpad >= R, "transpose_pad_colsum: bad arguments");
+    LL_REQUIRE((C % 2 == 0) && (Rpad % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0,
+               "transpose_pad_colsum: needs even C and Rpad and 4-byte aligned tensors");
+    dim3 grid((unsigned)((C + 63) / 64), (unsigned)((Rpad + 63) / 64));
+    auto S = static_cast<const uint16_t *>(src);
+    auto D = static_cast<uint16_t *>(dst);
+    LL_DISPATCH_16(dtype, (transpose_pad_kernel<__half, true><<<grid, 256, 0, as_stream(stream)>>>(S, D, R, C, Rpad, colsum)),
+                   (transpose_pad_kernel<__nv_bfloat16, true><<<grid, 256, 0, as_stream(stream)>>>(S, D, R, C, Rpad, colsum)), "transpose_pad_colsum");
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
 extern "C" int ll_transpose_pad(const void *src, void *dst, int64_t R, int C, int64_t Rpad, ll_stream_t stream)
 {
     LL_REQUIRE(src && dst && R > 0 && C > 0 && Rpad >= R, "transpose_pad: bad arguments");
     const bool fast = (C % 2 == 0) && (Rpad % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0;
     if (fast) {
         dim3 grid((unsigned)((C + 63) / 64), (unsigned)((Rpad + 63) / 64));
-        transpose_pad_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), R, C, Rpad);
+        transpose_pad_kernel<__half, false><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), R, C, Rpad, nullptr);
     } else {
         dim3 grid((unsigned)((C + 31) / 32), (unsigned)((Rpad + 31) / 32));
         transpose_pad_scalar_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), R, C, Rpad);

@@ -30,6 +30,13 @@ class CondDist(nn.Module):
     def forward(self, x):
         return self.Family.from_suff_param(self.mapper(x), **self.kwargs)
 
+    def forward_many(self, xs):
+        """``[forward(x) for x in xs]`` through ONE mapper call on the concatenated batch.  Only valid for
+        mappers that treat samples independently (no batch statistics): the caller checks."""
+        out = self.mapper(torch.cat(list(xs), dim=0))
+        sizes = [x.shape[0] for x in xs]
+        return [self.Family.from_suff_param(o, **self.kwargs) for o in out.split(sizes, dim=0)]
+
     def reset_parameters(self):
         weights_init(self)
 

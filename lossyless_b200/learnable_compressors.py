@@ -67,7 +67,8 @@ class LearnableCompressor(nn.Module):
         """Represent ``x``: codes / (de)quantised features, or the reconstruction."""
         if is_features is None:
             is_features = self.is_features
-        p_Zlx = self.p_ZlX(x)
+        cache = getattr(self, "_view_cache", None)
+        p_Zlx = cache[1] if cache is not None and cache[0] is x else self.p_ZlX(x)
         z = p_Zlx.rsample()
         if is_compress:
             z_hat = self.rate_estimator.compress(z, self)
@@ -81,8 +82,18 @@ class LearnableCompressor(nn.Module):
 
     def step(self, batch, is_rate_only=False):
         x, targets = batch
+        self._view_cache = None
         with Timer() as encoder_timer:
-            p_Zlx = self.p_ZlX(x)  # batch shape [B], event shape [z_dim]
+            x_pos = targets[1] if isinstance(targets, (tuple, list)) and len(targets) > 1 else None
+            if not is_rate_only and self._can_batch_views(x, x_pos):
+                # the contrastive distortion encodes the positive view through `parent(x_pos)` later in this step
+                # (lossyless/distortions.py:305-318): both views go through the CLIP tower in ONE call (twice the
+                # GEMM rows per launch, half the weight-gradient GEMMs when it is unfrozen); forward() below hands
+                # the second half back when it is asked for x_pos.  Same values: the tower has no batch statistics.
+                p_Zlx, p_pos = self.p_ZlX.forward_many([x, x_pos])
+                self._view_cache = (x_pos, p_pos)
+            else:
+                p_Zlx = self.p_ZlX(x)  # batch shape [B], event shape [z_dim]
         z = p_Zlx.rsample()
         z_hat, rates, r_logs, r_other = self.rate_estimator(z, p_Zlx, self)
 
@@ -110,7 +121,16 @@ class LearnableCompressor(nn.Module):
         other.update(d_other)
         other["X"] = x[0].detach().cpu()
         other.update(dict(z=z.detach()))
+        self._view_cache = None
         return loss, logs, other
+
+    def _can_batch_views(self, x, x_pos):
+        from .architectures import PretrainedSSL
+        from .distortions import ContrastiveDistortion
+
+        de = self.distortion_estimator
+        return (isinstance(de, ContrastiveDistortion) and not de.is_already_featurized and torch.is_tensor(x_pos)
+                and isinstance(self.p_ZlX.mapper, PretrainedSSL) and x_pos.shape == x.shape and x_pos.dtype == x.dtype)
 
     @property
     def final_beta_labda(self):

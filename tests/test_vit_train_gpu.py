@@ -32,6 +32,14 @@ def test_transpose_pad_and_colsum(cuda_device):
         assert torch.allclose(s, t.float().sum(0), rtol=1e-5, atol=1e-4)
     with pytest.raises(N.NativeError):
         N.call("ll_transpose_pad", N.ptr(t), N.ptr(t), 4, 4, 2, N.stream())  # Rpad < R
+    # transpose with the column sums (bias gradient) taken on the way
+    for dtype in DTYPES:
+        t = torch.randn(1237, 768, generator=g, device=cuda_device).to(dtype)
+        out = torch.empty((768, 1280), dtype=dtype, device=cuda_device)
+        db = torch.zeros(768, device=cuda_device)
+        N.call("ll_transpose_pad_colsum", N.ptr(t), N.ptr(out), 1237, 768, 1280, N.dtype_code(t), N.ptr(db), N.stream())
+        assert torch.equal(out[:, :1237], t.t()) and not out[:, 1237:].any()
+        assert torch.allclose(db, t.float().sum(0), rtol=1e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
