@@ -45,8 +45,29 @@ for name, M, Nn, K, act, res in shapes:
     mult = 12 if name in ("qkv", "out", "fc1", "fc2") else 1
     tot_ms += ms * mult
     tot_fl += fl * mult
-    print(f"{name:6s} M={M:6d} N={Nn:5d} K={K:5d}  {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  (x{mult})")
+    extra = ""
+    if os.environ.get("LL_CUBLAS"):
+        # library yard-stick on the same shape: cuBLASLt through torch (bias epilogue only; the activation /
+        # residual / LayerNorm-statistics work our epilogue fuses would be extra launches on top of this)
+        def ref(i):
+            torch.nn.functional.linear(As[i % nbuf], W, bias.half())
+
+        for i in range(3):
+            ref(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(reps):
+            ref(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_ref = e0.elapsed_time(e1) / reps
+        cub_ms = globals().get("cub_ms", 0.0) + ms_ref * mult
+        globals()["cub_ms"] = cub_ms
+        extra = f"   cuBLAS {ms_ref * 1e3:8.1f} us {fl / ms_ref / 1e9:7.1f} TFLOP/s"
+    print(f"{name:6s} M={M:6d} N={Nn:5d} K={K:5d}  {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  (x{mult}){extra}")
 print(f"per pass of {n_img} images: GEMM {tot_ms:.3f} ms, {tot_fl / tot_ms / 1e9:.1f} TFLOP/s, {n_img / tot_ms * 1e3:.0f} img/s GEMM-only")
+if os.environ.get("LL_CUBLAS"):
+    print(f"cuBLAS (bias epilogue only) on the same shapes: {cub_ms:.3f} ms, {tot_fl / cub_ms / 1e9:.1f} TFLOP/s")
 
 if os.environ.get("LL_GEMM_ONLY"):
     sys.exit(0)
