@@ -259,6 +259,12 @@ int ll_gemm(const void *A, const void *W, const float *bias, const void *residua
 int ll_gemm_ln(const void *A, const void *W, const float *bias, const void *residual, void *D,
                int64_t M, int N, int K, int dtype, int act, const void *row_stats_in,
                int stats_in_parts, void *row_stats_out, int stat_width, ll_stream_t stream);
+/* D[Mo, No] = A[Kt, Mo]^T @ B[Kt, No] on the same tcgen05 kernel with MN-major operand descriptors: the
+ * weight-gradient contraction dW = dY^T X of a linear layer (torch autograd through nn.Linear in the reference's
+ * unfrozen CLIP tower, lossyless/architectures.py:351-376) taken straight from the row-major activations and
+ * gradients -- no transposed copies.  A, B, D in `dtype` (LL_F16 / LL_BF16), fp32 accumulation.
+ * Mo % 128 == 0, No % 64 == 0, Kt arbitrary (rows past Kt are zero-filled by TMA). */
+int ll_gemm_tn(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, ll_stream_t stream);
 /* Force the GEMM's tile width (64/128/192/256; 0 = automatic wave-aware choice). Tests, tuning. */
 int ll_gemm_set_tile_n(int bn);
 /* CTA-pair (tcgen05 cta_group::2, 256-row tiles) policy: -1 automatic, 0 never, 1 always. */

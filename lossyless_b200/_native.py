@@ -83,6 +83,7 @@ _SIGNATURES = {
     "ll_attention_backward_set_impl": (c_int, [c_int]),
     "ll_gemm": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "ll_clip_preprocess_set_impl": (c_int, [c_int]),
+    "ll_gemm_tn": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "ll_gemm_ln": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
     "ll_gemm_set_tile_n": (c_int, [c_int]),
     "ll_gemm_set_cta_pair": (c_int, [c_int]),

@@ -303,14 +303,26 @@ def _transpose_pad(t):
     return out
 
 
+# Weight gradients: "tn" = ll_gemm_tn, the tcgen05 GEMM reading both operands MN-major straight from the row-major
+# activations / gradients (default); "transpose" = K-major GEMM on zero-padded transposed copies (the first
+# implementation, kept for A/B runs and as a cross-check in the tests).
+WGRAD_IMPL = "tn"
+
+
 def _wgrad(gy, x):
     """dW [N, K] = gy[M, N]^T @ x[M, K] (16-bit result, as autocast produces it)."""
+    if WGRAD_IMPL == "tn":
+        D = torch.empty((gy.shape[1], x.shape[1]), dtype=gy.dtype, device=gy.device)
+        N.call("ll_gemm_tn", N.ptr(gy), N.ptr(x), N.ptr(D), gy.shape[0], gy.shape[1], x.shape[1], N.dtype_code(gy), N.stream())
+        return D
     return _gemm(_transpose_pad(gy), _transpose_pad(x))
 
 
 def _wgrad_bias(gy, x):
-    """(dW, db): the weight gradient as above and db = column sums of gy (float32), taken while gy is being
-    transposed so that it is read once."""
+    """(dW, db): the weight gradient as above and db = column sums of gy (float32); on the transposing path the
+    sums are taken while gy is being transposed so that it is read once."""
+    if WGRAD_IMPL == "tn":
+        return _wgrad(gy, x), _colsum(gy)
     R, C = gy.shape
     Rp = (R + 63) // 64 * 64
     gyt = torch.empty((C, Rp), dtype=gy.dtype, device=gy.device)

@@ -181,6 +181,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int num_m = (M + kTileM - 1) / kTileM;
     const int num_tiles = num_m * num_n;
     const int num_kb = K / kBK;
+    const bool tn = (act & 0x2000) != 0;  // both operands MN-major (transposed): D = A^T B
 
     if (warp == kProducerWarp) {
         // ------------------------------------------------------------ TMA producer
@@ -192,7 +193,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int n0 = (tile % num_n) * BN + (int)cta_rank * S::kBRows;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if constexpr (kCtas == 2) {
+                    if (tn) {
+                        // TN operands (D = A^T B, weight gradients): A is [K rows, M columns], B is [K rows, N columns];
+                        // the same stage bytes arrive as 64-column x 64-row boxes, one per 64-element MN atom
+                        // (rows past the end of K are zero-filled by TMA, so K needs no padding)
+                        if constexpr (kCtas == 2) {
+                            const uint32_t lead_bar = ptx::map_to_cta(&full_bar[stage], 0);
+                            if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+                            for (int h = 0; h < kBM / 64; ++h)
+                                ptx::tma_load_2d_pair(sm_a + stage * kABytes + h * 8192, &tmap_a, lead_bar, m0 + 64 * h, kb * kBK);
+                            for (int h = 0; h < S::kBRows / 64; ++h)
+                                ptx::tma_load_2d_pair(sm_b + stage * S::kBBytes + h * 8192, &tmap_w, lead_bar, n0 + 64 * h, kb * kBK);
+                        } else {
+                            ptx::mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+                            for (int h = 0; h < kBM / 64; ++h)
+                                ptx::tma_load_2d(sm_a + stage * kABytes + h * 8192, &tmap_a, &full_bar[stage], m0 + 64 * h, kb * kBK);
+                            for (int h = 0; h < S::kBRows / 64; ++h)
+                                ptx::tma_load_2d(sm_b + stage * S::kBBytes + h * 8192, &tmap_w, &full_bar[stage], n0 + 64 * h, kb * kBK);
+                        }
+                    } else if constexpr (kCtas == 2) {
                         // both CTAs' bytes are counted on the LEADER's full barrier, which alone arms it
                         const uint32_t lead_bar = ptx::map_to_cta(&full_bar[stage], 0);
                         if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
@@ -224,15 +243,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sm_a + stage * kABytes));
-                    const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sm_b + stage * S::kBBytes));
+                    const uint32_t addr_a = ptx::smem_u32(sm_a + stage * kABytes), addr_b = ptx::smem_u32(sm_b + stage * S::kBBytes);
+                    const uint64_t da = tn ? ptx::make_mnmajor_sw128_desc(addr_a) : ptx::make_kmajor_sw128_desc(addr_a);
+                    const uint64_t db = tn ? ptx::make_mnmajor_sw128_desc(addr_b) : ptx::make_kmajor_sw128_desc(addr_b);
+                    // per K=16 step: K-major +32 B inside the 128 B swizzle row (start-address field += 2);
+                    // MN-major 16 K rows further down (2048 B, field += 128)
+                    const uint64_t kstep = tn ? 128 : 2;
+                    const uint32_t id = tn ? (idesc | (1u << 15) | (1u << 16)) : idesc;
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
-                        // +32 B per K=16 step inside the 128 B swizzle row: start-address field += 2
                         if constexpr (kCtas == 2)
-                            ptx::mma_f16_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            ptx::mma_f16_ss_pair(tmem_d, da + kstep * k, db + kstep * k, id, (kb | k) != 0);
                         else
-                            ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            ptx::mma_f16_ss(tmem_d, da + kstep * k, db + kstep * k, id, (kb | k) != 0);
                     }
                     // frees the smem stage (in both CTAs) when the MMAs retire
                     if constexpr (kCtas == 2)
@@ -648,7 +671,39 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
     return gemm_launch_tmaps(ta, tw, td, tr, bn, ctas, bias, residual != nullptr, M, N, K, dtype, act, stream);
 }
 
+// D[Mo, No] = A[Kt, Mo]^T @ B[Kt, No]: the weight-gradient contraction dW = dY^T X of a linear layer, with the
+// reduction (token) dimension as the ROWS of both operands, i.e. exactly as the activations and their gradients
+// sit in memory.  Same kernel, act bit 0x2000: MN-major shared-memory descriptors, 64 x 64 TMA boxes.
+int gemm_tn_launch(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, cudaStream_t stream)
+{
+    LL_REQUIRE(A && B && D, "gemm_tn: null pointer");
+    LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "gemm_tn: dtype must be LL_F16 or LL_BF16");
+    LL_REQUIRE(Kt > 0 && Mo > 0 && No > 0 && Mo % 128 == 0 && No % 64 == 0, "gemm_tn: need Mo %% 128 == 0 and No %% 64 == 0 (Kt=%lld Mo=%d No=%d)", (long long)Kt, Mo, No);
+    LL_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0, "gemm_tn: D must be 16-byte aligned");
+    int bn = 0, ctas = 1;
+    pick_tile(Mo, No, bn, ctas);
+    if (ctas == 2 && (bn == 192 || Mo % 256 != 0)) {  // a pair stages BN / 2 columns of B per CTA: whole 64-column atoms only
+        ctas = 1;
+        if (g_pair_mode == 1 && No % 256 == 0 && Mo % 256 == 0) ctas = 2, bn = 256;
+    }
+    CUtensorMap ta, tw, td;
+    int rc = make_tmap_2d(&ta, A, dtype, Kt, Mo, 64);
+    if (rc != LL_OK) return rc;
+    rc = make_tmap_2d(&tw, B, dtype, Kt, No, 64);
+    if (rc != LL_OK) return rc;
+    rc = make_tmap_2d(&td, D, dtype, Mo, No, 32);
+    if (rc != LL_OK) return rc;
+    const int64_t Kpad = (Kt + kBK - 1) / kBK * kBK;
+    LL_REQUIRE(Kpad < (1ll << 31), "gemm_tn: Kt too large");
+    return gemm_launch_tmaps(ta, tw, td, td, bn, ctas, nullptr, 0, Mo, No, (int)Kpad, dtype, 0x2000, stream);
+}
+
 }  // namespace ll
+
+extern "C" int ll_gemm_tn(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, ll_stream_t stream)
+{
+    return ll::gemm_tn_launch(A, B, D, Kt, Mo, No, dtype, ll::as_stream(stream));
+}
 
 extern "C" int ll_gemm_set_tile_n(int bn)
 {

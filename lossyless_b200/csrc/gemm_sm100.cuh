@@ -249,6 +249,23 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
     return d;
 }
 
+// MN-major operand tile in shared memory: the tile's non-reduction dimension (M of A / N of B) is the
+// contiguous one.  Built from TMA boxes of 64 (MN, contiguous = one 128 B swizzle row) x 64 (K rows), 8192 B
+// each, placed one after the other along MN.  Canonical layout (cute make_umma_desc<Major::MN>, SW128), in
+// 16-byte units: ((8, n), (8, k)) : ((1, LBO), (8, SBO)) -- K rows 128 B apart, 8-row K groups SBO = 1024 B
+// apart, 64-element MN atoms LBO = 8192 B apart.  One K = 16 instruction step = 16 rows = 2048 B (+128 in the
+// start-address field).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address
+    d |= (uint64_t)(8192u >> 4) << 16;             // leading byte offset: next 64-element MN atom
+    d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset: next 8-row K group
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
 // cute::UMMA::InstrDescriptor for kind::f16: fp32 accumulate, A K-major; B K-major or MN-major.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int is_bf16, int b_mn_major = 0)
 {

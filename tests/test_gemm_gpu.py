@@ -180,3 +180,28 @@ def test_gemm_fused_layernorm(cuda_device, dtype, M, Nn, act):
     nat.call("ll_gemm_ln", nat.ptr(A), nat.ptr(Wf), nat.ptr(bf), None, nat.ptr(D2), M, Nn, K, nat.dtype_code(A), act,
              nat.ptr(parts), 3, nat.ptr(st2), K, nat.stream())
     assert torch.equal(D, D2) and torch.equal(st_out, st2)
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("Kt,Mo,No", [(2500, 768, 3072), (12800, 768, 768), (137, 2304, 768), (64, 256, 512), (9, 768, 512)])
+def test_gemm_tn_weight_gradient_shape(cuda_device, dtype, Kt, Mo, No, pair):
+    """D = A^T B with the reduction dimension as the rows of both operands (MN-major descriptors, TMA zero fill
+    past the last row): the weight-gradient contraction, against torch in fp32."""
+    from lossyless_b200 import _native as N
+
+    g = torch.Generator(device=cuda_device).manual_seed(Kt + Mo)
+    A = torch.randn(Kt, Mo, generator=g, device=cuda_device).to(dtype)
+    B = torch.randn(Kt, No, generator=g, device=cuda_device).to(dtype)
+    D = torch.full((Mo, No), float("nan"), dtype=dtype, device=cuda_device)
+    N.call("ll_gemm_set_cta_pair", pair if pair else -1)
+    try:
+        N.call("ll_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(D), Kt, Mo, No, N.dtype_code(A), N.stream())
+    finally:
+        N.call("ll_gemm_set_cta_pair", -1)
+    ref = A.float().t() @ B.float()
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-3
+    assert torch.isfinite(D.float()).all()
+    assert (D.float() - ref).abs().max().item() < tol * ref.abs().max().item()
+    with pytest.raises(N.NativeError):
+        N.call("ll_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(D), Kt, Mo + 8, No, N.dtype_code(A), N.stream())

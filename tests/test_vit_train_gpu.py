@@ -146,6 +146,24 @@ def test_encoder_gradients_match_oracle_autograd(cuda_device, dtype):
     assert not bad, bad
 
 
+def test_weight_gradient_paths_agree(cuda_device, monkeypatch):
+    """ll_gemm_tn (MN-major operands, default) and the transposed-copy path give the same weight gradients up to
+    the 16-bit rounding of the result."""
+    from lossyless_b200 import clip_vit
+
+    grads = {}
+    for impl in ("tn", "transpose"):
+        monkeypatch.setattr(clip_vit, "WGRAD_IMPL", impl)
+        vit, sd, cfg = _trainable_vit(cuda_device, 2, torch.bfloat16)
+        gen = torch.Generator().manual_seed(5)
+        x = torch.randn(3, 3, 224, 224, generator=gen).to(cuda_device)
+        r = torch.randn(3, 512, generator=gen).to(cuda_device)
+        (vit(x) * r).sum().backward()
+        grads[impl] = {n: p.grad.clone() for n, p in vit.named_parameters()}
+    for n in grads["tn"]:
+        assert _rel(grads["tn"][n], grads["transpose"][n]) < 1e-2, n
+
+
 def test_full_depth_gradient_direction(cuda_device):
     """ViT-B/32 (12 blocks), 2 images, bf16 compute: the flattened gradient points where autograd's does."""
     vit, sd, cfg = _trainable_vit(cuda_device, 12, torch.bfloat16)

@@ -29,7 +29,12 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--only", default="", choices=["", "frozen", "unfrozen"])
     ap.add_argument("--batches", default="64,256", help="per-GPU batch sizes")
+    ap.add_argument("--wgrad", default="", choices=["", "tn", "transpose"], help="A/B: weight-gradient GEMM path (clip_vit.WGRAD_IMPL)")
     args = ap.parse_args()
+    if args.wgrad:
+        from lossyless_b200 import clip_vit
+
+        clip_vit.WGRAD_IMPL = args.wgrad
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
