@@ -44,16 +44,42 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and clock-event (throttle) reasons of one GPU sampled while the timed region runs: NVML queried
+    every 10 ms from a thread (the timed region of the default run is ~150 ms, and with eight ranks an
+    `nvidia-smi -lms` child per rank does not even deliver its first line in that time); falls back to the
+    nvidia-smi loop of the profiling recipe if NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop = index, [], None, None, False
+        self.samples, self.max_mhz, self.reason_bits = [], None, 0
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES may renumber the devices: look the GPU up by UUID
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)  # raises here if the query is unsupported
+        return pynvml, h
 
     def __enter__(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -63,17 +89,35 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def _poll(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.reason_bits |= int(reasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *a):
-        if self.proc is not None:
+        if self.nvml is not None:
+            self.stop = True
+            self.thread.join(timeout=2)
+        elif self.proc is not None:
             time.sleep(0.25)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
+        if self.nvml is not None and self.samples:
+            return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, b in self.BITS.items() if self.reason_bits & b), "samples": len(self.samples),
+                    "source": "nvml, 10 ms"}
         sm, mx, reasons = [], [], set()
         for r in self.rows:
             try:
@@ -86,7 +130,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 200"}
 
 
 # ----------------------------------------------------------------------------- CPU legs
