@@ -21,7 +21,6 @@ parameters.  Two execution paths, no CPU path:
   gradients only.
 """
 import ctypes
-import math
 
 import torch
 import torch.nn as nn

@@ -16,7 +16,6 @@ What runs where:
   * ``loss`` (aux loss over the 3 quantiles per channel, 1536 elements) stays plain torch.
 There is no CPU path for forward / compress / decompress: tensors must be on a B200.
 """
-import math
 
 import numpy as np
 import torch

@@ -3,7 +3,6 @@ scope): ``BASE_LOG`` (:27), ``Timer`` (:45-56), ``atleast_ndim`` (:330), ``Delta
 ``Annealer`` (:768-870), ``GatherFromGpus`` (:873-893), ``weights_init`` (:153), optimiser /
 scheduler factories (:492-593) and a minimal attribute-dict for hparams
 (utils/helpers.py ``NamespaceMap``)."""
-import math
 import time
 from functools import reduce
 from numbers import Number

@@ -50,7 +50,7 @@ def test_contrastive_golden_w1(cuda_device, golden_dir):
 def test_contrastive_forward_backward_vs_oracle(cuda_device, B, world):
     """loss and gradients wrt z_hat, z_pos_hat, projector weights and logit_scale; world=2 emulates
     the gathered remote tile (constant columns to the right of the own tile)."""
-    from lossyless_b200.distortions import _InfoNCE, _LogitsTile
+    from lossyless_b200.distortions import _LogitsTile
 
     gen = torch.Generator().manual_seed(B + world)
     proj = dict(w1=torch.randn(128, 512, generator=gen) * 0.05, b1=torch.randn(128, generator=gen) * 0.01,

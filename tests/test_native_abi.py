@@ -60,7 +60,7 @@ def test_pmf_to_quantized_cdf_matches_oracle(native_lib):
 @pytest.mark.parametrize("tag", TAGS)
 def test_entropy_bottleneck_update_matches_golden(native_lib, weights_dir, golden_dir, tag):
     """Product host path (torch CPU pmf + ll_build_cdf_tables) == oracle golden tables."""
-    from lossyless_b200.entropy_models import EntropyBottleneck, update_registered_buffers
+    from lossyless_b200.entropy_models import EntropyBottleneck
 
     sd = torch.load(os.path.join(weights_dir, f"{tag}_factorized_rate.pt"), map_location="cpu", weights_only=True)
     sd = {k[len("entropy_bottleneck."):]: v for k, v in sd.items() if k.startswith("entropy_bottleneck.")}

@@ -14,7 +14,6 @@ import sys
 import time
 import warnings
 
-import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
