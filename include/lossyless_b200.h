@@ -300,8 +300,9 @@ int ll_layernorm_backward(const void *x, const void *g_h, const float *gamma, co
  * The probabilities are recomputed from qkv.  S <= 64. */
 int ll_attention_backward(const void *qkv, const void *g_out, void *g_qkv, int64_t batch, int S, int H,
                           int dtype, ll_stream_t stream);
-/* 0 (default) = mma.sync tensor-core kernel (P and dS rounded to `dtype` between the products, as
- * flash-attention backward does), 1 = fp32 CUDA-core kernel. */
+/* 0 (default) = mma.sync tensor-core kernel fed by ldmatrix / ldmatrix.trans from one orientation of each
+ * operand (P and dS rounded to `dtype` between the products, as flash-attention backward does), 1 = fp32
+ * CUDA-core kernel, 2 = the first tensor-core version (operands copied in both orientations). */
 int ll_attention_backward_set_impl(int impl);
 
 /* ------------------------------------------------------ device: CLIP preprocessing */

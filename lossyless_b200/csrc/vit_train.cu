@@ -541,7 +541,189 @@ attention_backward_mma_kernel(const T *__restrict__ qkv, const T *__restrict__ g
     store(2);
 }
 
-static int g_attention_bwd_impl = 0;  // 0 = mma.sync kernel, 1 = fp32 CUDA-core kernel
+// ldmatrix variant (default).  Same five products, but the operands stay in shared memory in ONE orientation
+// (q, k, v, dO as [token][d]; P and dS as [query][key], 16-bit) and every fragment is fetched with ldmatrix.x4,
+// transposed by the instruction where the product needs the other orientation:
+//   S  = Q K^T      A: sQ            B: sK  ([n][k] as stored)
+//   dP = dO V^T     A: sG            B: sV  ([n][k] as stored)
+//   dQ = dS K       A: sS            B: sK  .trans  ([k][n] as stored)
+//   dK = dS^T Q     A: sS .trans     B: sQ  .trans
+//   dV = P^T dO     A: sP .trans     B: sG  .trans
+// No transposed copies: 55 KB of shared memory instead of 101 KB (4 CTAs per SM instead of 2) and none of the
+// bank-conflicting 16-bit scatter stores the first tensor-core version needed to build them.  Rows are 144 B apart
+// (72 elements): 16-byte aligned for ldmatrix and the eight row addresses of one 8 x 8 matrix fall in distinct
+// 16-byte bank groups.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+constexpr size_t kAlSmem = 6 * 64 * kAmP * 2;
+
+// acc[nt] (nt = 0..7: 16 x 8 output tiles) += A(m0.., :) * B for one warp, K = 64.
+//   kTransA = false: A[m][k] = As[m][k]        kTransA = true: A[m][k] = As[k][m]
+//   kTransB = false: B[k][n] = Bs[n][k]        kTransB = true: B[k][n] = Bs[k][n]
+template <typename T, bool kTransA, bool kTransB>
+__device__ __forceinline__ void warp_mma_ldsm(float (&acc)[8][4], uint32_t As, uint32_t Bs, int m0, int lane)
+{
+    const int l7 = lane & 7, mi = lane >> 3;  // matrix index 0..3 of the x4 load this lane addresses
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const int k0 = 16 * kk;
+        uint32_t a[4];
+        if (!kTransA) {
+            // matrices: (m 0-7, k 0-7), (m 8-15, k 0-7), (m 0-7, k 8-15), (m 8-15, k 8-15)
+            ldsm_x4(a, As + (uint32_t)(((m0 + l7 + (mi & 1) * 8) * kAmP + k0 + (mi >> 1) * 8) * 2));
+        } else {
+            // source rows are k: (k 0-7, m 0-7), (k 0-7, m 8-15), (k 8-15, m 0-7), (k 8-15, m 8-15), each transposed
+            ldsm_x4_t(a, As + (uint32_t)(((k0 + l7 + (mi >> 1) * 8) * kAmP + m0 + (mi & 1) * 8) * 2));
+        }
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {  // two 8-column output tiles per x4 load
+            const int n0 = 16 * np;
+            uint32_t b[4];
+            if (!kTransB) {
+                // source rows are n: (n 0-7, k 0-7), (n 0-7, k 8-15), (n 8-15, k 0-7), (n 8-15, k 8-15)
+                ldsm_x4(b, Bs + (uint32_t)(((n0 + l7 + (mi >> 1) * 8) * kAmP + k0 + (mi & 1) * 8) * 2));
+            } else {
+                // source rows are k: (k 0-7, n 0-7), (k 8-15, n 0-7), (k 0-7, n 8-15), (k 8-15, n 8-15), each transposed
+                ldsm_x4_t(b, Bs + (uint32_t)(((k0 + l7 + (mi & 1) * 8) * kAmP + n0 + (mi >> 1) * 8) * 2));
+            }
+            TrainMma<T>::mma(acc[2 * np], a, b[0], b[1]);
+            TrainMma<T>::mma(acc[2 * np + 1], a, b[2], b[3]);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128, 4)
+attention_backward_ldsm_kernel(const T *__restrict__ qkv, const T *__restrict__ g_out, T *__restrict__ g_qkv, int S, int H)
+{
+    extern __shared__ __align__(16) uint8_t ab_smem[];
+    T *sQ = reinterpret_cast<T *>(ab_smem);
+    T *sK = sQ + 64 * kAmP, *sV = sK + 64 * kAmP, *sG = sV + 64 * kAmP, *sP = sG + 64 * kAmP, *sS = sP + 64 * kAmP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int img = blockIdx.x / H, head = blockIdx.x % H;
+    const int64_t row0 = (int64_t)img * S;
+    const int ld = 3 * H * kAbD, ldo = H * kAbD;
+    const float scale = 0.125f;
+
+    // stage q, k, v, dO with 16-byte accesses (8 chunks of 8 elements per row); token rows >= S are zero
+    for (int i = tid; i < 64 * 8; i += 128) {
+        const int r = i >> 3, c = i & 7;
+        uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q, o = q;
+        if (r < S) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(qkv + (row0 + r) * ld + head * kAbD);
+            q = src[c];
+            k = src[c + (H * kAbD) / 8];
+            v = src[c + (2 * H * kAbD) / 8];
+            o = reinterpret_cast<const uint4 *>(g_out + (row0 + r) * ldo + head * kAbD)[c];
+        }
+        *reinterpret_cast<uint4 *>(sQ + r * kAmP + 8 * c) = q;
+        *reinterpret_cast<uint4 *>(sK + r * kAmP + 8 * c) = k;
+        *reinterpret_cast<uint4 *>(sV + r * kAmP + 8 * c) = v;
+        *reinterpret_cast<uint4 *>(sG + r * kAmP + 8 * c) = o;
+    }
+    __syncthreads();
+
+    const uint32_t aQ = (uint32_t)__cvta_generic_to_shared(sQ), aK = (uint32_t)__cvta_generic_to_shared(sK);
+    const uint32_t aV = (uint32_t)__cvta_generic_to_shared(sV), aG = (uint32_t)__cvta_generic_to_shared(sG);
+    const uint32_t aP = (uint32_t)__cvta_generic_to_shared(sP), aS = (uint32_t)__cvta_generic_to_shared(sS);
+    const int m0 = 16 * warp;
+    {
+        float sc[8][4], dp[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sc[nt][e] = 0.f, dp[nt][e] = 0.f;
+        warp_mma_ldsm<T, false, false>(sc, aQ, aK, m0, lane);
+        warp_mma_ldsm<T, false, false>(dp, aG, aV, m0, lane);
+        // element e of tile nt: row m0 + g + 8 * (e >> 1), column 8 nt + 2 t + (e & 1)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * nt + 2 * t + e;
+                    float &x = sc[nt][2 * h + e];
+                    x = col < S ? x * scale : -INFINITY;
+                    mx = fmaxf(mx, x);
+                }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float &x = sc[nt][2 * h + e];
+                    x = __expf(x - mx);  // exp(-inf) = 0 for the padded columns
+                    sum += x;
+                }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const float inv = 1.f / sum;
+            float delta = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    sc[nt][2 * h + e] *= inv;
+                    delta += sc[nt][2 * h + e] * dp[nt][2 * h + e];
+                }
+            delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+            delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+            const int row = m0 + g + 8 * h;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int col = 8 * nt + 2 * t;
+                const float p0 = sc[nt][2 * h], p1 = sc[nt][2 * h + 1];
+                *reinterpret_cast<uint32_t *>(sP + row * kAmP + col) = pack2<T>(p0, p1);
+                *reinterpret_cast<uint32_t *>(sS + row * kAmP + col) =
+                    pack2<T>(p0 * (dp[nt][2 * h] - delta) * scale, p1 * (dp[nt][2 * h + 1] - delta) * scale);
+            }
+        }
+    }
+    __syncthreads();
+
+    float acc[8][4];
+    auto store = [&](int which) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = m0 + g + 8 * h;
+            if (row < S) {
+                T *dst = g_qkv + (row0 + row) * ld + which * H * kAbD + head * kAbD;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+                    *reinterpret_cast<uint32_t *>(dst + 8 * nt + 2 * t) = pack2<T>(acc[nt][2 * h], acc[nt][2 * h + 1]);
+            }
+        }
+    };
+    auto clear = [&]() {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+    };
+    clear();
+    warp_mma_ldsm<T, false, true>(acc, aS, aK, m0, lane);  // dQ rows m0..: sum_j dS[i][j] K[j][d]
+    store(0);
+    clear();
+    warp_mma_ldsm<T, true, true>(acc, aS, aQ, m0, lane);   // dK rows m0..: sum_i dS[i][j] Q[i][d]
+    store(1);
+    clear();
+    warp_mma_ldsm<T, true, true>(acc, aP, aG, m0, lane);   // dV rows m0..: sum_i P[i][j] dO[i][d]
+    store(2);
+}
+
+static int g_attention_bwd_impl = 0;  // 0 = ldmatrix kernel, 1 = fp32 CUDA-core kernel, 2 = first mma.sync kernel (transposed copies)
 
 }  // namespace ll
 
@@ -663,6 +845,19 @@ extern "C" int ll_attention_backward(const void *qkv, const void *g_out, void *g
     const unsigned grid = (unsigned)(batch * H);
     cudaStream_t s = as_stream(stream);
     if (g_attention_bwd_impl == 0) {
+        static bool attr3_set = false;
+        if (!attr3_set) {
+            LL_CUDA_CHECK(cudaFuncSetAttribute(attention_backward_ldsm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAlSmem));
+            LL_CUDA_CHECK(cudaFuncSetAttribute(attention_backward_ldsm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAlSmem));
+            attr3_set = true;
+        }
+        LL_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(g_out)) & 15) == 0, "attention_backward: qkv / g_out must be 16-byte aligned");
+        LL_DISPATCH_16(dtype, (attention_backward_ldsm_kernel<__half><<<grid, 128, kAlSmem, s>>>(static_cast<const __half *>(qkv), static_cast<const __half *>(g_out), static_cast<__half *>(g_qkv), S, H)),
+                       (attention_backward_ldsm_kernel<__nv_bfloat16><<<grid, 128, kAlSmem, s>>>(static_cast<const __nv_bfloat16 *>(qkv), static_cast<const __nv_bfloat16 *>(g_out), static_cast<__nv_bfloat16 *>(g_qkv), S, H)), "attention_backward");
+        LL_LAUNCH_CHECK();
+        return LL_OK;
+    }
+    if (g_attention_bwd_impl == 2) {
         static bool attr2_set = false;
         if (!attr2_set) {
             LL_CUDA_CHECK(cudaFuncSetAttribute(attention_backward_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAmSmem));
@@ -682,7 +877,7 @@ extern "C" int ll_attention_backward(const void *qkv, const void *g_out, void *g
 
 extern "C" int ll_attention_backward_set_impl(int impl)
 {
-    LL_REQUIRE(impl == 0 || impl == 1, "attention_backward_set_impl: 0 = mma.sync kernel, 1 = fp32 CUDA-core kernel");
+    LL_REQUIRE(impl >= 0 && impl <= 2, "attention_backward_set_impl: 0 = ldmatrix mma.sync kernel, 1 = fp32 CUDA-core kernel, 2 = first mma.sync kernel");
     g_attention_bwd_impl = impl;
     return LL_OK;
 }

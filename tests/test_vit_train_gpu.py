@@ -85,11 +85,12 @@ def test_layernorm_backward(cuda_device, dtype, with_res):
     assert _rel(gw, wr.grad) < 1e-4 and _rel(gb, br.grad) < 1e-4  # fp32 accumulation of the 16-bit inputs
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2])
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("S,B,H", [(50, 5, 12), (64, 2, 3), (17, 3, 2)])
 def test_attention_backward(cuda_device, dtype, S, B, H, impl):
-    """impl 0 = mma.sync kernel (P / dS rounded to the 16-bit type between the products), 1 = fp32 kernel"""
+    """impl 0 = ldmatrix-fed mma.sync kernel (P / dS rounded to the 16-bit type between the products), 1 = fp32
+    kernel, 2 = the first mma.sync kernel (operands staged in both orientations)"""
     from lossyless_b200 import _native as N
 
     d = 64
