@@ -80,6 +80,14 @@ transpose_pad_scalar_kernel(const uint16_t *__restrict__ src, uint16_t *__restri
 }
 
 // ------------------------------------------------------------------------- column sums
+// out[c] += sum_r src[r, c].  A CTA covers 256 columns x 64 rows: thread = (32 column groups of 8) x (8 row
+// lanes), one 16-byte load per thread and row, two rows in flight; the 8 row lanes are combined through shared
+// memory and each CTA adds its 256 partial sums with one atomic per column.  (The first version read 2 bytes
+// per thread: 1.2 TB/s.)  Needs C % 8 == 0 and a 16-byte aligned base; other shapes take the scalar kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T *__restrict__ src, int64_t R, int C, int rows_per_cta, float *__restrict__ out);
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T *__restrict__ src, int64_t R, int C, int64_t rows_per_cta, float *__restrict__ out)
@@ -116,6 +124,44 @@ __device__ __forceinline__ void store8(T *p, const float *v)
     *reinterpret_cast<uint4 *>(p) = raw;
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T *__restrict__ src, int64_t R, int C, int rows_per_cta, float *__restrict__ out)
+{
+    __shared__ float part[8][256 + 8];
+    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 256 + cg * 8;
+    const int64_t r_begin = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r_end = min(R, r_begin + rows_per_cta);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c0 < C) {
+        int64_t r = r_begin + rl;
+        for (; r + 8 < r_end; r += 16) {  // two independent loads in flight
+            float a[8], b[8];
+            load8<T>(src + r * C + c0, a);
+            load8<T>(src + (r + 8) * C + c0, b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += a[k] + b[k];
+        }
+        for (; r < r_end; r += 8) {
+            float a[8];
+            load8<T>(src + r * C + c0, a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += a[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part[rl][cg * 8 + k] = acc[k];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < C) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += part[j][threadIdx.x];
+        atomicAdd(out + c, sum);
+    }
+}
+
 // ------------------------------------------------------------------------- QuickGELU
 // 8 elements (16 bytes) per thread per step; the tail (n % 8) is handled by the last thread scalar-wise.
 template <typename T>
@@ -124,7 +170,17 @@ quickgelu_forward_kernel(const T *__restrict__ u, T *__restrict__ f, int64_t n)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n8 = n / 8;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n8; i += 2 * stride) {  // two independent 16-byte loads in flight per thread
+        float x[8], y[8];
+        load8<T>(u + 8 * i, x);
+        load8<T>(u + 8 * (i + stride), y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = x[k] / (1.f + __expf(-1.702f * x[k])), y[k] = y[k] / (1.f + __expf(-1.702f * y[k]));
+        store8<T>(f + 8 * i, x);
+        store8<T>(f + 8 * (i + stride), y);
+    }
+    for (; i < n8; i += stride) {
         float x[8];
         load8<T>(u + 8 * i, x);
 #pragma unroll
@@ -145,15 +201,28 @@ quickgelu_backward_kernel(const T *__restrict__ u, const T *__restrict__ g_f, T 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n8 = n / 8;
     // d/dx [x s(1.702 x)] = s + 1.702 x s (1 - s)
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    auto dgelu = [](float x, float g) {
+        const float sg = 1.f / (1.f + __expf(-1.702f * x));
+        return g * (sg + 1.702f * x * sg * (1.f - sg));
+    };
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n8; i += 2 * stride) {  // four independent 16-byte loads in flight per thread
+        float x[8], g[8], y[8], h[8];
+        load8<T>(u + 8 * i, x);
+        load8<T>(g_f + 8 * i, g);
+        load8<T>(u + 8 * (i + stride), y);
+        load8<T>(g_f + 8 * (i + stride), h);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g[k] = dgelu(x[k], g[k]), h[k] = dgelu(y[k], h[k]);
+        store8<T>(g_u + 8 * i, g);
+        store8<T>(g_u + 8 * (i + stride), h);
+    }
+    for (; i < n8; i += stride) {
         float x[8], g[8];
         load8<T>(u + 8 * i, x);
         load8<T>(g_f + 8 * i, g);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float sg = 1.f / (1.f + __expf(-1.702f * x[k]));
-            g[k] *= sg + 1.702f * x[k] * sg * (1.f - sg);
-        }
+        for (int k = 0; k < 8; ++k) g[k] = dgelu(x[k], g[k]);
         store8<T>(g_u + 8 * i, g);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -769,9 +838,17 @@ extern "C" int ll_transpose_pad(const void *src, void *dst, int64_t R, int C, in
 extern "C" int ll_colsum(const void *src, int64_t R, int C, int dtype, float *out, ll_stream_t stream)
 {
     LL_REQUIRE(src && out && R > 0 && C > 0, "colsum: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    if (C % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int rows_per_cta = 64;
+        dim3 grid((unsigned)((C + 255) / 256), (unsigned)((R + rows_per_cta - 1) / rows_per_cta));
+        LL_DISPATCH_16(dtype, (colsum_vec_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half *>(src), R, C, rows_per_cta, out)),
+                       (colsum_vec_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(src), R, C, rows_per_cta, out)), "colsum");
+        LL_LAUNCH_CHECK();
+        return LL_OK;
+    }
     const int64_t rows_per_cta = 256;
     dim3 grid((unsigned)((C + 63) / 64), (unsigned)((R + rows_per_cta - 1) / rows_per_cta));
-    cudaStream_t s = as_stream(stream);
     LL_DISPATCH_16(dtype, (colsum_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half *>(src), R, C, rows_per_cta, out)),
                    (colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(src), R, C, rows_per_cta, out)), "colsum");
     LL_LAUNCH_CHECK();
