@@ -296,7 +296,10 @@ class ClipCompressor(nn.Module):
         pipe = getattr(self, "_pipe", None)
         if pipe is None or pipe["key"] != key or pipe["cap"] < need:
             if pipe is not None:
-                pipe["stream"].synchronize()  # nothing may still be copying into the slots we drop
+                # nothing may still be copying into, or (the previous batch's encoder) reading from, the slots we
+                # drop: their memory can come straight back as the new slots, which the copy stream fills at once
+                pipe["stream"].synchronize()
+                torch.cuda.current_stream(dev).synchronize()
             pipe = dict(key=key, cap=need, stream=torch.cuda.Stream(dev),
                         buf=[torch.empty((need,) + tuple(X_host.shape[1:]), dtype=X_host.dtype, device=dev) for _ in range(2)],
                         ready=[torch.cuda.Event(), torch.cuda.Event()], consumed=[None, None], next=0)
