@@ -92,3 +92,7 @@ def test_compress_stream_matches_blocking_calls(compressor):
     want = [bytes(comp.compress_batch_to_host(b)[0].numpy().data) for b in raw]
     assert [bytes(rec.numpy().data) for rec, _ in comp.compress_stream(iter(raw))] == want
     assert list(comp.compress_stream(iter([]))) == []
+    # default sub_batch (one H2D copy and one encoder pass per batch): the staging slots grow with the batch size
+    # (5 -> 400) and are re-created while the previous batch may still be in flight
+    got = [bytes(rec.numpy().data) for rec, _ in comp.compress_stream(iter(batches[:4]))]
+    assert got == [bytes(comp.compress_batch_to_host(b)[0].numpy().data) for b in batches[:4]]
