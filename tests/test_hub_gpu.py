@@ -92,6 +92,12 @@ def test_compress_stream_matches_blocking_calls(compressor):
     want = [bytes(comp.compress_batch_to_host(b)[0].numpy().data) for b in raw]
     assert [bytes(rec.numpy().data) for rec, _ in comp.compress_stream(iter(raw))] == want
     assert list(comp.compress_stream(iter([]))) == []
+    # coalescing: consecutive small batches share one encoder pass; one yield per group, records in input order
+    small = [torch.randn(n, 3, 224, 224, generator=g).half().pin_memory() for n in (100, 100, 100, 60, 300, 7)]
+    per_batch = [bytes(comp.compress_batch_to_host(b)[0].numpy().data) for b in small]
+    got = [(bytes(rec.numpy().data), n) for rec, n in comp.compress_stream(iter(small), coalesce=256)]
+    assert [n for _, n in got] == [200, 160, 300, 7]  # 100+100 | 100+60 | 300 (>= limit: alone) | 7
+    assert b"".join(r for r, _ in got) == b"".join(per_batch)
     # default sub_batch (one H2D copy and one encoder pass per batch): the staging slots grow with the batch size
     # (5 -> 400) and are re-created while the previous batch may still be in flight
     got = [bytes(rec.numpy().data) for rec, _ in comp.compress_stream(iter(batches[:4]))]
