@@ -63,14 +63,19 @@ def compress_dataset_sharded(compressor, dataset, file, label_file=None, batch_s
     (n_images, file_bytes) on rank 0, (n_images_local, None) elsewhere."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     start, end = shard_range(len(dataset), rank, world)
-    blob, labels, pinned = bytearray(), [], None
-    for i0 in range(start, end, batch_size):
-        items = [dataset[i] for i in range(i0, min(end, i0 + batch_size))]
-        x = torch.stack([it[0] for it in items])
-        records, _, pinned = compressor.compress_batch_to_host(x, pinned)
+    blob, labels = bytearray(), []
+
+    def batches():
+        for i0 in range(start, end, batch_size):
+            items = [dataset[i] for i in range(i0, min(end, i0 + batch_size))]
+            if label_file is not None:
+                labels.extend(int(it[1]) for it in items)
+            yield torch.stack([it[0] for it in items]).pin_memory()
+
+    # the rank's slice goes through compress_dataset's own pipelined loop (H2D of the next pass under the kernels
+    # of the current one, small batches grouped into encoder passes of up to 1512 images)
+    for records, _ in compressor.compress_stream(batches(), coalesce=1512):
         blob += records.numpy().tobytes()
-        if label_file is not None:
-            labels += [int(it[1]) for it in items]
     blobs, counts = gather_record_blobs(bytes(blob), end - start, group)
     if label_file is not None:
         lab = [None] * world if rank == 0 else None
