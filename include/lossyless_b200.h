@@ -349,6 +349,15 @@ int ll_contrastive_ce_backward(const float *logits, int n, int n_cols, int ld, f
                                float *g_logits_local, int ld_g, float *g_inv_temp,
                                ll_stream_t stream);
 
+/* The same two entry points with 1/temperature read from DEVICE memory (one float): the temperature is a trained
+ * parameter (lossyless/distortions.py:228-236), and passing it by value forces the host to wait for the GPU in
+ * the middle of every training step. */
+int ll_contrastive_ce_forward_dev(const float *logits, int n, int n_cols, int ld, float pos_add,
+                                  const float *inv_temp_dev, float *loss, float *lse, ll_stream_t stream);
+int ll_contrastive_ce_backward_dev(const float *logits, int n, int n_cols, int ld, float pos_add,
+                                   const float *inv_temp_dev, const float *lse, const float *g_loss,
+                                   float *g_logits_local, int ld_g, float *g_inv_temp, ll_stream_t stream);
+
 /* replaces LossyZDistortion.forward (lossyless/distortions.py:445):
  * dist[r] = sum_c |z_hat - z + 1e-6|;  optional backward sign tensor. */
 int ll_lossy_z_forward(const float *z_hat, const float *z, int64_t rows, int C, float eps,

@@ -111,7 +111,8 @@ __device__ __forceinline__ void lse_push(float &m, float &s, float v)
 }
 
 __global__ void __launch_bounds__(256)
-infonce_forward_kernel(const float *__restrict__ logits, int n, int n_cols, int ld, float pos_add, float inv_temp,
+infonce_forward_kernel(const float *__restrict__ logits, int n, int n_cols, int ld, float pos_add, float inv_temp_host,
+                       const float *__restrict__ inv_temp_dev,
                        float *__restrict__ loss, float *__restrict__ lse_out)
 {
     const int lane = threadIdx.x & 31;
@@ -119,6 +120,7 @@ infonce_forward_kernel(const float *__restrict__ logits, int n, int n_cols, int 
     if (i >= n) return;
     const int pos = (i + n / 2) % n;
     const float *row = logits + (int64_t)i * ld;
+    const float inv_temp = inv_temp_dev != nullptr ? __ldg(inv_temp_dev) : inv_temp_host;
     float m = -FLT_MAX, s = 0.f;
     for (int j = lane; j < n_cols; j += 32) {
         if (j == i) continue;
@@ -141,7 +143,8 @@ infonce_forward_kernel(const float *__restrict__ logits, int n, int n_cols, int 
 }
 
 __global__ void __launch_bounds__(256)
-infonce_backward_kernel(const float *__restrict__ logits, int n, int n_cols, int ld, float pos_add, float inv_temp,
+infonce_backward_kernel(const float *__restrict__ logits, int n, int n_cols, int ld, float pos_add, float inv_temp_host,
+                        const float *__restrict__ inv_temp_dev,
                         const float *__restrict__ lse, const float *__restrict__ g_loss,
                         float *__restrict__ g_local, int ld_g, float *__restrict__ g_inv_temp)
 {
@@ -151,6 +154,7 @@ infonce_backward_kernel(const float *__restrict__ logits, int n, int n_cols, int
     const int pos = (i + n / 2) % n;
     const float *row = logits + (int64_t)i * ld;
     const float gl = g_loss[i], l = lse[i];
+    const float inv_temp = inv_temp_dev != nullptr ? __ldg(inv_temp_dev) : inv_temp_host;
     float gt = 0.f;  // d loss_i / d inv_temp = sum_j (p_j - [j == pos]) * (logit_j + add_j)
     for (int j = lane; j < n_cols; j += 32) {
         float gij = 0.f;
@@ -222,7 +226,16 @@ extern "C" int ll_contrastive_ce_forward(const float *logits, int n, int n_cols,
                                          float *loss, float *lse, ll_stream_t stream)
 {
     LL_REQUIRE(logits && loss && lse && n > 1 && (n % 2) == 0 && n_cols >= n && ld >= n_cols, "contrastive_ce_forward: bad arguments");
-    infonce_forward_kernel<<<(n * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(logits, n, n_cols, ld, pos_add, inv_temp, loss, lse);
+    infonce_forward_kernel<<<(n * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(logits, n, n_cols, ld, pos_add, inv_temp, nullptr, loss, lse);
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+extern "C" int ll_contrastive_ce_forward_dev(const float *logits, int n, int n_cols, int ld, float pos_add,
+                                             const float *inv_temp_dev, float *loss, float *lse, ll_stream_t stream)
+{
+    LL_REQUIRE(logits && inv_temp_dev && loss && lse && n > 1 && (n % 2) == 0 && n_cols >= n && ld >= n_cols, "contrastive_ce_forward_dev: bad arguments");
+    infonce_forward_kernel<<<(n * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(logits, n, n_cols, ld, pos_add, 0.f, inv_temp_dev, loss, lse);
     LL_LAUNCH_CHECK();
     return LL_OK;
 }
@@ -232,7 +245,17 @@ extern "C" int ll_contrastive_ce_backward(const float *logits, int n, int n_cols
                                           float *g_inv_temp, ll_stream_t stream)
 {
     LL_REQUIRE(logits && lse && g_loss && g_logits_local && n > 1 && (n % 2) == 0 && n_cols >= n && ld >= n_cols && ld_g >= n, "contrastive_ce_backward: bad arguments");
-    infonce_backward_kernel<<<(n * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(logits, n, n_cols, ld, pos_add, inv_temp, lse, g_loss, g_logits_local, ld_g, g_inv_temp);
+    infonce_backward_kernel<<<(n * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(logits, n, n_cols, ld, pos_add, inv_temp, nullptr, lse, g_loss, g_logits_local, ld_g, g_inv_temp);
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+extern "C" int ll_contrastive_ce_backward_dev(const float *logits, int n, int n_cols, int ld, float pos_add,
+                                              const float *inv_temp_dev, const float *lse, const float *g_loss,
+                                              float *g_logits_local, int ld_g, float *g_inv_temp, ll_stream_t stream)
+{
+    LL_REQUIRE(logits && inv_temp_dev && lse && g_loss && g_logits_local && n > 1 && (n % 2) == 0 && n_cols >= n && ld >= n_cols && ld_g >= n, "contrastive_ce_backward_dev: bad arguments");
+    infonce_backward_kernel<<<(n * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(logits, n, n_cols, ld, pos_add, 0.f, inv_temp_dev, lse, g_loss, g_logits_local, ld_g, g_inv_temp);
     LL_LAUNCH_CHECK();
     return LL_OK;
 }

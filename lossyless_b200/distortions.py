@@ -64,19 +64,21 @@ class _InfoNCE(torch.autograd.Function):
         n, n_cols = logits.shape
         loss = torch.empty(n, dtype=torch.float32, device=logits.device)
         lse = torch.empty(n, dtype=torch.float32, device=logits.device)
-        it = float(inv_temp.detach())
-        N.call("ll_contrastive_ce_forward", N.ptr(logits), n, n_cols, logits.stride(0), pos_add, it, N.ptr(loss), N.ptr(lse), N.stream())
-        ctx.save_for_backward(logits, lse)
-        ctx.it, ctx.pos_add = it, pos_add
+        # 1 / temperature stays on the device (a float() here would make the host wait for the whole encoder
+        # forward in the middle of every training step)
+        it = inv_temp.detach().float().reshape(1).contiguous()
+        N.call("ll_contrastive_ce_forward_dev", N.ptr(logits), n, n_cols, logits.stride(0), pos_add, N.ptr(it), N.ptr(loss), N.ptr(lse), N.stream())
+        ctx.save_for_backward(logits, lse, it)
+        ctx.pos_add = pos_add
         return loss
 
     @staticmethod
     def backward(ctx, g_loss):
-        logits, lse = ctx.saved_tensors
+        logits, lse, it = ctx.saved_tensors
         n, n_cols = logits.shape
         g = torch.zeros_like(logits)  # remote tiles get no gradient (lossyless/helpers.py:885-890)
         g_it = torch.zeros(1, dtype=torch.float32, device=logits.device)
-        N.call("ll_contrastive_ce_backward", N.ptr(logits), n, n_cols, logits.stride(0), ctx.pos_add, ctx.it, N.ptr(lse),
+        N.call("ll_contrastive_ce_backward_dev", N.ptr(logits), n, n_cols, logits.stride(0), ctx.pos_add, N.ptr(it), N.ptr(lse),
                N.ptr(g_loss.contiguous().float()), N.ptr(g), g.stride(0), N.ptr(g_it), N.stream())
         return g, g_it.reshape(()), None
 

@@ -9,6 +9,7 @@ entry of ``idcs_to_compressors`` ("main", then "coder"), gradient clipping, opti
 gradient all-reduce (buckets only -- the encode path itself has no collective).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -119,7 +120,9 @@ class LearnableCompressor(nn.Module):
         logs.update(dict(zmin=z_hat.min(), zmax=z_hat.max(), zmean=z_hat.mean()))
         other.update(r_other)
         other.update(d_other)
-        other["X"] = x[0].detach().cpu()
+        # the reference copies this sample to the host here (for its plotting callbacks); a .cpu() per step is a full
+        # host-device synchronisation, so the tensor stays on the device and consumers copy it if they want it
+        other["X"] = x[0].detach()
         other.update(dict(z=z.detach()))
         self._view_cache = None
         return loss, logs, other
@@ -156,7 +159,12 @@ class LearnableCompressor(nn.Module):
 
     # -- Lightning-style hooks -----------------------------------------------------------
     def log_dict(self, d, **kw):
-        self.logged.update({k: (float(v) if torch.is_tensor(v) else v) for k, v in d.items()})
+        if getattr(self, "_defer_log_sync", False):
+            # inside fit(): keep the 0-dim tensors; fit() turns them into floats once, at its end -- a float() per
+            # logged scalar per step makes the host wait for the GPU between the forward and the backward pass
+            self.logged.update({k: (v.detach() if torch.is_tensor(v) else v) for k, v in d.items()})
+        else:
+            self.logged.update({k: (float(v) if torch.is_tensor(v) else v) for k, v in d.items()})
 
     def training_step(self, batch, batch_idx, optimizer_idx=0):
         curr_step = self.idcs_to_compressors[optimizer_idx]
@@ -255,6 +263,18 @@ class LearnableCompressor(nn.Module):
         optimizers, schedulers = self.configure_optimizers()
         is_dist = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.train()
+        # no host synchronisation inside the loop (see log_dict); LL_SYNC_LOGS=1 restores a float() per logged scalar (A/B)
+        self._defer_log_sync = os.environ.get("LL_SYNC_LOGS", "0") != "1"
+        try:
+            self._fit_loop(batches, optimizers, max_steps, grad_clip, is_dist, process_group, grad_comm_dtype)
+        finally:
+            self._defer_log_sync = False
+            self.logged = {k: (float(v) if torch.is_tensor(v) else v) for k, v in self.logged.items()}
+        for s in schedulers:
+            s["scheduler"].step()
+        return self.logged
+
+    def _fit_loop(self, batches, optimizers, max_steps, grad_clip, is_dist, process_group, grad_comm_dtype):
         for batch_idx, batch in enumerate(batches):
             if max_steps is not None and self.global_step >= max_steps:
                 break
@@ -269,9 +289,6 @@ class LearnableCompressor(nn.Module):
                     torch.nn.utils.clip_grad_norm_(params, grad_clip)
                 opt.step()
             self.global_step += 1
-        for s in schedulers:
-            s["scheduler"].step()
-        return self.logged
 
 
 def _plain(d):
