@@ -39,6 +39,28 @@ except ImportError:  # pragma: no cover
         return it
 
 
+def group_host_batches(host_batches, limit):
+    """Groups consecutive host batches into lists whose image counts add up to at most ``limit`` (what one encoder
+    pass / staging slot takes), keeping the order.  A batch that is already on the device, that alone reaches the
+    limit, or whose dtype / image shape differs from the open group's closes that group; ``limit <= 0`` disables
+    grouping (every batch is its own group)."""
+    cur, n = [], 0
+    for X in host_batches:
+        if limit <= 0 or X.is_cuda or X.shape[0] >= limit:
+            if cur:
+                yield cur
+                cur, n = [], 0
+            yield [X]
+            continue
+        if cur and (n + X.shape[0] > limit or X.dtype != cur[0].dtype or X.shape[1:] != cur[0].shape[1:]):
+            yield cur
+            cur, n = [], 0
+        cur.append(X)
+        n += X.shape[0]
+    if cur:
+        yield cur
+
+
 class ClipCompressor(nn.Module):
     """Our CLIP compressor.
 
@@ -296,22 +318,7 @@ class ClipCompressor(nn.Module):
             self._size_next = 0
 
         def groups():
-            limit = min(int(coalesce), int(sub_batch))
-            cur, n = [], 0
-            for X in host_batches:
-                if limit <= 0 or X.is_cuda or X.shape[0] >= limit:
-                    if cur:
-                        yield cur
-                        cur, n = [], 0
-                    yield [X]
-                    continue
-                if cur and (n + X.shape[0] > limit or X.dtype != cur[0].dtype or X.shape[1:] != cur[0].shape[1:]):
-                    yield cur
-                    cur, n = [], 0
-                cur.append(X)
-                n += X.shape[0]
-            if cur:
-                yield cur
+            return group_host_batches(host_batches, min(int(coalesce), int(sub_batch)))
 
         def enqueue(group):
             X_host = group[0] if len(group) == 1 else group

@@ -159,3 +159,23 @@ def test_freezer_callback():
     holder.enc = vit
     Freezer("enc").freeze_before_training(holder)
     assert not vit._trainable and not any(p.requires_grad for p in vit.parameters())
+
+
+def test_group_host_batches():
+    """compress_dataset's grouping of DataLoader batches into encoder passes (hub/compressor.py): order kept,
+    no group above the limit, dtype / shape changes and oversized batches close a group, 0 disables it."""
+    from lossyless_b200.hub.compressor import group_host_batches
+
+    def mk(n, dtype=torch.float16, hw=8):
+        return torch.zeros(n, 3, hw, hw, dtype=dtype)
+
+    sizes = lambda groups: [[int(x.shape[0]) for x in g] for g in groups]
+    bs = [mk(100), mk(100), mk(100), mk(60), mk(300), mk(7)]
+    assert sizes(group_host_batches(iter(bs), 256)) == [[100, 100], [100, 60], [300], [7]]
+    assert sizes(group_host_batches(iter(bs), 0)) == [[100], [100], [100], [60], [300], [7]]
+    assert sizes(group_host_batches(iter(bs), 1512)) == [[100, 100, 100, 60, 300, 7]]
+    mixed = [mk(10), mk(10, torch.float32), mk(10, torch.float32), mk(10, torch.float32, hw=4), mk(10, torch.uint8)]
+    assert sizes(group_host_batches(iter(mixed), 100)) == [[10], [10, 10], [10], [10]]
+    flat = [x for g in group_host_batches(iter(bs), 256) for x in g]
+    assert all(a is b for a, b in zip(flat, bs))
+    assert list(group_host_batches(iter([]), 256)) == []
