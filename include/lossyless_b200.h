@@ -160,15 +160,20 @@ int ll_eb_forward(const void *z, int z_dtype, int64_t rows, int C, const float *
                   const float *packed, float likelihood_bound, float *z_hat, float *q,
                   float *rates, ll_stream_t stream);
 
-/* Backward of ll_eb_forward in training (noise) mode.  Given g_rates [rows] (dL/drates),
- * g_zhat [rows,C] or NULL (dL/dz_hat), writes gz float32 [rows,C] (dL/dz), and accumulates
- * gparam float32 [LL_EB_NPARAM, C] (gradient w.r.t. the *derived* parameters;
- * softplus'/tanh' chain is applied by the caller), g_bias [C], g_exp_scale [C].
- * replaces autograd through lossyless/rates.py:534-554. */
+/* Backward of ll_eb_forward.  Incoming gradients (each may be NULL, not all): g_rates [rows]
+ * (dL/drates), g_q [rows,C] (dL/dq, a gradient taken on the likelihood output itself, e.g.
+ * -log q(s) summed outside: HRateHyperprior, lossyless/rates.py:640-650), g_zhat [rows,C]
+ * (dL/dz_hat).  Writes gz float32 [rows,C] (dL/dz) and accumulates gparam float32
+ * [LL_EB_NPARAM, C] (gradient w.r.t. the *derived* parameters; the softplus'/tanh' chain is
+ * applied by the caller), g_bias [C], g_exp_scale [C].  noise == NULL is eval mode: v =
+ * round(x - median) + median has zero derivative w.r.t. x (torch.round), so gz is zero and only
+ * the parameters receive gradients; `medians` is required then.
+ * replaces autograd through lossyless/rates.py:534-554 / compressai EntropyBottleneck.forward. */
 int ll_eb_backward(const void *z, int z_dtype, int64_t rows, int C, const float *noise,
-                   const float *bias, const float *exp_scale, const float *packed,
-                   float likelihood_bound, const float *g_rates, const float *g_zhat, float *gz,
-                   float *gparam, float *g_bias, float *g_exp_scale, ll_stream_t stream);
+                   const float *bias, const float *exp_scale, const float *medians,
+                   const float *packed, float likelihood_bound, const float *g_rates,
+                   const float *g_q, const float *g_zhat, float *gz, float *gparam, float *g_bias,
+                   float *g_exp_scale, ll_stream_t stream);
 
 /* ------------------------------------------------------------ device: CLIP ViT-B/32 */
 

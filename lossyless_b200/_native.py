@@ -59,7 +59,7 @@ _SIGNATURES = {
     "ll_rans_decode": (c_int, [_P, _P, _P, c_int64, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ll_eb_pack_params": (c_int, [POINTER(_P), POINTER(_P), POINTER(_P), c_int, _P, _P]),
     "ll_eb_forward": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P]),
-    "ll_eb_backward": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "ll_eb_backward": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ll_vit_create": (c_int, [POINTER(VitConfig), POINTER(VitWeights), POINTER(_P)]),
     "ll_vit_destroy": (None, [_P]),
     "ll_vit_workspace_bytes": (c_int64, [_P, c_int64]),

@@ -194,7 +194,8 @@ template <typename T>
 __global__ void __launch_bounds__(kEbThreads)
 eb_backward_kernel(const T *__restrict__ z, int64_t rows, int C, int rows_per_cta, const float *__restrict__ noise,
                    const float *__restrict__ bias, const float *__restrict__ exp_scale,
-                   const float *__restrict__ packed, float bound, const float *__restrict__ g_rates,
+                   const float *__restrict__ medians, const float *__restrict__ packed, float bound,
+                   const float *__restrict__ g_rates, const float *__restrict__ g_q,
                    const float *__restrict__ g_zhat, float *__restrict__ gz, float *__restrict__ gparam,
                    float *__restrict__ g_bias, float *__restrict__ g_es)
 {
@@ -207,15 +208,17 @@ eb_backward_kernel(const T *__restrict__ z, int64_t rows, int C, int rows_per_ct
         G[i] = 0.f;
     }
     const float b = bias ? bias[c] : 0.f, es = exp_scale ? exp_scale[c] : 1.f;
+    const float med = noise ? 0.f : medians[c];
     float acc_b = 0.f, acc_es = 0.f;
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
     const int64_t r1 = min(rows, r0 + rows_per_cta);
     for (int64_t r = r0; r < r1; ++r) {
         const int64_t idx = r * C + c;
         const float zf = to_float<T>(z[idx]);
-        const float zb = zf + b;
-        const float x = bias ? zb * es : zf;
-        const float v = x + noise[idx];
+        const float zb = __fadd_rn(zf, b);
+        const float x = bias ? __fmul_rn(zb, es) : zf;  // the forward's own rounding (matters for round() in eval mode)
+        // training: v = x + noise (dv/dx = 1); eval: v = round(x - med) + med (dv/dx = 0, as torch.round)
+        const float v = noise ? x + noise[idx] : __fadd_rn(rintf(__fsub_rn(x, med)), med);
         Trace trl, tru;
         const float lower = logits_fwd(P, v - 0.5f, trl);
         const float upper = logits_fwd(P, v + 0.5f, tru);
@@ -226,19 +229,21 @@ eb_backward_kernel(const T *__restrict__ z, int64_t rows, int C, int rows_per_ct
         const float lik = fabsf(diff);
         const float q = fmaxf(lik, bound);
         // rate = -log q ;  LowerBound passes the gradient where lik >= bound or grad < 0
-        float g_lik = -g_rates[r] / q;
+        // (+ a gradient arriving directly on the likelihood output, e.g. -log q(s) taken outside the kernel)
+        float g_lik = (g_rates ? -g_rates[r] / q : 0.f) + (g_q ? g_q[idx] : 0.f);
         if (!(lik >= bound || g_lik < 0.f)) g_lik = 0.f;
         const float sd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
         const float gu = g_lik * sd * sgn * su * (1.f - su);
         const float gl = -g_lik * sd * sgn * sl * (1.f - sl);
         float gv = logits_bwd(P, v + 0.5f, tru, gu, G) + logits_bwd(P, v - 0.5f, trl, gl, G);
+        if (!noise) gv = 0.f;
         if (g_zhat) {
             const float gh = g_zhat[idx];
             if (bias) {
-                gv += gh / es;                // z_hat = v / es - b
+                if (noise) gv += gh / es;     // z_hat = v / es - b
                 acc_es -= gh * v / (es * es);
                 acc_b -= gh;
-            } else {
+            } else if (noise) {
                 gv += gh;
             }
         }
@@ -314,11 +319,13 @@ extern "C" int ll_eb_forward(const void *z, int z_dtype, int64_t rows, int C, co
 }
 
 extern "C" int ll_eb_backward(const void *z, int z_dtype, int64_t rows, int C, const float *noise, const float *bias,
-                              const float *exp_scale, const float *packed, float bound, const float *g_rates,
-                              const float *g_zhat, float *gz, float *gparam, float *g_bias, float *g_exp_scale,
-                              ll_stream_t stream)
+                              const float *exp_scale, const float *medians, const float *packed, float bound,
+                              const float *g_rates, const float *g_q, const float *g_zhat, float *gz, float *gparam,
+                              float *g_bias, float *g_exp_scale, ll_stream_t stream)
 {
-    LL_REQUIRE(z && noise && packed && g_rates && gz && gparam, "eb_backward: null pointer (noise is required: training mode only)");
+    LL_REQUIRE(z && packed && gz && gparam, "eb_backward: null pointer");
+    LL_REQUIRE(noise || medians, "eb_backward: eval mode (noise == NULL) needs the medians");
+    LL_REQUIRE(g_rates || g_q || g_zhat, "eb_backward: no incoming gradient");
     LL_REQUIRE((bias == nullptr) == (exp_scale == nullptr), "eb_backward: bias and exp_scale go together");
     LL_REQUIRE(!bias || (g_bias && g_exp_scale), "eb_backward: g_bias / g_exp_scale required with bias");
     LL_REQUIRE(rows >= 0 && C > 0, "eb_backward: bad sizes");
@@ -328,9 +335,9 @@ extern "C" int ll_eb_backward(const void *z, int z_dtype, int64_t rows, int C, c
     eb_grid(rows, C, grid, rpc);
     cudaStream_t s = as_stream(stream);
     switch (z_dtype) {
-        case LL_F32: eb_backward_kernel<float><<<grid, kEbThreads, 0, s>>>((const float *)z, rows, C, rpc, noise, bias, exp_scale, packed, bound, g_rates, g_zhat, gz, gparam, g_bias, g_exp_scale); break;
-        case LL_F16: eb_backward_kernel<__half><<<grid, kEbThreads, 0, s>>>((const __half *)z, rows, C, rpc, noise, bias, exp_scale, packed, bound, g_rates, g_zhat, gz, gparam, g_bias, g_exp_scale); break;
-        case LL_BF16: eb_backward_kernel<__nv_bfloat16><<<grid, kEbThreads, 0, s>>>((const __nv_bfloat16 *)z, rows, C, rpc, noise, bias, exp_scale, packed, bound, g_rates, g_zhat, gz, gparam, g_bias, g_exp_scale); break;
+        case LL_F32: eb_backward_kernel<float><<<grid, kEbThreads, 0, s>>>((const float *)z, rows, C, rpc, noise, bias, exp_scale, medians, packed, bound, g_rates, g_q, g_zhat, gz, gparam, g_bias, g_exp_scale); break;
+        case LL_F16: eb_backward_kernel<__half><<<grid, kEbThreads, 0, s>>>((const __half *)z, rows, C, rpc, noise, bias, exp_scale, medians, packed, bound, g_rates, g_q, g_zhat, gz, gparam, g_bias, g_exp_scale); break;
+        case LL_BF16: eb_backward_kernel<__nv_bfloat16><<<grid, kEbThreads, 0, s>>>((const __nv_bfloat16 *)z, rows, C, rpc, noise, bias, exp_scale, medians, packed, bound, g_rates, g_q, g_zhat, gz, gparam, g_bias, g_exp_scale); break;
         default: return fail(LL_ERR_INVALID, "eb_backward: unknown dtype %d", z_dtype);
     }
     LL_LAUNCH_CHECK();

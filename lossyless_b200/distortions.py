@@ -16,7 +16,7 @@ from . import _native as N
 from .architectures import get_Architecture
 from .helpers import BASE_LOG, gather_from_gpus, weights_init
 
-__all__ = ["get_distortion_estimator", "ContrastiveDistortion", "LossyZDistortion", "DirectDistortion"]
+__all__ = ["get_distortion_estimator", "ContrastiveDistortion", "LossyZDistortion", "DirectDistortion", "prediction_loss"]
 
 
 def get_distortion_estimator(mode, **kwargs):
@@ -191,17 +191,43 @@ class LossyZDistortion(nn.Module):
         return dist, dict(), dict()
 
 
+def prediction_loss(Y_hat, y, is_classification=True, agg_over_tasks="mean"):
+    """lossyless/helpers.py:439-489: log loss (classification) or squared error, averaged over the target
+    dimension (dim 1), then aggregated over tasks (trailing dimensions) -> [batch, 1] (or [batch, n_tasks])."""
+    if is_classification:
+        loss = F.cross_entropy(Y_hat, y.long(), reduction="none")
+    else:
+        loss = F.mse_loss(Y_hat, y, reduction="none")
+    while loss.dim() < 3:  # atleast_ndim(loss, 3): n_tasks = 1 if not given
+        loss = loss.unsqueeze(-1)
+    batch_size, Y_dim = loss.shape[:2]
+    loss = loss.view(batch_size, Y_dim, -1).mean(dim=1)  # [batch, n_tasks]
+    if agg_over_tasks is None:
+        return loss
+    if agg_over_tasks in ("max", "min", "median"):
+        return getattr(loss, agg_over_tasks)(keepdim=True, dim=1)[0]
+    if agg_over_tasks in ("mean", "sum", "std"):
+        return getattr(loss, agg_over_tasks)(keepdim=True, dim=1)
+    raise ValueError(f"Unkown agg_over_tasks={agg_over_tasks}.")
+
+
 class DirectDistortion(nn.Module):
-    """Direct variational bound for vector targets (``data_mode="distribution"``): decoder MLP +
-    summed squared error.  Plain torch -- only the CPU plumbing config (banana) uses it."""
+    """Direct variational bound for vector targets (``data_mode="distribution"``, lossyless/distortions.py:41-172):
+    decoder MLP + ``prediction_loss`` (squared error averaged over the target dimension for regression targets, log
+    loss for classification targets), summed over what is left per sample.  Plain torch -- only the CPU plumbing
+    config (banana) uses it; image decoders (cnn / balle, un-normalisation) are outside the hot path."""
 
     def __init__(self, z_dim, y_shape, arch=None, arch_kwargs=dict(), dataset=None, is_normalized=False,
                  data_mode="distribution", name=None, **kwargs):
         super().__init__()
         if data_mode != "distribution":
             raise NotImplementedError("image decoders (cnn / balle) are outside the B200 hot path")
-        self.is_img_out = False
+        if is_normalized:
+            raise NotImplementedError("Can curently only deal with normalized data if it's an image.")
+        self.dataset, self.is_img_out, self.is_normalized = dataset, False, False
         self.q_YlZ = get_Architecture(arch or "mlp", **arch_kwargs)(z_dim, y_shape)
+        self.kwargs = dict(kwargs)  # -> prediction_loss (is_classification, agg_over_tasks)
+        self.kwargs.setdefault("is_classification", False)  # the vector configs (banana) regress their target
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -209,6 +235,6 @@ class DirectDistortion(nn.Module):
 
     def forward(self, z_hat, aux_target, _, __):
         Y_hat = self.q_YlZ(z_hat)
-        neg_log_q_ylz = F.mse_loss(Y_hat, aux_target, reduction="none").flatten(1).sum(-1)
+        neg_log_q_ylz = prediction_loss(Y_hat, aux_target, **self.kwargs).flatten(1).sum(-1)
         logs = dict(H_q_TlZ=neg_log_q_ylz.mean() / math.log(BASE_LOG))
         return neg_log_q_ylz, logs, dict(Y_hat=Y_hat[0].detach().cpu(), Y=aux_target[0].detach().cpu())

@@ -581,7 +581,7 @@ class _EBRate(torch.autograd.Function):
     """(z, biasing, scaling, *eb params) -> (z_hat, q, rates) through ll_eb_forward/backward."""
 
     @staticmethod
-    def forward(ctx, eb, z, noise, biasing, scaling, exp_scale, *params):
+    def forward(ctx, eb, z, noise, biasing, scaling, exp_scale, want_rates, *params):
         N.require_cuda(z, "z")
         z = z.contiguous()
         rows, C = z.shape
@@ -595,34 +595,37 @@ class _EBRate(torch.autograd.Function):
         med = eb._get_medians().detach().reshape(-1).float().contiguous()
         z_hat = torch.empty((rows, C), dtype=torch.float32, device=dev)
         q = torch.empty((rows, C), dtype=torch.float32, device=dev)
-        rates = torch.zeros(rows, dtype=torch.float32, device=dev)
+        rates = torch.zeros(rows, dtype=torch.float32, device=dev) if want_rates else None
         nz = noise.contiguous() if noise is not None else None
         N.call("ll_eb_forward", N.ptr(z), N.dtype_code(z), rows, C, N.ptr(nz), N.ptr(b), N.ptr(es), N.ptr(med),
                N.ptr(packed), _bound(eb), N.ptr(z_hat), N.ptr(q), N.ptr(rates), N.stream())
         ctx.eb, ctx.has_affine, ctx.training_mode = eb, has_affine, noise is not None
-        ctx.save_for_backward(z, nz, b, es, packed, q, *raw[0], *raw[2])
-        ctx.mark_non_differentiable(q)  # gradients flow through the fused `rates` output
+        ctx.save_for_backward(z, nz, b, es, med, packed, q, *raw[0], *raw[2])
+        # q is differentiable too: HRateHyperprior takes -log q(s) of the side bottleneck outside this function
+        # (lossyless/rates.py:640-650); its gradient arrives as g_q and is folded into the same backward launch
         ctx.set_materialize_grads(False)
         return z_hat, q, rates
 
     @staticmethod
     def backward(ctx, g_zhat, g_q, g_rates):
         eb = ctx.eb
-        z, nz, b, es, packed, q, *raw = ctx.saved_tensors
-        if not ctx.training_mode:
-            raise NotImplementedError("backward through the EntropyBottleneck is only defined in training (noise) mode")
+        z, nz, b, es, med, packed, q, *raw = ctx.saved_tensors
         ms, fs = raw[:5], raw[5:]
         rows, C = z.shape
         dev = z.device
-        # likelihood gradients arrive either through rates (-log q summed) or directly through q
-        g_r = g_rates.contiguous().float() if g_rates is not None else torch.zeros(rows, device=dev)
+        if g_zhat is None and g_q is None and g_rates is None:
+            return (None,) * (7 + 14)
+        # likelihood gradients arrive through rates (-log q summed inside the kernel) and / or directly through q;
+        # eval mode (nz is None): round() passes nothing to z, the parameters still get their gradients
+        g_r = g_rates.contiguous().float() if g_rates is not None else None
+        g_qc = g_q.contiguous().float() if g_q is not None else None
         gz = torch.empty((rows, C), dtype=torch.float32, device=dev)
         gparam = torch.zeros((N.LL_EB_NPARAM, C), dtype=torch.float32, device=dev)
         gb = torch.zeros(C, dtype=torch.float32, device=dev) if ctx.has_affine else None
         ges = torch.zeros(C, dtype=torch.float32, device=dev) if ctx.has_affine else None
         gh = g_zhat.contiguous().float() if g_zhat is not None else None
-        N.call("ll_eb_backward", N.ptr(z), N.dtype_code(z), rows, C, N.ptr(nz), N.ptr(b), N.ptr(es), N.ptr(packed),
-               _bound(eb), N.ptr(g_r), N.ptr(gh), N.ptr(gz), N.ptr(gparam), N.ptr(gb), N.ptr(ges), N.stream())
+        N.call("ll_eb_backward", N.ptr(z), N.dtype_code(z), rows, C, N.ptr(nz), N.ptr(b), N.ptr(es), N.ptr(med), N.ptr(packed),
+               _bound(eb), N.ptr(g_r), N.ptr(g_qc), N.ptr(gh), N.ptr(gz), N.ptr(gparam), N.ptr(gb), N.ptr(ges), N.stream())
         # chain rule from the derived parameters back to the raw ones (58 x C elementwise, torch)
         grads_m, grads_b, grads_f = [], [], []
         offs_m, offs_b, offs_f = [0, 9, 24, 39, 54], [3, 18, 33, 48, 57], [6, 21, 36, 51]
@@ -643,7 +646,7 @@ class _EBRate(torch.autograd.Function):
             params_grads += [grads_m[i], grads_b[i]]
             if i < 4:
                 params_grads.append(grads_f[i])
-        return (None, gz.to(z.dtype), None, g_bias, g_scaling, None, *params_grads)
+        return (None, gz.to(z.dtype), None, g_bias, g_scaling, None, None, *params_grads)
 
 
 def eb_rate_forward(eb, z, noise, biasing, scaling, want_rates=True, exp_scale=None):
@@ -652,10 +655,11 @@ def eb_rate_forward(eb, z, noise, biasing, scaling, want_rates=True, exp_scale=N
     z [rows, C]; noise [rows, C] float32 (training) or None (eval: dequantise); biasing /
     scaling are the HRateEstimator parameters (None, None: z is already z_in and the returned
     z_hat is in the bottleneck's domain); ``exp_scale`` optionally supplies a precomputed
-    exp(scaling) (the codec's CPU-evaluated one).  Returns (z_hat, q, rates)."""
+    exp(scaling) (the codec's CPU-evaluated one).  Returns (z_hat, q, rates); ``rates`` is None when
+    ``want_rates`` is False (the per-row reduction and its atomics are skipped)."""
     params = []
     for i in range(5):
         params += [getattr(eb, f"_matrix{i}"), getattr(eb, f"_bias{i}")]
         if i < 4:
             params.append(getattr(eb, f"_factor{i}"))
-    return _EBRate.apply(eb, z, noise, biasing, scaling, exp_scale, *params)
+    return _EBRate.apply(eb, z, noise, biasing, scaling, exp_scale, bool(want_rates), *params)
