@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the encode hot path: img/sec through CLIP ViT-B/32 + EntropyBottleneck + rANS.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--mode encode|train]
 
 One "step" = one batch of synthetic CLIP-normalised 3x224x224 fp16 images through
 ``clip_compressor_b005`` (ViT-B/32 -> process_z_in -> quantise -> rANS -> container records),
@@ -13,8 +13,16 @@ Prints ONE JSON line on rank 0 (contract in the task statement):
   roofline  the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / event-timed GEMM time,
             against the measured bf16 peak in MEASURED_PEAKS.json
   cpu_baseline  the oracle port of the same path on the host cores, bounded sample (N=1)
+  parity    bits/img of BOTH arms on the SAME images and the SAME (fp16-rounded) ViT weights for the three
+            published bottlenecks: GPU vs fp32 CPU oracle, symbol-flip rate of the 16-bit encoder, and the
+            byte-identity of the EB + rANS stage given identical z (N=1)
+  decode    decompress_dataset: device-resident and end-to-end (file -> Z_hat in host memory) img/s, CPU oracle beside
 With ``--impl reference`` the CPU restatement of the reference's own call pattern is timed
-instead (the reference itself cannot be installed: compressai / clip are not available).
+instead (the reference itself cannot be installed: compressai / clip are not available), on the same
+images and weights, 128 images per step (the reference's DataLoader batch, hub/compressor.py:155), with every
+host core (torchrun exports OMP_NUM_THREADS=1: it is undone here).
+``--mode train`` times BASELINE config 3 instead: the rate-distortion training step (CLIP ViT-B/32 unfrozen,
+BINCE, beta = 0.01, per-GPU batch 256, bf16 gradient buckets over NCCL) -- the one path with collectives.
 """
 import argparse
 import json
@@ -134,12 +142,32 @@ class ClockSampler:
                 "source": "nvidia-smi -lms 200"}
 
 
+# ----------------------------------------------------------------------------- shared inputs
+def bench_images(n, rank=0):
+    """The synthetic batch BOTH arms use: CLIP-normalised-like N(0,1) fp16 images from a CPU generator (so the
+    CPU reference arm and the GPU arm see the same pixels), seed 1234 + rank."""
+    import torch
+
+    return torch.randn(n, 3, 224, 224, generator=torch.Generator().manual_seed(1234 + rank)).half()
+
+
+def bench_vit_state_dict():
+    """The ViT-B/32 weights BOTH arms use: the package's seeded random init (no pretrained CLIP offline), rounded
+    to fp16 as the hub model stores them, as float32 CPU tensors under CLIP's own key names."""
+    import torch
+
+    from lossyless_b200.clip_vit import VisionTransformer
+
+    vit = VisionTransformer(224, 32, 768, 12, 12, 512)
+    return {k: v.detach().half().float() for k, v in vit.state_dict().items()}
+
+
 # ----------------------------------------------------------------------------- CPU legs
-def cpu_reference_pipeline(n_images, seed=0, faithful=True):
+def cpu_reference_pipeline(x, faithful=True, tag="beta5e-02"):
     """The reference's path restated on the CPU (oracle): fp32 ViT-B/32 (torch CPU, all host
     threads) -> process_z_in -> quantise -> one rANS call per image.  faithful=True mirrors
     compressai 1.1.5's call pattern (per-image Python loop, `.tolist()` of the symbols and of the
-    whole CDF table, hub/compressor.py:98).  Returns (seconds, bits_per_img)."""
+    whole CDF table, hub/compressor.py:98).  x: fp16 images.  Returns (seconds, bits_per_img, z fp16, strings)."""
     import numpy as np
     import torch
 
@@ -147,104 +175,162 @@ def cpu_reference_pipeline(n_images, seed=0, faithful=True):
     from oracle import rans
     from oracle import vit as ovit
 
-    st = _cpu_state()
-    x = torch.randn(n_images, 3, 224, 224, generator=torch.Generator().manual_seed(seed)).half().float()
+    st = _cpu_state(tag)
+    n_images = x.shape[0]
     t0 = time.perf_counter()
     with torch.no_grad():
-        z = ovit.forward(st["vit"], x).half()  # reference: fp16 z
+        z = ovit.forward(_cpu_vit(), x.float()).half()  # reference: fp16 z
     z_in = oeb.process_z_in(z, st["sd"]["biasing"], st["sd"]["scaling"])
     sym = torch.round(z_in - oeb.medians(st["eb"])[None]).int()
     tab = st["tab"]
-    nbytes = 0
     if faithful:
         idx = list(range(512))
         cdf_t, len_t, off_t = torch.from_numpy(tab["cdf"]), torch.from_numpy(tab["cdf_length"]), torch.from_numpy(tab["offset"])
+        strings = []
         for i in range(n_images):
-            s = rans.encode_with_indexes(sym[i].reshape(-1).int().tolist(), idx, np.array(cdf_t.tolist(), dtype=np.int32),
-                                         len_t.reshape(-1).int().tolist(), off_t.reshape(-1).int().tolist())
-            nbytes += len(s) + 4
+            strings.append(rans.encode_with_indexes(sym[i].reshape(-1).int().tolist(), idx, np.array(cdf_t.tolist(), dtype=np.int32),
+                                                    len_t.reshape(-1).int().tolist(), off_t.reshape(-1).int().tolist()))
     else:
-        nbytes = sum(len(s) + 4 for s in rans.encode_batch(sym.numpy(), tab["cdf"], tab["cdf_length"], tab["offset"]))
-    return time.perf_counter() - t0, 8.0 * nbytes / n_images
+        strings = rans.encode_batch(sym.numpy(), tab["cdf"], tab["cdf_length"], tab["offset"])
+    nbytes = sum(len(s) + 4 for s in strings)
+    return time.perf_counter() - t0, 8.0 * nbytes / n_images, z, strings
 
 
 _CPU = {}
 
 
-def _cpu_state():
-    if not _CPU:
+def _cpu_vit():
+    if "vit" not in _CPU:
+        _CPU["vit"] = bench_vit_state_dict()
+    return _CPU["vit"]
+
+
+def _cpu_state(tag="beta5e-02"):
+    if tag not in _CPU:
         import torch
 
         from oracle import eb as oeb
-        from oracle import vit as ovit
 
-        sd = torch.load(os.path.join(ROOT, "lossyless_b200", "hub", "weights", "beta5e-02_factorized_rate.pt"),
+        sd = torch.load(os.path.join(ROOT, "lossyless_b200", "hub", "weights", f"{tag}_factorized_rate.pt"),
                         map_location="cpu", weights_only=True)
         eb = oeb.split_state_dict(sd)
-        _CPU.update(sd=sd, eb=eb, tab=oeb.update(eb), vit=ovit.init_state_dict(0))
-    return _CPU
+        _CPU[tag] = dict(sd=sd, eb=eb, tab=oeb.update(eb))
+    return _CPU[tag]
+
+
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is ONE process and is entitled to the box."""
+    import torch
+
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+REF_BATCH = 128  # hub/compressor.py:155 kwargs_dataloader=dict(batch_size=128, ...)
 
 
 def run_reference_arm(args):
     """`--impl reference`: the reference's CPU path (oracle port; compressai / clip cannot be
-    installed) timed on this box's host cores; rank 0 only."""
+    installed) timed on this box's host cores; rank 0 only (the other ranks exit 0 without work)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     import torch
 
-    n = args.cpu_images
+    cores = use_all_host_threads()
+    n = args.cpu_images or REF_BATCH
+    X = bench_images(max(n, min(1512, n * max(args.steps, 1))))
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_pipeline(min(n, 4))
-    t, bits = 0.0, 0.0
+        cpu_reference_pipeline(X[:4])
+    t, bits = 0.0, []
     for s in range(args.steps):
-        dt, bits = cpu_reference_pipeline(n, seed=s)
+        lo = (s * n) % max(1, X.shape[0] - n + 1)
+        dt, b, _, _ = cpu_reference_pipeline(X[lo: lo + n])
         t += dt
+        bits.append(b)
     value = n * args.steps / t
-    cores = torch.get_num_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{n} images per step on the host CPU", "bits_per_img": bits},
+        "config": {"workload": WORKLOAD, "sample": f"{n} images per step on the host CPU (the reference's DataLoader batch)",
+                   "bits_per_img": sum(bits) / len(bits), "inputs": "bench_images(seed 1234): the GPU arm's own images and ViT weights"},
         "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps x {n} images: fp32 torch-CPU ViT-B/32 + per-image rANS "
-                                   f"(compressai call pattern), os.cpu_count()={os.cpu_count()}"},
+                                   f"(compressai call pattern), torch threads {cores}, os.cpu_count()={os.cpu_count()}, "
+                                   f"OMP_NUM_THREADS env was {os.environ.get('OMP_NUM_THREADS', 'unset')}"},
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def parity_leg(comp, X, z_gpu, n=256):
+    """Both arms on the SAME n images and the SAME ViT weights, for the three published bottlenecks: bits/img of the
+    GPU path (fp16 tcgen05 ViT -> fused quantise + rANS kernel) against the fp32 CPU oracle, the symbol-flip rate
+    the 16-bit encoder causes, and whether the EB + rANS stage is byte-identical when both are fed the GPU's z."""
+    import numpy as np
+    import torch
+
+    from lossyless_b200.rates import get_rate_estimator
+    from oracle import eb as oeb
+    from oracle import rans
+    from oracle import vit as ovit
+
+    n = min(n, X.shape[0])
+    x_cpu = X[:n].cpu()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        z_f32 = ovit.forward(_cpu_vit(), x_cpu.float())
+    t_vit = time.perf_counter() - t0
+    z_ref = z_f32.half()  # the reference's clip(X) is fp16
+    zg = z_gpu[:n]
+    dz = (zg.float().cpu() - z_f32).abs()
+    out = {"images": n, "weights": "identical: the GPU arm's fp16 ViT-B/32 weights, run in fp32 by the oracle",
+           "vit_abs_err_vs_fp32": {"max": float(dz.max()), "mean": float(dz.mean()), "z_rms": float(z_f32.pow(2).mean().sqrt())},
+           "oracle_vit_img_per_s": n / t_vit}
+    for tag, beta in (("beta1e-01", 0.1), ("beta5e-02", 0.05), ("beta1e-02", 0.01)):
+        st = _cpu_state(tag)
+        r = get_rate_estimator("H_factorized", z_dim=512, kwargs_ent_bottleneck=dict(init_scale=10, filters=[3, 3, 3, 3]))
+        r.load_state_dict(st["sd"])
+        r.to(zg.device).eval()
+        r.prepare_compressor_()
+        with torch.no_grad():
+            s_gpu = r.compress(zg)[0]
+        med = oeb.medians(st["eb"])[None]
+        sym_ref = torch.round(oeb.process_z_in(z_ref, st["sd"]["biasing"], st["sd"]["scaling"]) - med).int()
+        sym_gpu = torch.round(oeb.process_z_in(zg.cpu(), st["sd"]["biasing"], st["sd"]["scaling"]) - med).int()
+        tab = st["tab"]
+        s_ref = rans.encode_batch(sym_ref.numpy(), tab["cdf"], tab["cdf_length"], tab["offset"])
+        s_same_z = rans.encode_batch(sym_gpu.numpy(), tab["cdf"], tab["cdf_length"], tab["offset"])
+        bits_gpu = 8.0 * sum(len(s) + 4 for s in s_gpu) / n
+        bits_ref = 8.0 * sum(len(s) + 4 for s in s_ref) / n
+        out[tag] = {"beta": beta, "bits_per_img_gpu": bits_gpu, "bits_per_img_oracle": bits_ref,
+                    "delta_bits_pct": 100.0 * (bits_gpu - bits_ref) / bits_ref,
+                    "symbol_flip_rate": float((sym_gpu != sym_ref).float().mean()),
+                    "max_symbol_delta": int((sym_gpu - sym_ref).abs().max()),
+                    "bytes_identical_given_z": s_gpu == s_same_z}
+    return out
 
 
 # ----------------------------------------------------------------------------- GPU arm
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (average over one block's four GEMMs) from the
     committed ncu --set full capture; None if the summary is not in the tree."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_vit_gemms_dram_traffic.json")
-    try:
-        with open(path) as f:
-            return float(json.load(f)["per_launch_dram_bytes_layer_average"])
-    except (OSError, KeyError, ValueError):
-        return None
+    prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
+    for name in ("r02_ncu_vit_gemms_dram_traffic.json", "r01_ncu_vit_gemms_dram_traffic.json"):
+        try:
+            with open(os.path.join(prof, name)) as f:
+                return float(json.load(f)["per_launch_dram_bytes_layer_average"]), name
+        except (OSError, KeyError, ValueError):
+            continue
+    return None, None
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1512, help="images per step per GPU (one 1512-image encoder pass = 4 full rounds of 74 CTA pairs x 256 token rows)")
-    ap.add_argument("--chunk", type=int, default=0, help="images per internal ViT pass (0 = library default)")
-    ap.add_argument("--cpu-images", type=int, default=16, help="images per CPU-baseline step")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fuse-ln", action="store_true", help="A/B: run ln_1 / ln_2 as separate kernels")
-    ap.add_argument("--attn-impl", type=int, default=-1, help="A/B: ll_attention_set_impl (0 cp.async, 1 tcgen05, 2 TMA); -1 = library default")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-
-    if args.impl == "reference":
-        return run_reference_arm(args)
-
-    warnings.filterwarnings("ignore", message="no CLIP weights given")
+def dist_setup():
     import torch
     import torch.distributed as dist
 
@@ -263,20 +349,48 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(v):
+    def reduce(v, op):
         if world == 1:
             return v
         t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    return rank, local_rank, world, dev, barrier, (lambda v: reduce(v, dist.ReduceOp.MAX)), (lambda v: reduce(v, dist.ReduceOp.SUM))
 
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="encode", choices=["encode", "train"])
+    ap.add_argument("--batch", type=int, default=0, help="units per step per GPU (encode: 1512 images = one encoder pass of 4 full rounds of 74 CTA pairs x 256 token rows; train: 256 samples)")
+    ap.add_argument("--chunk", type=int, default=0, help="images per internal ViT pass (0 = library default)")
+    ap.add_argument("--cpu-images", type=int, default=0, help="images per CPU-baseline step (0: 128 for --impl reference, 32 for the cpu_baseline leg)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse-ln", action="store_true", help="A/B: run ln_1 / ln_2 as separate kernels")
+    ap.add_argument("--attn-impl", type=int, default=-1, help="A/B: ll_attention_set_impl (0 cp.async, 1 tcgen05, 2 TMA); -1 = library default")
+    ap.add_argument("--roofline-seconds", type=float, default=2.0, help="length of the event-bracketed roofline leg")
+    ap.add_argument("--frozen", action="store_true", help="--mode train: freeze the CLIP tower (config/finetune/freezer.yaml)")
+    ap.add_argument("--distortion", default="BINCE", choices=["BINCE", "lossy_Z"], help="--mode train")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    warnings.filterwarnings("ignore", message="no CLIP weights given")
+    if args.mode == "train":
+        return run_train(args)
+    return run_encode(args)
+
+
+def run_encode(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world, dev, barrier, max_over_ranks, sum_over_ranks = dist_setup()
     import hubconf
 
     comp, _ = hubconf.clip_compressor_b005(device=f"cuda:{local_rank}")
@@ -288,11 +402,10 @@ def main():
         from lossyless_b200 import _native as _N
 
         _N.call("ll_attention_set_impl", args.attn_impl)
-    B = args.batch
+    B = args.batch or 1512
     # encode shards by image: every rank codes its own independent batch, no collective on the path
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    X = torch.randn(B, 3, 224, 224, generator=gen, device=dev, dtype=torch.float32).half()
-    X_host = X.cpu().pin_memory()
+    X_host = bench_images(B, rank).pin_memory()
+    X = X_host.to(dev)
 
     def step_device():
         return comp._compress_records(X, mode=1)
@@ -351,6 +464,15 @@ def main():
     e2e_run(raw_host, args.steps)
     barrier()
     e2e_raw = world * B * args.steps / max_over_ranks(time.perf_counter() - t0)
+    # ---- e2e from CLIP-sized uint8 pixels (224 x 224 x 3, 150 KB per image instead of 301 KB of fp16): what a
+    # DataLoader that resizes on the CPU but leaves ToTensor / Normalize to the GPU feeds
+    u8_host = torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
+    e2e_run(u8_host, 2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(u8_host, args.steps)
+    barrier()
+    e2e_u8 = world * B * args.steps / max_over_ranks(time.perf_counter() - t0)
 
     # ---- what the host link gives: a bare pinned H2D copy of one 378-image sub-batch, nothing else running
     probe_dst = torch.empty_like(X[:378])
@@ -362,16 +484,68 @@ def main():
     ev1.record()
     torch.cuda.synchronize()
     h2d_gbps = 4 * probe_dst.numel() * 2 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    h2d_min = -max_over_ranks(-h2d_gbps)
 
-    # ---- roofline leg: same steps with every GEMM launch bracketed by events
+    # ---- decode: decompress_dataset.  value = kernels only, streams resident in HBM; e2e = the public call on a
+    # container file (file read into pinned memory, index, H2D, decode, Z_hat back in host memory)
+    import tempfile
+
+    reps = 8
+    blob = bytes(packed[:total_bytes].cpu().numpy().data)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, f"Z{rank}.bin")
+        with open(path, "wb") as f:
+            f.write((reps * B).to_bytes(4, "big"))
+            for _ in range(reps):
+                f.write(blob)
+        data_h, off_h, lens_h = comp.load_container(path)
+        n_dec = len(lens_h)
+        z_dev = torch.empty((n_dec, 512), dtype=torch.float32, device=dev)
+        comp.decode_records(data_h, off_h, lens_h, out=z_dev)
+        data_d = data_h.to(dev)
+        off_d, lens_d = torch.from_numpy(off_h).to(dev), torch.from_numpy(lens_h).to(dev)
+        status = torch.zeros(n_dec, dtype=torch.int32, device=dev)
+        es = comp._exp_scale()
+
+        def decode_device():
+            comp.entropy_bottleneck.decompress_from_device(data_d, off_d, lens_d, bias=comp.biasing, exp_scale=es, status_out=status, out=z_dev)
+
+        decode_device()
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(args.steps):
+            decode_device()
+        d1.record()
+        barrier()
+        dec_ms = max_over_ranks(d0.elapsed_time(d1))
+        assert int(status.sum().item()) == 0
+        comp.decompress_dataset(path, is_info=False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            Zd = comp.decompress_dataset(path, is_info=False)
+        barrier()
+        dec_e2e_s = max_over_ranks(time.perf_counter() - t0) / 3
+        assert Zd.shape == (n_dec, 512)
+    decode = {"value": world * n_dec * args.steps / (dec_ms / 1e3), "unit": "img/s", "images": n_dec, "ms_per_call": dec_ms / args.steps,
+              "bytes_per_img": {"in": float(lens_h.mean()), "out": 2048},
+              "achieved_gbs": (float(lens_h.sum()) + 2048.0 * n_dec) * args.steps / (dec_ms / 1e3) / 1e9,
+              "e2e": {"value": world * n_dec / dec_e2e_s, "unit": "img/s", "api": "ClipCompressor.decompress_dataset(file) -> np.ndarray",
+                      "h2d_bytes_per_call": int(off_h[-1]), "d2h_bytes_per_call": n_dec * 2048}}
+
+    # ---- roofline leg: the same steps with every GEMM launch bracketed by events, for >= --roofline-seconds
+    n_prof = max(5, int(args.roofline_seconds / max(ms / args.steps / 1e3, 1e-4)))
+    n_prof = min(n_prof, 400)
     comp.clip.profile_begin()
-    for _ in range(max(2, min(args.steps, 5))):
+    for _ in range(n_prof):
         step_device()
     gemm_ms, gemm_flops, gemm_launches = comp.clip.profile_end()
-    breakdown = {k: v / max(2, min(args.steps, 5)) for k, v in comp.clip.profile_breakdown().items()}
+    breakdown = {k: v / n_prof for k, v in comp.clip.profile_breakdown().items()}
     pk = peaks()
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     vit_launches = comp.clip.launches(B)
+    traffic, traffic_src = ncu_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -381,27 +555,148 @@ def main():
                    "bits_per_img": bits_per_img, "sharding": "independent images per rank, no collective"},
         "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 2, "d2h_bytes_per_step": total_bytes + 8,
                 "input": "pinned host fp16 [B,3,224,224] CLIP-normalised tensors (what the reference's loop body receives)",
-                "api": "ClipCompressor.compress_stream (compress_dataset's loop)", "h2d_link_gbps": h2d_gbps, "blocking_per_batch_call": e2e_blocking},
+                "api": "ClipCompressor.compress_stream (compress_dataset's loop)", "h2d_link_gbps": h2d_gbps, "h2d_link_gbps_min_over_ranks": h2d_min,
+                "blocking_per_batch_call": e2e_blocking},
         "e2e_raw_uint8": {"value": e2e_raw, "unit": "img/s", "h2d_bytes_per_step": B * 96 * 96 * 3,
                           "input": "pinned host uint8 [B,96,96,3] STL10-shaped images; resize/crop/normalise on the GPU"},
+        "e2e_clip_uint8": {"value": e2e_u8, "unit": "img/s", "h2d_bytes_per_step": B * 224 * 224 * 3,
+                           "input": "pinned host uint8 [B,224,224,3] CLIP-sized pixels; ToTensor/Normalize on the GPU"},
+        "decode": decode,
         "gpu_launches": args.steps * (vit_launches + 1 + 2),
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all ViT linears)", "achieved": achieved,
-                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": ncu_traffic(),
-                     "traffic_unit": "bytes of DRAM read + write per GEMM launch (ncu --set full capture, profiles/r01_ncu_vit_gemms_dram_traffic.json)",
-                     "peak_source": pk["source"], "gemm_ms_per_step": gemm_ms / max(2, min(args.steps, 5)),
-                     "gemm_launches_per_step": gemm_launches // max(2, min(args.steps, 5)),
+                     "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
+                     "traffic_unit": f"bytes of DRAM read + write per GEMM launch (ncu --set full capture, profiles/{traffic_src})",
+                     "peak_source": pk["source"], "gemm_ms_per_step": gemm_ms / n_prof,
+                     "gemm_launches_per_step": gemm_launches // n_prof, "leg_steps": n_prof, "leg_seconds": n_prof * ms / args.steps / 1e3,
                      "algorithmic_gflop_per_img": GFLOP_GEMM_PER_IMG,
                      "kernel_ms_per_step": breakdown},
         "clocks": clocks.summary(),
     }
     if world == 1 and not args.no_cpu_baseline:
-        n = args.cpu_images
-        cpu_reference_pipeline(4)
-        t, _ = cpu_reference_pipeline(n)
-        reps = max(1, min(8, int(12.0 / max(t, 1e-3))))
-        tt = t + sum(cpu_reference_pipeline(n, seed=i + 1)[0] for i in range(reps - 1))
-        line["cpu_baseline"] = {"value": n * reps / tt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{reps} x {n} images: fp32 torch-CPU ViT-B/32 + per-image rANS oracle, os.cpu_count()={os.cpu_count()}"}
+        cores = use_all_host_threads()
+        n = args.cpu_images or 32
+        cpu_reference_pipeline(X_host[:4])
+        t, _, _, _ = cpu_reference_pipeline(X_host[:n])
+        reps_c = max(1, min(8, int(10.0 / max(t, 1e-3))))
+        tt = t + sum(cpu_reference_pipeline(X_host[(i + 1) * n: (i + 2) * n])[0] for i in range(reps_c - 1))
+        line["cpu_baseline"] = {"value": n * reps_c / tt, "unit": "img/s", "cores": cores, "kind": "port",
+                                "sample": f"{reps_c} x {n} of the step's own images: fp32 torch-CPU ViT-B/32 + per-image rANS oracle (compressai call pattern), os.cpu_count()={os.cpu_count()}"}
+        with torch.no_grad():
+            z_gpu = comp.clip(X[:256])
+        line["parity"] = parity_leg(comp, X, z_gpu, 256)
+        # CPU decode beside the GPU decode: the oracle's C decoder, single thread, on a bounded sample of the same file
+        from oracle import eb as oeb
+
+        st = _cpu_state("beta5e-02")
+        raw = data_h.numpy()
+        n_cpu = min(2048, n_dec)
+        strings = [raw[off_h[i]: off_h[i] + lens_h[i]].tobytes() for i in range(n_cpu)]
+        t0 = time.perf_counter()
+        zd, _ = oeb.decompress(st["eb"], st["tab"], strings)
+        zd = oeb.process_z_out(zd, st["sd"]["biasing"], st["sd"]["scaling"])
+        t_dec = time.perf_counter() - t0
+        line["decode"]["cpu_baseline"] = {"value": n_cpu / t_dec, "unit": "img/s", "cores": 1, "kind": "port",
+                                          "sample": f"{n_cpu} records of the same file, batched C rANS decoder (oracle), one thread",
+                                          "matches_gpu": bool(torch.equal(zd, z_dev[:n_cpu].cpu()))}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- training mode (BASELINE config 3)
+TRAIN_METRIC = "img/sec rate-distortion training step (CLIP ViT-B/32, H_factorized + contrastive, beta=0.01)"
+
+
+def run_train(args):
+    """One step = LearnableCompressor.fit's loop body on one per-GPU batch: forward of both views through the CLIP
+    tower, EntropyBottleneck rate, contrastive (BINCE) distortion incl. the logits-tile all_gather, backward through
+    the tower, bf16 gradient-bucket all-reduce over NCCL, clip, AdamW ("main") + the coder optimiser pass."""
+    import torch
+    import torch.distributed as dist
+
+    from lossyless_b200.learnable_compressors import LearnableCompressor, default_clip_hparams
+
+    rank, local_rank, world, dev, barrier, max_over_ranks, sum_over_ranks = dist_setup()
+    B = args.batch or 256
+    torch.manual_seed(1234)  # identical parameters on every rank (the ViT init is seeded separately)
+    hp = default_clip_hparams(distortion=args.distortion, beta=1e-2, max_steps=1000, n_data=50000, is_frozen=args.frozen)
+    model = LearnableCompressor(hp).to(dev).train()
+    fit_kw = {} if args.frozen else dict(grad_comm_dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    xp_host = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    x, x_pos = x_host.to(dev), xp_host.to(dev)
+    batch = (x, (None, x_pos))
+    model.fit([batch] * args.warmup, **fit_kw)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        logged = model.fit([batch] * args.steps, **fit_kw)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+    value = world * B * args.steps / (ms / 1e3)
+
+    # the same steps without the gradient all-reduce (ranks drift apart: timing only) -> exposed collective time
+    exposed = None
+    if world > 1:
+        model.fit([batch] * 2, skip_grad_sync=True, **fit_kw)
+        barrier()
+        e0.record()
+        model.fit([batch] * args.steps, skip_grad_sync=True, **fit_kw)
+        e1.record()
+        barrier()
+        ms_nosync = max_over_ranks(e0.elapsed_time(e1))
+        exposed = (ms - ms_nosync) / args.steps
+
+    # e2e: host batches (pinned fp32, what a DataLoader hands over) -> H2D inside the step, loss read back per step
+    def host_batches(n):
+        for _ in range(n):
+            yield (x_host.to(dev, non_blocking=True), (None, xp_host.to(dev, non_blocking=True)))
+
+    def e2e_steps(n):
+        out = 0.0
+        for b in host_batches(n):
+            lg = model.fit([b], **fit_kw)
+            out = lg["train/feat/loss"]  # fit() returns floats: a D2H read of the step's loss
+        return out
+
+    e2e_steps(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps(args.steps)
+    barrier()
+    e2e = world * B * args.steps / max_over_ranks(time.perf_counter() - t0)
+    views = 2 if args.distortion == "BINCE" else 1
+    passes = 1 if args.frozen else 3  # forward (+ backward = 2x) through the tower
+    flops = world * B * views * passes * GFLOP_GEMM_PER_IMG * 1e9
+    pk = peaks()
+    achieved = flops / (ms / args.steps / 1e3) / 1e12 / world
+    n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    line = {
+        "metric": TRAIN_METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 GEMMs (fp32 accumulate, fp32 master weights, fp32 entropy model)" if not args.frozen else "f16 tower, fp32 entropy model",
+        "data": "synthetic",
+        "config": {"workload": f"RD training step, CLIP ViT-B/32 {'frozen' if args.frozen else 'unfrozen'}, rate=H_factorized, distortion={args.distortion}, "
+                               f"per-GPU batch {B}, AdamW 1e-3 / 3e-4, clip 3 (SURVEY 8d config 3)",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}", "trainable_params": n_params,
+                   "l2": f"inputs {2 * B * 3 * 224 * 224 * 4 / 1e6:.0f} MB/step and {n_params * 2 / 1e6:.0f} MB of bf16 weights > 126 MB L2"},
+        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": 2 * B * 3 * 224 * 224 * 4, "d2h_bytes_per_step": 4 * len(logged),
+                "api": "LearnableCompressor.fit([batch]) per step with pinned host float32 batches; logged scalars read back"},
+        "collective": {"grad_allreduce_bytes_per_step": (n_params * 2 if not args.frozen else n_params * 4) if world > 1 else 0,
+                       "logits_tile_allgather_bytes_per_rank": (2 * B) ** 2 * 4 if (world > 1 and args.distortion == "BINCE") else 0,
+                       "exposed_ms_per_step": exposed},
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (forward, dgrad and wgrad of every ViT linear)",
+                     "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                     "peak_source": pk["source"], "algorithmic_gflop_per_sample": views * passes * GFLOP_GEMM_PER_IMG,
+                     "note": "whole-step FLOP rate per GPU (step time includes every non-GEMM kernel and the collectives)"},
+        "loss": logged.get("train/feat/loss"), "rate_bits": logged.get("train/feat/rate"),
+        "clocks": clocks.summary(),
+    }
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

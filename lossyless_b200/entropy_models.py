@@ -197,9 +197,13 @@ class EntropyModel(nn.Module):
         N.call("ll_rans_pack", N.ptr(scratch), N.ptr(lens), rows, cap, mode, N.ptr(packed), N.ptr(offsets), N.stream())
         return packed, offsets, lens, symbols
 
-    def decompress_from_device(self, data, offsets, lens, bias=None, exp_scale=None, want_symbols=False, indexes=None, means=None):
+    def decompress_from_device(self, data, offsets, lens, bias=None, exp_scale=None, want_symbols=False, indexes=None, means=None,
+                               status_out=None, out=None):
         """Batched decode of streams stored in a device byte buffer -> (z_hat [rows,C] fp32,
-        symbols|None).  Raises ValueError if any stream is malformed."""
+        symbols|None).  Raises ValueError if any stream is malformed -- unless ``status_out`` (int32 [rows], device)
+        is given: then the per-row status words are left there for the caller to check once (no host
+        synchronisation per call; this is what lets a decode loop be pipelined).  ``out`` optionally supplies the
+        [rows, C] float32 destination."""
         N.require_cuda(data, "data")
         if self.entropy_coder is None:
             self.entropy_coder = _RansCoder()
@@ -211,17 +215,21 @@ class EntropyModel(nn.Module):
         mu = means.detach().float().contiguous() if means is not None else None
         if rows == 0:
             return torch.empty((0, C), dtype=torch.float32, device=data.device), None
-        z_hat = torch.empty((rows, C), dtype=torch.float32, device=data.device)
-        status = torch.empty(rows, dtype=torch.int32, device=data.device)
+        z_hat = out if out is not None else torch.empty((rows, C), dtype=torch.float32, device=data.device)
+        if z_hat.shape != (rows, C) or z_hat.dtype != torch.float32 or not z_hat.is_contiguous():
+            raise ValueError("`out` must be a contiguous float32 [rows, C] tensor")
+        status = status_out if status_out is not None else torch.empty(rows, dtype=torch.int32, device=data.device)
         symbols = torch.empty((rows, C), dtype=torch.int32, device=data.device) if want_symbols else None
+        offsets, lens = offsets.contiguous(), lens.contiguous()
         b = bias.detach().float().contiguous() if bias is not None else None
         es = exp_scale.detach().float().contiguous() if exp_scale is not None else None
         N.call("ll_rans_decode_indexed", N.ptr(data), N.ptr(offsets), N.ptr(lens), rows, C, N.ptr(t["cdf"]), t["stride"],
                N.ptr(t["cdf_len"]), N.ptr(t["offset"]), N.ptr(med), N.ptr(idx), N.ptr(mu), N.ptr(b), N.ptr(es), N.ptr(z_hat),
                N.ptr(symbols), N.ptr(status), N.stream())
-        bad = int(status.sum().item())
-        if bad:
-            raise ValueError(f"{bad} of {rows} rANS streams are truncated or corrupt")
+        if status_out is None:
+            bad = int(status.sum().item())
+            if bad:
+                raise ValueError(f"{bad} of {rows} rANS streams are truncated or corrupt")
         return z_hat, symbols
 
     @staticmethod

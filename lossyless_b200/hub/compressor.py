@@ -373,6 +373,9 @@ class ClipCompressor(nn.Module):
             pipe = dict(key=key, cap=need, stream=torch.cuda.Stream(dev),
                         buf=[torch.empty((need,) + tuple(X_host.shape[1:]), dtype=X_host.dtype, device=dev) for _ in range(2)],
                         ready=[torch.cuda.Event(), torch.cuda.Event()], consumed=[None, None], next=0)
+            # the caching allocator may hand the new slots a block that a kernel still queued on the main stream is
+            # using (e.g. a previous ViT workspace): the copy stream must not write into them before that work is done
+            pipe["stream"].wait_stream(torch.cuda.current_stream(dev))
             self._pipe = pipe
         return pipe
 
@@ -408,39 +411,95 @@ class ClipCompressor(nn.Module):
         enc_time = (time.time() - start) / max(n, 1)
         rate = 8 * Path(file).stat().st_size / max(n, 1)
 
-        if label_file is not None:
-            np.save(label_file, np.concatenate(Y), allow_pickle=False)  # no pickle for portability
+        if label_file is not None:  # no pickle for portability
+            np.save(label_file, np.concatenate(Y) if Y else np.zeros(0, dtype=np.uint16), allow_pickle=False)
 
         if is_info:
             print(f"Rate: {rate:.2f} bits/img | Encoding: {1/enc_time:.2f} img/sec ")
 
-    def decompress_dataset(self, file, label_file=None, is_info=True, is_cpu=True, batch_size=8192):
+    def load_container(self, file):
+        """Reads a container written by ``compress_dataset`` into page-locked memory and indexes its records on the
+        host (``ll_container_index``): returns (data uint8 pinned [size + 16], offsets int64 [N + 1] of each record's
+        payload, lens int32 [N]).  Raises ValueError on a truncated / malformed file."""
+        import os
+
+        size = os.path.getsize(str(file))
+        if size < 4:
+            raise ValueError(f"{file}: truncated container (no record count)")
+        pin = torch.cuda.is_available()
+        data = torch.empty(size + 16, dtype=torch.uint8, pin_memory=pin)  # +16: the decoder prefetches a word ahead
+        view = data.numpy()
+        with open(str(file), "rb") as f:
+            got = f.readinto(memoryview(view)[:size])
+        if got != size:
+            raise ValueError(f"{file}: short read ({got} of {size} bytes)")
+        view[size:] = 0
+        n_Z = struct.unpack(">I", view[:4].tobytes())[0]
+        offsets = np.zeros(n_Z + 1, dtype=np.int64)
+        lens = np.zeros(n_Z, dtype=np.int32)
+        try:
+            N.call("ll_container_index", view.ctypes.data, size, 4, n_Z, offsets.ctypes.data, lens.ctypes.data)
+        except N.NativeError as e:
+            raise ValueError(f"{file}: {e}") from None
+        if n_Z and ((lens % 4 != 0).any() or (lens < 8).any()):
+            raise ValueError(f"{file}: malformed record length (rANS streams are >= 8 bytes, multiple of 4)")
+        return data, offsets, lens
+
+    @torch.no_grad()
+    def decode_records(self, data, offsets, lens, lo=0, hi=None, batch_size=32768, out=None):
+        """Decodes records [lo, hi) of an indexed container (``load_container``) as a software pipeline and returns
+        ``Z_hat`` float32 [hi - lo, 512] in page-locked host memory (or in ``out``, a device tensor, without the D2H
+        leg).  Only the byte range of the slice crosses the link; the slice is walked in chunks of ``batch_size`` rows:
+        chunk i + 1 decodes on the main stream while chunk i's rows travel back on a copy stream; the per-row status
+        words are checked ONCE at the end (one host synchronisation per call, none per chunk)."""
+        dev = torch.device(self.device)
+        hi = len(lens) if hi is None else hi
+        n = hi - lo
+        to_host = out is None
+        if to_host:
+            out = torch.empty((n, self.z_dim), dtype=torch.float32, pin_memory=True)
+        if n == 0:
+            return out
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_d2h_stream", None) is None:
+            self._d2h_stream = torch.cuda.Stream(dev)
+        d2h = self._d2h_stream
+        b0, b1 = int(offsets[lo]), int(offsets[hi])
+        data_d = torch.empty(b1 - b0 + 16, dtype=torch.uint8, device=dev)
+        data_d.copy_(data[b0: b1 + 16], non_blocking=True)  # `data` carries 16 pad bytes past the last record
+        off_d = torch.from_numpy(offsets[lo: hi + 1] - b0).to(dev, non_blocking=True)
+        lens_d = torch.from_numpy(np.ascontiguousarray(lens[lo:hi])).to(dev, non_blocking=True)
+        status = torch.zeros(n, dtype=torch.int32, device=dev)
+        es = self._exp_scale()
+        keep = []
+        for i0 in range(0, n, batch_size):
+            i1 = min(n, i0 + batch_size)
+            dst = out[i0:i1] if not to_host else None
+            z, _ = self.entropy_bottleneck.decompress_from_device(
+                data_d, off_d[i0:i1 + 1], lens_d[i0:i1], bias=self.biasing, exp_scale=es, status_out=status[i0:i1], out=dst)
+            if to_host:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(ev)
+                    out[i0:i1].copy_(z, non_blocking=True)
+                    z.record_stream(d2h)
+                keep.append(z)
+        bad = int(status.sum().item())  # the one synchronisation of the main stream
+        d2h.synchronize()
+        if bad:
+            raise ValueError(f"{bad} of {n} rANS streams are truncated or corrupt")
+        return out
+
+    def decompress_dataset(self, file, label_file=None, is_info=True, is_cpu=True, batch_size=32768):
         """Decompress a dataset saved by ``compress_dataset``; returns ``Z_hat`` float32 [N,512]
         (and ``Y`` int64 if ``label_file``).  ``is_cpu`` is accepted but decoding runs on the GPU."""
         if str(self.device).startswith("cpu"):
             raise N.NativeError("decompress_dataset needs the compressor on a B200 (cuda); there is no CPU path")
         start = time.time()
-        raw = np.fromfile(str(file), dtype=np.uint8)
-        if raw.size < 4:
-            raise ValueError(f"{file}: truncated container (no record count)")
-        n_Z = struct.unpack(">I", raw[:4].tobytes())[0]
-        offsets = np.zeros(n_Z + 1, dtype=np.int64)
-        lens = np.zeros(n_Z, dtype=np.int32)
-        try:
-            N.call("ll_container_index", raw.ctypes.data, raw.size, 4, n_Z, offsets.ctypes.data, lens.ctypes.data)
-        except N.NativeError as e:
-            raise ValueError(f"{file}: {e}") from None
-        if n_Z and ((lens % 4 != 0).any() or (lens < 8).any()):
-            raise ValueError(f"{file}: malformed record length (rANS streams are >= 8 bytes, multiple of 4)")
-        Z_hat = np.empty((n_Z, self.z_dim), dtype=np.float32)
-        data = torch.from_numpy(np.concatenate([raw, np.zeros(16, dtype=np.uint8)])).to(self.device)
-        off_d, lens_d = torch.from_numpy(offsets).to(self.device), torch.from_numpy(lens).to(self.device)
-        es = self._exp_scale()
-        for i0 in _progress(range(0, n_Z, batch_size)):
-            i1 = min(n_Z, i0 + batch_size)
-            z, _ = self.entropy_bottleneck.decompress_from_device(
-                data, off_d[i0:i1 + 1].contiguous(), lens_d[i0:i1].contiguous(), bias=self.biasing, exp_scale=es)
-            Z_hat[i0:i1] = z.cpu().numpy()
+        data, offsets, lens = self.load_container(file)
+        n_Z = len(lens)
+        Z_hat = self.decode_records(data, offsets, lens, 0, n_Z, batch_size=batch_size).numpy()
 
         dec_time = (time.time() - start) / max(n_Z, 1)
         if is_info:

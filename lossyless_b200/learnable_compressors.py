@@ -227,13 +227,17 @@ class LearnableCompressor(nn.Module):
     # -- minimal trainer -----------------------------------------------------------------
     # -- checkpoints (Lightning's file layout, reference main.py:516-547) ------------------
     def save_checkpoint(self, path, weights_only=True):
-        """``trainer.save_checkpoint(path, weights_only=True)``: ``state_dict`` + ``hyper_parameters`` +
-        step counters under Lightning's key names, so the reference's ``load_from_checkpoint`` and this
-        class's read each other's files (the module / parameter names are the reference's)."""
+        """``trainer.save_checkpoint(path, weights_only=True)``: ``state_dict`` + ``hyper_parameters`` + step counters
+        under Lightning's key names.  ``hparams_name`` is written as Lightning 1.x writes it for
+        ``save_hyperparameters(hparams)`` (``hparams_type`` only exists for omegaconf containers): without ``hparams_name`` its ``_load_model_state`` would spread the
+        hyper-parameters as keyword arguments instead of passing the one ``hparams`` container the reference's
+        ``LearnableCompressor.__init__(hparams)`` takes.  Non-plain entries are made portable: ``torch.dtype`` values
+        become strings, an embedded CLIP state dict (``encoder.arch_kwargs.clip_state_dict``) is dropped -- the
+        weights are in ``state_dict`` already."""
         self.rate_estimator.make_pickable_()
         ckpt = dict(state_dict=self.state_dict(), hyper_parameters=_plain(self.hparams), global_step=self.global_step,
-                    epoch=self.current_epoch)
-        ckpt["pytorch-lightning_version"] = "1.1.5"  # what requirements/environment.yaml pins; informational
+                    epoch=self.current_epoch, hparams_name="hparams")
+        ckpt["pytorch-lightning_version"] = "1.3.8"  # what requirements/environment.yaml pins; informational
         torch.save(ckpt, path)
 
     @classmethod
@@ -244,7 +248,7 @@ class LearnableCompressor(nn.Module):
         ckpt = checkpoint_path if isinstance(checkpoint_path, dict) else torch.load(checkpoint_path, map_location=map_location, weights_only=False)
         if "state_dict" not in ckpt or "hyper_parameters" not in ckpt:
             raise KeyError("not a Lightning checkpoint: need 'state_dict' and 'hyper_parameters'")
-        hp = dict(ckpt["hyper_parameters"])
+        hp = _unplain(dict(ckpt["hyper_parameters"]))
         hp.update(kwargs)
         model = cls(NamespaceMap(hp))
         model.load_state_dict(ckpt["state_dict"], strict=strict)
@@ -252,16 +256,28 @@ class LearnableCompressor(nn.Module):
         model.current_epoch = int(ckpt.get("epoch", 0))
         return model
 
-    def fit(self, batches, max_steps=None, grad_clip=3.0, process_group=None, grad_comm_dtype=None, callbacks=()):
-        """Lightning-free ``Trainer.fit``: per batch, one pass per optimiser ("main" then "coder");
-        ``gradient_clip_val=3`` as config/main.yaml; with ``torch.distributed`` initialised the
+    def fit(self, batches, max_steps=None, grad_clip=3.0, process_group=None, grad_comm_dtype=None, callbacks=(),
+            skip_grad_sync=False):
+        """Lightning-free ``Trainer.fit``, ONE EPOCH per call: per batch, one pass per optimiser ("main" then
+        "coder"); ``gradient_clip_val=3`` as config/main.yaml; with ``torch.distributed`` initialised the
         trainable gradients are all-reduced (mean) in flat buckets per pass (``allreduce_mean_``;
-        ``grad_comm_dtype=torch.bfloat16`` for the bf16 buckets of an unfrozen encoder)."""
-        for cb in callbacks:  # BaseFinetuning hooks run before the optimisers see the parameters
-            if hasattr(cb, "freeze_before_training"):
-                cb.freeze_before_training(self)
-        optimizers, schedulers = self.configure_optimizers()
-        is_dist = torch.distributed.is_available() and torch.distributed.is_initialized()
+        ``grad_comm_dtype=torch.bfloat16`` for the bf16 buckets of an unfrozen encoder).
+
+        Optimisers and schedulers are built ONCE (first call; ``configure_optimizers``) and kept on the module, so
+        AdamW moments survive across calls; at the end of every call the schedulers step (Lightning's default
+        ``interval="epoch"``) and ``current_epoch`` advances -- ``expdecay`` / ``MultiStepLR`` schedules and
+        ``warmup_k_epoch`` see the epochs go by.  ``reset_optimizers_()`` drops the cached state (e.g. after
+        un-freezing parameters)."""
+        state = getattr(self, "_trainer_state", None)
+        if state is None:
+            for cb in callbacks:  # BaseFinetuning hooks run before the optimisers see the parameters
+                if hasattr(cb, "freeze_before_training"):
+                    cb.freeze_before_training(self)
+            optimizers, schedulers = self.configure_optimizers()
+            state = self._trainer_state = dict(optimizers=optimizers, schedulers=schedulers)
+        optimizers, schedulers = state["optimizers"], state["schedulers"]
+        # skip_grad_sync: timing A/B only (bench.py --mode train measures the exposed collective time with it)
+        is_dist = torch.distributed.is_available() and torch.distributed.is_initialized() and not skip_grad_sync
         self.train()
         # no host synchronisation inside the loop (see log_dict); LL_SYNC_LOGS=1 restores a float() per logged scalar (A/B)
         self._defer_log_sync = os.environ.get("LL_SYNC_LOGS", "0") != "1"
@@ -272,7 +288,12 @@ class LearnableCompressor(nn.Module):
             self.logged = {k: (float(v) if torch.is_tensor(v) else v) for k, v in self.logged.items()}
         for s in schedulers:
             s["scheduler"].step()
+        self.current_epoch += 1
         return self.logged
+
+    def reset_optimizers_(self):
+        """Forget the optimisers / schedulers ``fit`` keeps between calls (they are rebuilt on the next call)."""
+        self._trainer_state = None
 
     def _fit_loop(self, batches, optimizers, max_steps, grad_clip, is_dist, process_group, grad_comm_dtype):
         for batch_idx, batch in enumerate(batches):
@@ -291,12 +312,28 @@ class LearnableCompressor(nn.Module):
             self.global_step += 1
 
 
-def _plain(d):
-    """NamespaceMap -> nested plain dicts (what ends up under 'hyper_parameters'); dtypes become strings."""
+def _plain(d, key=None):
+    """NamespaceMap -> nested plain dicts (what ends up under 'hyper_parameters'): ``torch.dtype`` values become
+    strings ("torch.bfloat16"), embedded state dicts (``clip_state_dict``) are dropped."""
+    if key == "clip_state_dict":
+        return None
     if isinstance(d, dict):
-        return {k: _plain(v) for k, v in d.items()}
+        return {k: _plain(v, k) for k, v in d.items()}
     if isinstance(d, (list, tuple)):
         return type(d)(_plain(v) for v in d)
+    if isinstance(d, torch.dtype):
+        return str(d)
+    return d
+
+
+def _unplain(d):
+    """Inverse of ``_plain`` for the dtype strings."""
+    if isinstance(d, dict):
+        return {k: _unplain(v) for k, v in d.items()}
+    if isinstance(d, (list, tuple)):
+        return type(d)(_unplain(v) for v in d)
+    if isinstance(d, str) and d.startswith("torch.") and isinstance(getattr(torch, d[6:], None), torch.dtype):
+        return getattr(torch, d[6:])
     return d
 
 

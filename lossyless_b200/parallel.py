@@ -5,6 +5,11 @@ under torchrun / torch.distributed:
     slice of the dataset with NO collective on the data path; the per-rank record blobs are
     gathered once at the end and rank 0 writes header + blobs in rank order, so the file is
     byte-identical to the single-GPU file (hub/compressor.py:192-196 format);
+  * decode (``decompress_dataset``): records are independent too -> the container is indexed on every rank (a
+    host-side walk over the length prefixes), the records are split into contiguous ranges by the PREFIX SUM OF
+    THEIR LENGTHS (equal bytes per rank: a stream's decode time follows its length), every rank decodes its range
+    with no collective on the data path, and the rows are gathered once on rank 0 in record order
+    (hub/compressor.py:209-254 is the serial loop this replaces);
   * rate-distortion training: data parallel, gradient all-reduce on the (small) trainable
     bucket only (``learnable_compressors.allreduce_mean_``) plus the reference's all_gather of
     logit tiles inside the contrastive distortion (``helpers.GatherFromGpus``).
@@ -16,7 +21,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "gather_record_blobs", "write_container", "compress_dataset_sharded"]
+__all__ = ["shard_range", "gather_record_blobs", "write_container", "compress_dataset_sharded",
+           "split_records_by_bytes", "gather_rows", "decompress_dataset_sharded"]
 
 
 def shard_range(n, rank, world):
@@ -86,3 +92,59 @@ def compress_dataset_sharded(compressor, dataset, file, label_file=None, batch_s
     if label_file is not None:
         np.save(label_file, np.concatenate([np.asarray(l, dtype=np.uint16) for l in lab]), allow_pickle=False)
     return sum(counts), Path(file).stat().st_size
+
+
+def split_records_by_bytes(lens, world):
+    """Contiguous record ranges [(lo, hi)] * world with (nearly) equal payload bytes: rank r takes the records whose
+    cumulative length falls in [r, r + 1) * total / world.  Every record lands in exactly one range, in order."""
+    lens = np.asarray(lens, dtype=np.int64)
+    n = len(lens)
+    if n == 0:
+        return [(0, 0)] * world
+    csum = np.cumsum(lens + 4)  # + the 4-byte length prefix each record carries
+    total = int(csum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(csum, r * total / world, side="left")))
+    cuts.append(n)
+    cuts = np.maximum.accumulate(np.minimum(cuts, n))
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
+
+
+def gather_rows(rows, counts, group=None):
+    """Row blocks of every rank (``rows`` [counts[rank], C] float32, device tensor under nccl, CPU tensor under gloo)
+    -> on rank 0 one [sum(counts), C] CPU tensor in rank order; None elsewhere.  One padded gather."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cap = max(max(counts), 1)
+    C = rows.shape[1]
+    pad = torch.zeros((cap, C), dtype=rows.dtype, device=rows.device)
+    pad[: rows.shape[0]] = rows
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, bufs, dst=0, group=group)
+    if rank != 0:
+        return None
+    return torch.cat([bufs[r][: counts[r]].cpu() for r in range(world)], dim=0)
+
+
+@torch.no_grad()
+def decompress_dataset_sharded(compressor, file, label_file=None, group=None, decode_fn=None):
+    """``ClipCompressor.decompress_dataset`` over all ranks of the process group.  Returns ``Z_hat`` float32
+    [N, 512] (and ``Y``) on rank 0, None elsewhere.  ``decode_fn(data, offsets, lens, lo, hi) -> [hi - lo, C]
+    tensor`` replaces the compressor's GPU decode (the gloo test injects a host decoder)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    data, offsets, lens = compressor.load_container(file)
+    spans = split_records_by_bytes(lens, world)
+    lo, hi = spans[rank]
+    if decode_fn is not None:
+        z = decode_fn(data, offsets, lens, lo, hi)
+    else:
+        dev = torch.device(compressor.device)
+        z = torch.empty((hi - lo, compressor.z_dim), dtype=torch.float32, device=dev)
+        compressor.decode_records(data, offsets, lens, lo, hi, out=z)
+    Z = gather_rows(z, [b - a for a, b in spans], group)
+    if rank != 0:
+        return None
+    Z = Z.numpy()
+    if label_file is not None:
+        return Z, np.load(label_file, allow_pickle=False).astype(np.int64)
+    return Z

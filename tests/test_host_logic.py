@@ -124,7 +124,8 @@ def test_checkpoint_layout_roundtrip(tmp_path):
     path = tmp_path / "best_feat.ckpt"
     model.save_checkpoint(path)
     raw = torch.load(path, map_location="cpu", weights_only=False)
-    assert {"state_dict", "hyper_parameters", "global_step", "epoch"} <= set(raw)
+    assert {"state_dict", "hyper_parameters", "global_step", "epoch", "hparams_name"} <= set(raw)
+    assert raw["hparams_name"] == "hparams"  # Lightning passes ONE container to __init__(hparams) only with this key
     assert any(k.startswith("p_ZlX.mapper.") for k in raw["state_dict"])
     assert any(k.startswith("rate_estimator.entropy_bottleneck.") for k in raw["state_dict"])
     assert isinstance(raw["hyper_parameters"], dict) and type(raw["hyper_parameters"]["rate"]) is dict
@@ -134,6 +135,53 @@ def test_checkpoint_layout_roundtrip(tmp_path):
         assert torch.equal(a, b), k
     with pytest.raises(KeyError):
         LearnableCompressor.load_from_checkpoint({"weights": {}})
+
+
+def test_checkpoint_hparams_are_portable(tmp_path):
+    """torch.dtype entries are stringified and an embedded CLIP state dict is dropped from 'hyper_parameters'."""
+    import torch
+
+    from lossyless_b200.learnable_compressors import _plain, _unplain
+
+    hp = dict(encoder=dict(arch_kwargs=dict(compute_dtype=torch.bfloat16, clip_state_dict={"w": torch.zeros(3)}, is_frozen=True)), n=(1, 2))
+    plain = _plain(hp)
+    assert plain == dict(encoder=dict(arch_kwargs=dict(compute_dtype="torch.bfloat16", clip_state_dict=None, is_frozen=True)), n=(1, 2))
+    assert _unplain(plain)["encoder"]["arch_kwargs"]["compute_dtype"] is torch.bfloat16
+
+
+def test_fit_keeps_optimizer_state_and_steps_schedulers():
+    """fit() = one epoch per call: optimisers / schedulers are built once, AdamW moments survive across calls, the
+    schedulers step once per call and current_epoch advances (they used to be rebuilt on every call)."""
+    import torch
+
+    from lossyless_b200.learnable_compressors import LearnableCompressor
+
+    hp = _banana_hparams()
+    from lossyless_b200.helpers import NamespaceMap
+
+    hp["scheduler_feat"] = NamespaceMap(modes=["expdecay"], kwargs=dict(expdecay=dict(epochs=10, decay_factor=100)))
+    model = LearnableCompressor(hp)
+    seen = {}
+
+    def fake_step(self_, batch, batch_idx, optimizer_idx=0):  # a CPU-only loss over every trainable parameter
+        ps = [p for g in seen["opt"][optimizer_idx].param_groups for p in g["params"]]
+        return sum((p ** 2).sum() for p in ps)
+
+    opts, scheds = model.configure_optimizers()
+    model._trainer_state = dict(optimizers=opts, schedulers=scheds)
+    seen["opt"] = opts
+    model.training_step = fake_step.__get__(model)
+    lr0 = opts[0].param_groups[0]["lr"]
+    model.fit([None, None])
+    assert model.current_epoch == 1 and model.global_step == 2
+    st = opts[0].state[opts[0].param_groups[0]["params"][0]]
+    assert int(st["step"]) == 2
+    model.fit([None])
+    assert model._trainer_state["optimizers"][0] is opts[0] and int(st["step"]) == 3 and model.current_epoch == 2
+    assert len(scheds) == 1
+    assert opts[0].param_groups[0]["lr"] == pytest.approx(lr0 * (1 / 100) ** (2 / 10))  # two epochs of the decay
+    model.reset_optimizers_()
+    assert model._trainer_state is None
 
 
 def test_freezer_callback():

@@ -41,7 +41,7 @@ def _worker(rank, world, port, tmp):
     import hubconf
     from lossyless_b200.distortions import ContrastiveDistortion
     from lossyless_b200.learnable_compressors import allreduce_mean_
-    from lossyless_b200.parallel import compress_dataset_sharded
+    from lossyless_b200.parallel import compress_dataset_sharded, decompress_dataset_sharded
     from oracle import losses as olosses
 
     comp, _ = hubconf.clip_compressor_b005(device=f"cuda:{rank}")
@@ -49,6 +49,16 @@ def _worker(rank, world, port, tmp):
     compress_dataset_sharded(comp, ds, os.path.join(tmp, "sharded.bin"), label_file=os.path.join(tmp, "y.npy"), batch_size=16)
     if rank == 0:
         comp.compress_dataset(ds, os.path.join(tmp, "single.bin"), kwargs_dataloader=dict(batch_size=16, num_workers=0), is_info=False)
+    dist.barrier()
+    # sharded decode of that file: records split by the prefix sum of their lengths, no collective on the data path,
+    # rows gathered on rank 0 == the single-GPU decode
+    out = decompress_dataset_sharded(comp, os.path.join(tmp, "sharded.bin"), label_file=os.path.join(tmp, "y.npy"))
+    if rank == 0:
+        Z, Y = out
+        Z1 = comp.decompress_dataset(os.path.join(tmp, "sharded.bin"), is_info=False)
+        assert Z.shape == (45, 512) and np.array_equal(Z, Z1) and Y.tolist() == [i % 7 for i in range(45)]
+    else:
+        assert out is None
 
     # contrastive distortion with the real all_gather: same projector on both ranks, different data
     gen = torch.Generator().manual_seed(7)
