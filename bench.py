@@ -634,7 +634,7 @@ def run_train(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        logged = model.fit([batch] * args.steps, **fit_kw)
+        logged = dict(model.fit([batch] * args.steps, **fit_kw))  # a copy: later fit() calls update the same dict
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))

@@ -189,6 +189,72 @@ clip_preprocess_fused_kernel(const uint8_t *__restrict__ img, int H, int W, int 
     }
 }
 
+// Identity-size variant (H == W == n_px: torchvision's Resize returns the image unchanged and the centre crop is the
+// whole image): only ToTensor + Normalize + the cast remain -- uint8 HWC (or CHW) in, 16-/32-bit CHW out.  This is the
+// CLIP-sized uint8 feed of compress_dataset (150 KB per image over the host link instead of 301 KB of fp16).  One CTA
+// per 8 image rows: 16-byte loads into shared memory, normalisation through the same 3 x 256 IEEE look-up table as the
+// fused kernel above (same bits), 16-byte stores of 8 (16-bit) or 4 (fp32) neighbouring pixels of one channel plane.
+constexpr int kIdRows = 8;
+constexpr int kIdThreads = 256;
+
+template <typename TOut>
+__global__ void __launch_bounds__(kIdThreads)
+clip_normalize_u8_kernel(const uint8_t *__restrict__ img, int n_px, int layout, float m0, float m1, float m2, float s0, float s1,
+                         float s2, TOut *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int kPerVec = 16 / (int)sizeof(TOut);
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.y;
+    const int y0 = blockIdx.x * kIdRows;
+    const int rows = min(kIdRows, n_px - y0);
+    TOut *s_lut = reinterpret_cast<TOut *>(smem);
+    uint8_t *s_in = smem + 3 * 256 * sizeof(TOut);  // [3 planes or 1 HWC slab][rows * n_px (* 3)], 16-byte aligned pieces
+    for (int i = tid; i < 3 * 256; i += kIdThreads) {
+        const int c = i >> 8;
+        const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), std = c == 0 ? s0 : (c == 1 ? s1 : s2);
+        s_lut[i] = from_float<TOut>(__fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.f), mean), std));
+    }
+    const int plane = n_px * n_px;
+    if (layout == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(img + (b * plane + (int64_t)y0 * n_px) * 3);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_in);
+        for (int i = tid; i < (rows * n_px * 3) >> 4; i += kIdThreads) dst[i] = __ldg(src + i);
+    } else {
+        for (int c = 0; c < 3; ++c) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(img + (b * 3 + c) * (int64_t)plane + (int64_t)y0 * n_px);
+            uint4 *dst = reinterpret_cast<uint4 *>(s_in + c * kIdRows * n_px);
+            for (int i = tid; i < (rows * n_px) >> 4; i += kIdThreads) dst[i] = __ldg(src + i);
+        }
+    }
+    __syncthreads();
+    const int vec_per_row = n_px / kPerVec;
+    for (int i = tid; i < 3 * rows * vec_per_row; i += kIdThreads) {
+        const int xv = i % vec_per_row, r = (i / vec_per_row) % rows, c = i / (vec_per_row * rows);
+        alignas(16) TOut v[kPerVec];
+#pragma unroll
+        for (int k = 0; k < kPerVec; ++k) {
+            const int x = xv * kPerVec + k;
+            const int px = layout == 0 ? s_in[(r * n_px + x) * 3 + c] : s_in[c * kIdRows * n_px + r * n_px + x];
+            v[k] = s_lut[(c << 8) + px];
+        }
+        *reinterpret_cast<uint4 *>(out + ((b * 3 + c) * (int64_t)plane + (int64_t)(y0 + r) * n_px) + xv * kPerVec) =
+            *reinterpret_cast<const uint4 *>(v);
+    }
+}
+
+template <typename TOut>
+static int launch_identity(const uint8_t *img, int64_t B, int n_px, int layout, const float *mean3, const float *std3, TOut *out,
+                           cudaStream_t s)
+{
+    const int smem = 3 * 256 * (int)sizeof(TOut) + 3 * kIdRows * n_px;
+    dim3 grid((unsigned)((n_px + kIdRows - 1) / kIdRows), (unsigned)B);
+    clip_normalize_u8_kernel<TOut><<<grid, kIdThreads, smem, s>>>(img, n_px, layout, mean3[0], mean3[1], mean3[2], std3[0], std3[1],
+                                                                std3[2], out);
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
 template <typename TOut>
 static int launch_fused(const uint8_t *img, int64_t B, int H, int W, int layout, const int32_t *coef_h, const int32_t *bounds_h,
                         int ksize_h, const int32_t *coef_v, const int32_t *bounds_v, int ksize_v, const float *mean3,
@@ -223,6 +289,17 @@ extern "C" int ll_clip_preprocess(const uint8_t *img, int64_t B, int H, int W, i
     LL_REQUIRE(B >= 0 && H > 0 && W > 0 && n_px > 0 && ksize_h > 0 && ksize_v > 0 && (layout == 0 || layout == 1), "clip_preprocess: bad arguments");
     if (B == 0) return LL_OK;
     cudaStream_t s = as_stream(stream);
+    // no resize needed (Resize(n_px) leaves an n_px x n_px image unchanged; bicubic coefficients at scale 1 are the
+    // identity, so the general path gives the same bytes): normalise only
+    if (g_preprocess_impl != 1 && H == n_px && W == n_px && n_px % 16 == 0 && n_px * 3 * kIdRows <= 40 * 1024 && B <= 65535 &&
+        (reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        switch (out_dtype) {
+            case LL_F32: return launch_identity<float>(img, B, n_px, layout, mean3, std3, (float *)out, s);
+            case LL_F16: return launch_identity<__half>(img, B, n_px, layout, mean3, std3, (__half *)out, s);
+            case LL_BF16: return launch_identity<__nv_bfloat16>(img, B, n_px, layout, mean3, std3, (__nv_bfloat16 *)out, s);
+            default: return fail(LL_ERR_INVALID, "clip_preprocess: unknown output dtype %d", out_dtype);
+        }
+    }
     // small images: both passes out of shared memory, one CTA per image
     const int out_elem = out_dtype == LL_F32 ? 4 : 2;
     const FusedLayout fl = fused_layout(H, W, n_px, ksize_h, ksize_v, out_elem);

@@ -45,7 +45,8 @@ def test_forward_golden(cuda_device, weights_dir, golden_dir, tag):
     eb.eval()
     out, lik = eb((oeb.process_z_in(z.cpu(), sd["biasing"], sd["scaling"])).to(cuda_device).reshape(-1, 512, 1, 1))
     assert out.shape == (16, 512, 1, 1)
-    assert np.allclose(lik.reshape(16, 512).cpu().numpy(), g[f"{tag}/q_eval"], rtol=1e-4, atol=1e-10)
+    assert lik.requires_grad  # the likelihood is differentiable w.r.t. the bottleneck parameters, as compressai's
+    assert np.allclose(lik.detach().reshape(16, 512).cpu().numpy(), g[f"{tag}/q_eval"], rtol=1e-4, atol=1e-10)
 
 
 def test_backward_vs_oracle_autograd(cuda_device, weights_dir):

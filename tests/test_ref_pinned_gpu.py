@@ -29,11 +29,11 @@ def T(a, dev="cuda"):
     return torch.from_numpy(np.asarray(a)).to(dev)
 
 
-def close_grad(got, want, name, rtol=2e-3):
+def close_grad(got, want, name, rtol=2e-3, atol=0.0):
     got, want = got.detach().double().cpu(), torch.from_numpy(np.asarray(want)).double()
     scale = want.abs().max().item() + 1e-12
     err = (got - want).abs().max().item()
-    assert err < rtol * scale, (name, err, scale)
+    assert err < rtol * scale + atol, (name, err, scale)
 
 
 class replay_noise:
@@ -267,7 +267,9 @@ def test_step_vs_reference(cuda_device, ref, distortion, monkeypatch):
         key = pre + "grad/" + n
         if key in g.files:
             assert p.grad is not None, n
-            close_grad(p.grad, g[key], n, rtol=5e-3)
+            # atol: with is_endToEnd=False and the lossy-Z distortion the encoder's gradient is analytically ZERO
+            # (d/dz of ||z + noise/e^s - z||); the reference's own value is float32 cancellation residue of ~1e-8
+            close_grad(p.grad, g[key], n, rtol=5e-3, atol=1e-6 if n.startswith("p_ZlX.") and distortion == "lossy_Z" else 0.0)
             n_checked += 1
         else:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
