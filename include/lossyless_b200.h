@@ -225,6 +225,10 @@ int ll_vit_set_chunk(ll_vit_t *v, int64_t chunk);
  * GEMM epilogues leave per-row statistics, see ll_gemm_ln).  on = 0 runs the separate LayerNorm kernels. */
 int ll_vit_set_fuse_layernorm(ll_vit_t *v, int on);
 
+/* 1 (default): the patch-embedding GEMM reads the image batch directly (ll_gemm_patch_embed) whenever the input has
+ * the model's 16-bit dtype; 0: always go through the im2col copy (patchify kernel).  A/B and fallback knob. */
+int ll_vit_set_direct_patch(ll_vit_t *v, int on);
+
 /* Per-GEMM device timing for the roofline report: between begin and end every GEMM launch of
  * ll_vit_forward is bracketed by cudaEvents on the launch stream; end synchronises and returns
  * the summed GEMM milliseconds, algorithmic FLOPs (2*M*N*K) and launch count. */
@@ -264,6 +268,14 @@ int ll_gemm(const void *A, const void *W, const float *bias, const void *residua
 int ll_gemm_ln(const void *A, const void *W, const float *bias, const void *residual, void *D,
                int64_t M, int N, int K, int dtype, int act, const void *row_stats_in,
                int stats_in_parts, void *row_stats_out, int stat_width, ll_stream_t stream);
+/* Patch embedding without im2col (CLIP conv1: 3 -> width, kernel = stride = patch, no bias; clip/model.py
+ * VisionTransformer.conv1, reached from hub/compressor.py:93): D[n * 64, N] = patches(x) @ W[N, 3 patch^2]^T with the A
+ * operand TMA-loaded straight from the image batch x [n, 3, res, res] (16-bit `dtype`) through a 5-D tensor map.
+ * Needs patch == 32 and res / patch <= 8.  Every image owns 64 rows of D: row gy * 8 + gx holds patch (gy, gx); the
+ * padding rows (gy or gx >= res / patch) are zero. */
+int ll_gemm_patch_embed(const void *x, const void *W, void *D, int64_t n_images, int N, int res,
+                        int patch, int dtype, ll_stream_t stream);
+
 /* D[Mo, No] = A[Kt, Mo]^T @ B[Kt, No] on the same tcgen05 kernel with MN-major operand descriptors: the
  * weight-gradient contraction dW = dY^T X of a linear layer (torch autograd through nn.Linear in the reference's
  * unfrozen CLIP tower, lossyless/architectures.py:351-376) taken straight from the row-major activations and

@@ -84,6 +84,8 @@ _SIGNATURES = {
     "ll_gemm": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "ll_clip_preprocess_set_impl": (c_int, [c_int]),
     "ll_gemm_tn": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "ll_gemm_patch_embed": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "ll_vit_set_direct_patch": (c_int, [_P, c_int]),
     "ll_gemm_ln": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
     "ll_gemm_set_tile_n": (c_int, [c_int]),
     "ll_gemm_set_cta_pair": (c_int, [c_int]),

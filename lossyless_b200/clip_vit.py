@@ -199,6 +199,11 @@ class VisionTransformer(nn.Module):
         nat = self._native or self._build_native()
         N.call("ll_vit_set_fuse_layernorm", nat["handle"], int(bool(on)))
 
+    def set_direct_patch(self, on):
+        """Patch-embedding GEMM reads the image batch through a 5-D TMA map (default) or an im2col copy (A/B knob)."""
+        nat = self._native or self._build_native()
+        N.call("ll_vit_set_direct_patch", nat["handle"], int(bool(on)))
+
     def launches(self, batch):
         nat = self._native or self._build_native()
         return int(N.load().ll_vit_launches(nat["handle"], int(batch)))

@@ -26,20 +26,37 @@ __device__ constexpr int kMOff[4] = {kM0, kM1, kM2, kM3};
 __device__ constexpr int kBOff[4] = {kB0, kB1, kB2, kB3};
 __device__ constexpr int kFOff[4] = {kF0, kF1, kF2, kF3};
 
-// tanh and sigmoid on two MUFU operations each (ex2.approx: relative error 2^-22; approximate division:
-// 2 ulp): absolute error <= ~2e-7, i.e. at the rounding level of the float32 activations they feed.  The
-// full-precision libdevice versions cost ~25 instructions apiece and made the kernel 3x slower; the per-
-// element budget is 24 tanh + 2 sigmoid + 1 log, so these two functions ARE the kernel.
+// tanh and sigmoid from ex2.approx and ONE approximate reciprocal per group of three (relative error of either MUFU
+// operation 2^-22): the three gated units of a layer share a reciprocal -- 1/(d0 d1 d2), then back to 1/d_j with four
+// multiplications -- so a layer costs 3 EX2 + 1 RCP = 4 MUFU operations instead of 6, and a likelihood 36 instead of 53
+// (the kernel is bound by the quarter-rate special-function pipe: 24 tanh + 2 sigmoid + 1 log per element, DESIGN.md
+// 4.4).  Absolute error <= ~3e-7, the rounding level of the float32 activations they feed.  The full-precision
+// libdevice versions cost ~25 instructions apiece and made the kernel 3x slower.
 __device__ __forceinline__ float ex2_approx(float x)
 {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float tanh_fast(float a)
+__device__ __forceinline__ float rcp_approx(float x)
 {
-    // 1 - 2 / (1 + e^{2a});  e -> inf gives 1, e -> 0 gives -1
-    return 1.f - __fdividef(2.f, 1.f + ex2_approx(a * 2.8853900817779268f));
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// t_j = tanh(a_j) = 1 - 2 / (1 + e^{2 a_j}).  The exponent is clamped at 2^40 (tanh is 1 to 1e-12 there) so that the
+// product of the three denominators stays finite.
+__device__ __forceinline__ void tanh3(const float (&a)[3], float (&t)[3])
+{
+    float d[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) d[j] = 1.f + ex2_approx(fminf(a[j] * 2.8853900817779268f, 40.f));
+    const float p01 = d[0] * d[1];
+    const float r = rcp_approx(p01 * d[2]);
+    const float r01 = r * d[2];
+    t[0] = fmaf(-2.f, r01 * d[1], 1.f);
+    t[1] = fmaf(-2.f, r01 * d[0], 1.f);
+    t[2] = fmaf(-2.f, r * p01, 1.f);
 }
 
 // logits_cumulative for one scalar; keeps gated activations g[k][j] and tanh values t[k][j]
@@ -50,29 +67,39 @@ struct Trace {
 
 __device__ __forceinline__ float logits_fwd(const float (&P)[kNP], float v, Trace &tr)
 {
+    float a[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const float a = fmaf(P[kM0 + j], v, P[kB0 + j]);
-        const float t = tanh_fast(a);
-        tr.t[0][j] = t;
-        tr.g[0][j] = fmaf(P[kF0 + j], t, a);
-    }
+    for (int j = 0; j < 3; ++j) a[j] = fmaf(P[kM0 + j], v, P[kB0 + j]);
+    tanh3(a, tr.t[0]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) tr.g[0][j] = fmaf(P[kF0 + j], tr.t[0][j], a[j]);
 #pragma unroll
     for (int k = 1; k < 4; ++k) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            float a = P[kBOff[k] + j];
+            a[j] = P[kBOff[k] + j];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) a = fmaf(P[kMOff[k] + 3 * j + i], tr.g[k - 1][i], a);
-            const float t = tanh_fast(a);
-            tr.t[k][j] = t;
-            tr.g[k][j] = fmaf(P[kFOff[k] + j], t, a);
+            for (int i = 0; i < 3; ++i) a[j] = fmaf(P[kMOff[k] + 3 * j + i], tr.g[k - 1][i], a[j]);
         }
+        tanh3(a, tr.t[k]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) tr.g[k][j] = fmaf(P[kFOff[k] + j], tr.t[k][j], a[j]);
     }
     float out = P[kB4];
 #pragma unroll
     for (int i = 0; i < 3; ++i) out = fmaf(P[kM4 + i], tr.g[3][i], out);
     return out;
+}
+
+// sigmoid(x0), sigmoid(x1) with one reciprocal: s_j = 1 / (1 + e^{-x_j}); exponents clamped at 2^60 (sigmoid < 1e-18,
+// far below the likelihood bound) so that the product of the two denominators stays finite
+__device__ __forceinline__ void sigmoid2(float x0, float x1, float &s0, float &s1)
+{
+    const float d0 = 1.f + ex2_approx(fminf(-1.4426950408889634f * x0, 60.f));
+    const float d1 = 1.f + ex2_approx(fminf(-1.4426950408889634f * x1, 60.f));
+    const float r = rcp_approx(d0 * d1);
+    s0 = r * d1;
+    s1 = r * d0;
 }
 
 // accumulates d(out)/d(params) * gl into G and returns d(out)/dv * gl
@@ -119,8 +146,6 @@ __device__ __forceinline__ float logits_bwd(const float (&P)[kNP], float v, cons
     return gv;
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + ex2_approx(-1.4426950408889634f * x)); }
-
 __global__ void eb_pack_params_kernel(const float *m0, const float *m1, const float *m2, const float *m3, const float *m4,
                                       const float *b0, const float *b1, const float *b2, const float *b3, const float *b4,
                                       const float *f0, const float *f1, const float *f2, const float *f3, int C,
@@ -162,30 +187,48 @@ eb_forward_kernel(const T *__restrict__ z, int64_t rows, int C, int rows_per_cta
     const float b = bias ? bias[cc] : 0.f, es = exp_scale ? exp_scale[cc] : 1.f, med = medians[cc];
     const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
     const int64_t r1 = min(rows, r0 + rows_per_cta);
-    for (int64_t r = r0; r < r1; ++r) {
-        const int64_t idx = r * C + cc;
-        float x = to_float<T>(z[idx]);
-        if (bias) x = __fmul_rn(__fadd_rn(x, b), es);  // process_z_in
-        float v;
-        if (noise)
-            v = x + noise[idx];
-        else
-            v = __fadd_rn(rintf(__fsub_rn(x, med)), med);  // quantize "dequantize"
+    // two rows per iteration: four independent logits chains (lower / upper of each row) in flight per thread
+    for (int64_t r = r0; r < r1; r += 2) {
+        const bool two = r + 1 < r1;
+        const int64_t idx0 = r * C + cc, idx1 = two ? idx0 + C : idx0;
+        float x[2] = {to_float<T>(z[idx0]), to_float<T>(z[idx1])};
+        float nz[2] = {0.f, 0.f};
+        if (noise) nz[0] = noise[idx0], nz[1] = noise[idx1];
+        float v[2], nl[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (bias) x[u] = __fmul_rn(__fadd_rn(x[u], b), es);  // process_z_in
+            v[u] = noise ? x[u] + nz[u] : __fadd_rn(rintf(__fsub_rn(x[u], med)), med);  // quantize "noise" / "dequantize"
+        }
         Trace tr;
-        const float lower = logits_fwd(P, v - 0.5f, tr);
-        const float upper = logits_fwd(P, v + 0.5f, tr);
-        const float sum = lower + upper;
-        const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
-        const float lik = fabsf(sigmoidf_(sgn * upper) - sigmoidf_(sgn * lower));
-        const float q = fmaxf(lik, bound);  // LowerBound
-        float nl = live ? -logf(q) : 0.f;
-        if (live) {
-            z_hat[idx] = bias ? __fsub_rn(__fdiv_rn(v, es), b) : v;  // process_z_out
-            if (q_out) q_out[idx] = q;
+        float lower[2], upper[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            lower[u] = logits_fwd(P, v[u] - 0.5f, tr);
+            upper[u] = logits_fwd(P, v[u] + 0.5f, tr);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const float sum = lower[u] + upper[u];
+            const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
+            float su, sl;
+            sigmoid2(sgn * upper[u], sgn * lower[u], su, sl);
+            const float lik = fabsf(su - sl);
+            const float q = fmaxf(lik, bound);  // LowerBound
+            nl[u] = live && (u == 0 || two) ? -__logf(q) : 0.f;
+            if (live && (u == 0 || two)) {
+                const int64_t idx = u ? idx1 : idx0;
+                z_hat[idx] = bias ? __fsub_rn(__fdiv_rn(v[u], es), b) : v[u];  // process_z_out
+                if (q_out) q_out[idx] = q;
+            }
         }
         if (rates) {
-            nl = warp_sum(nl);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&rates[r], nl);
+            nl[0] = warp_sum(nl[0]);
+            nl[1] = warp_sum(nl[1]);
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&rates[r], nl[0]);
+                if (two) atomicAdd(&rates[r + 1], nl[1]);
+            }
         }
     }
 }
@@ -224,7 +267,8 @@ eb_backward_kernel(const T *__restrict__ z, int64_t rows, int C, int rows_per_ct
         const float upper = logits_fwd(P, v + 0.5f, tru);
         const float sum = lower + upper;
         const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
-        const float su = sigmoidf_(sgn * upper), sl = sigmoidf_(sgn * lower);
+        float su, sl;
+        sigmoid2(sgn * upper, sgn * lower, su, sl);
         const float diff = su - sl;
         const float lik = fabsf(diff);
         const float q = fmaxf(lik, bound);
@@ -263,22 +307,33 @@ eb_backward_kernel(const T *__restrict__ z, int64_t rows, int C, int rows_per_ct
     }
 }
 
-static int eb_grid(int64_t rows, int C, dim3 &grid, int &rows_per_cta)
+// One wave: `per_sm` = the kernel's resident CTAs per SM (occupancy query), so that the grid is 148 x per_sm CTAs and
+// no SM waits for a second, partially filled wave; at least 8 rows per slab to amortise the parameter load.
+static int eb_grid(int64_t rows, int C, int per_sm, dim3 &grid, int &rows_per_cta)
 {
     const int cx = (C + kEbThreads - 1) / kEbThreads;
-    // enough row slabs for ~4 CTAs per SM, at least 8 rows per slab to amortise the parameter load
-    int64_t slabs = (4LL * num_sms() + cx - 1) / cx;
+    int64_t slabs = ((int64_t)per_sm * num_sms()) / cx;
+    if (slabs < 1) slabs = 1;
     int64_t rpc = (rows + slabs - 1) / slabs;
+    rpc = (rpc + 1) & ~(int64_t)1;  // the forward kernel walks row pairs
     if (rpc < 8) rpc = 8;
     slabs = (rows + rpc - 1) / rpc;
     if (slabs > 65535) {
         slabs = 65535;
-        rpc = (rows + slabs - 1) / slabs;
+        rpc = ((rows + slabs - 1) / slabs + 1) & ~(int64_t)1;
         slabs = (rows + rpc - 1) / rpc;
     }
     rows_per_cta = (int)rpc;
     grid = dim3((unsigned)cx, (unsigned)slabs, 1);
     return LL_OK;
+}
+
+template <typename K>
+static int resident_ctas(K kernel)
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kEbThreads, 0) != cudaSuccess || n < 1) n = 4;
+    return n;
 }
 
 }  // namespace ll
@@ -306,7 +361,8 @@ extern "C" int ll_eb_forward(const void *z, int z_dtype, int64_t rows, int C, co
     if (rows == 0) return LL_OK;
     dim3 grid;
     int rpc;
-    eb_grid(rows, C, grid, rpc);
+    static const int per_sm = resident_ctas(eb_forward_kernel<float>);
+    eb_grid(rows, C, per_sm, grid, rpc);
     cudaStream_t s = as_stream(stream);
     switch (z_dtype) {
         case LL_F32: eb_forward_kernel<float><<<grid, kEbThreads, 0, s>>>((const float *)z, rows, C, rpc, noise, bias, exp_scale, medians, packed, bound, z_hat, q, rates); break;
@@ -332,7 +388,8 @@ extern "C" int ll_eb_backward(const void *z, int z_dtype, int64_t rows, int C, c
     if (rows == 0) return LL_OK;
     dim3 grid;
     int rpc;
-    eb_grid(rows, C, grid, rpc);
+    static const int per_sm = resident_ctas(eb_backward_kernel<float>);
+    eb_grid(rows, C, per_sm, grid, rpc);
     cudaStream_t s = as_stream(stream);
     switch (z_dtype) {
         case LL_F32: eb_backward_kernel<float><<<grid, kEbThreads, 0, s>>>((const float *)z, rows, C, rpc, noise, bias, exp_scale, medians, packed, bound, g_rates, g_q, g_zhat, gz, gparam, g_bias, g_exp_scale); break;

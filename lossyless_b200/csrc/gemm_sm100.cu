@@ -204,6 +204,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int num_tiles = num_m * num_n;
     const int num_kb = K / kBK;
     const bool tn = (act & 0x2000) != 0;  // both operands MN-major (transposed): D = A^T B
+    // patch-embedding mode: A is the image batch itself (5-D map); bits 16.. of `act` hold the K blocks per channel
+    const bool patch_mode = (act & 0x8000) != 0;
+    const int kb_per_channel = act >> 16;
 
     if (warp == kProducerWarp) {
         // ------------------------------------------------------------ TMA producer
@@ -232,6 +235,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                 ptx::tma_load_2d(sm_a + stage * kABytes + h * 8192, &tmap_a, &full_bar[stage], m0 + 64 * h, kb * kBK);
                             for (int h = 0; h < S::kBRows / 64; ++h)
                                 ptx::tma_load_2d(sm_b + stage * S::kBBytes + h * 8192, &tmap_w, &full_bar[stage], n0 + 64 * h, kb * kBK);
+                        }
+                    } else if (patch_mode) {
+                        // im2col-free patch embedding: this CTA's 128 A rows are the 8 x 8 (padded) patch grids of two
+                        // images; K block kb = pixel rows [py0, py0 + 2) of channel ch of every patch.  Box (fastest
+                        // first) [32 px][2 py][8 gx][8 gy][1 image-channel] lands as 64 rows x 128 B, K-major.
+                        const int ch = kb / kb_per_channel, py0 = (kb % kb_per_channel) * 2;
+                        const int img = m0 / kPatchRowsPerImage;
+                        if constexpr (kCtas == 2) {
+                            const uint32_t lead_bar = ptx::map_to_cta(&full_bar[stage], 0);
+                            if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+                            ptx::tma_load_5d_pair(sm_a + stage * kABytes, &tmap_a, lead_bar, 0, py0, 0, 0, 3 * img + ch);
+                            ptx::tma_load_5d_pair(sm_a + stage * kABytes + 8192, &tmap_a, lead_bar, 0, py0, 0, 0, 3 * (img + 1) + ch);
+                            ptx::tma_load_2d_pair(sm_b + stage * S::kBBytes, &tmap_w, lead_bar, kb * kBK, n0);
+                        } else {
+                            ptx::mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+                            ptx::tma_load_5d(sm_a + stage * kABytes, &tmap_a, &full_bar[stage], 0, py0, 0, 0, 3 * img + ch);
+                            ptx::tma_load_5d(sm_a + stage * kABytes + 8192, &tmap_a, &full_bar[stage], 0, py0, 0, 0, 3 * (img + 1) + ch);
+                            ptx::tma_load_2d(sm_b + stage * S::kBBytes, &tmap_w, &full_bar[stage], kb * kBK, n0);
                         }
                     } else if constexpr (kCtas == 2) {
                         // both CTAs' bytes are counted on the LEADER's full barrier, which alone arms it
@@ -564,6 +585,29 @@ int make_tmap_3d(CUtensorMap *map, const void *base, int dtype, int64_t batch, i
     return LL_OK;
 }
 
+// 5-D map over the image batch x [n, 3, R, R] for the patch-embedding A operand.  Dimensions, fastest first:
+// px [P] (stride 1 element), py [P] (stride R), gx [g] (stride P), gy [g] (stride P R), image-channel [3 n] (stride R R);
+// box [P, 2, 8, 8, 1].  The strides are not monotonic (gx < py): TMA only asks for multiples of 16 bytes.
+static int make_tmap_patch5d(CUtensorMap *map, const void *x, int dtype, int64_t n, int res, int patch)
+{
+    const TmapKey key{x, res, patch, n, 0, dtype, 5};
+    if (tmap_cache_get(key, map)) return LL_OK;
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    LL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+    const int g = res / patch;
+    const cuuint64_t dims[5] = {(cuuint64_t)patch, (cuuint64_t)patch, (cuuint64_t)g, (cuuint64_t)g, (cuuint64_t)(3 * n)};
+    const cuuint64_t strides[4] = {(cuuint64_t)res * 2, (cuuint64_t)patch * 2, (cuuint64_t)patch * res * 2, (cuuint64_t)res * res * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)patch, 2, (cuuint32_t)kPatchGridPitch, (cuuint32_t)kPatchGridPitch, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapDataType dt = dtype == LL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = fn(map, dt, 5, const_cast<void *>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled (5-D patch map) failed with CUresult %d", (int)r);
+    tmap_cache_put(key, *map);
+    return LL_OK;
+}
+
 // optional fused-LayerNorm epilogue operands of the next gemm_launch on this thread
 static thread_local const float2 *t_stats_in = nullptr;
 static thread_local float2 *t_stats_out = nullptr;
@@ -704,6 +748,28 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
     return gemm_launch_tmaps(ta, tw, td, tr, bn, ctas, bias, residual != nullptr, M, N, K, dtype, act, stream);
 }
 
+int gemm_patch_launch(const void *x, const void *W, void *D, int64_t n_images, int N, int res, int patch, int dtype, cudaStream_t stream)
+{
+    LL_REQUIRE(x && W && D, "gemm_patch: null pointer");
+    LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "gemm_patch: dtype must be LL_F16 or LL_BF16");
+    LL_REQUIRE(patch == 32 && res % patch == 0 && res / patch <= kPatchGridPitch && n_images > 0 && N % 64 == 0,
+               "gemm_patch: needs patch 32, a patch grid of at most 8 x 8 and N %% 64 == 0 (res=%d patch=%d N=%d)", res, patch, N);
+    LL_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0, "gemm_patch: D must be 16-byte aligned");
+    const int64_t M = n_images * kPatchRowsPerImage;
+    const int K = 3 * patch * patch;
+    int bn = 0, ctas = 1;
+    pick_tile(M, N, bn, ctas);
+    CUtensorMap ta, tw, td;
+    int rc = make_tmap_patch5d(&ta, x, dtype, n_images, res, patch);
+    if (rc != LL_OK) return rc;
+    rc = make_tmap_2d(&tw, W, dtype, N, K, bn / ctas);
+    if (rc != LL_OK) return rc;
+    rc = make_tmap_2d(&td, D, dtype, M, N, 32);
+    if (rc != LL_OK) return rc;
+    const int kb_per_channel = patch * patch / kBK;
+    return gemm_launch_tmaps(ta, tw, td, td, bn, ctas, nullptr, 0, M, N, K, dtype, 0x8000 | (kb_per_channel << 16), stream);
+}
+
 // D[Mo, No] = A[Kt, Mo]^T @ B[Kt, No]: the weight-gradient contraction dW = dY^T X of a linear layer, with the
 // reduction (token) dimension as the ROWS of both operands, i.e. exactly as the activations and their gradients
 // sit in memory.  Same kernel, act bit 0x2000: MN-major shared-memory descriptors, 64 x 64 TMA boxes.
@@ -736,6 +802,12 @@ int gemm_tn_launch(const void *A, const void *B, void *D, int64_t Kt, int Mo, in
 extern "C" int ll_gemm_tn(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, ll_stream_t stream)
 {
     return ll::gemm_tn_launch(A, B, D, Kt, Mo, No, dtype, ll::as_stream(stream));
+}
+
+extern "C" int ll_gemm_patch_embed(const void *x, const void *W, void *D, int64_t n_images, int N, int res, int patch, int dtype,
+                                   ll_stream_t stream)
+{
+    return ll::gemm_patch_launch(x, W, D, n_images, N, res, patch, dtype, ll::as_stream(stream));
 }
 
 extern "C" int ll_gemm_set_tile_n(int bn)

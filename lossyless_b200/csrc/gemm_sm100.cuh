@@ -25,6 +25,14 @@ int make_tmap_2d(CUtensorMap *map, const void *base, int dtype, int64_t rows, in
 // `rows` of one batch entry are zero-filled on load and clipped on store (per-image token tiles).
 int make_tmap_3d(CUtensorMap *map, const void *base, int dtype, int64_t batch, int64_t rows, int64_t cols, int box_rows);
 
+// Patch embedding without im2col: D[n * 64, N] = patches(x) @ W[N, 3 P^2]^T with the A operand TMA-loaded straight from
+// the image batch x [n, 3, R, R] (16-bit, `dtype`) through a 5-D tensor map.  P must be 32 (a 64-wide K block = 2 pixel
+// rows of one channel of a patch) and the patch grid g = R / P at most 8: every image occupies 64 rows of D, row
+// gy * 8 + gx for patch (gy, gx); rows with gy >= g or gx >= g are zero (TMA out-of-bounds fill).
+int gemm_patch_launch(const void *x, const void *W, void *D, int64_t n_images, int N, int res, int patch, int dtype, cudaStream_t stream);
+constexpr int kPatchRowsPerImage = 64;
+constexpr int kPatchGridPitch = 8;
+
 namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,6 +104,24 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
             smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// 5-D tiled TMA load (the patch-embedding operand read straight from the NCHW image batch; SASS: UTMALDG.5D)
+__device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *m, uint64_t *bar, int c0, int c1, int c2, int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(void *smem_dst, const CUtensorMap *m, uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                                 int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *smem_src, int c0, int c1, int c2)

@@ -169,7 +169,7 @@ template <typename T, int kChunks>
 __global__ void __launch_bounds__(256)
 assemble_lnpre_kernel(const T *__restrict__ patch_out, const T *__restrict__ cls, const T *__restrict__ pos,
                       const float *__restrict__ gamma, const float *__restrict__ beta, T *__restrict__ x, int64_t B,
-                      int S, float2 *__restrict__ row_stats)
+                      int S, float2 *__restrict__ row_stats, int grid, int grid_pitch, int rows_per_image)
 {
     pdl_wait();
     pdl_launch_dependents();
@@ -179,7 +179,10 @@ assemble_lnpre_kernel(const T *__restrict__ patch_out, const T *__restrict__ cls
     if (r >= B * S) return;
     const int64_t b = r / S;
     const int s = (int)(r % S);
-    const T *src = s == 0 ? cls : patch_out + (b * (S - 1) + (s - 1)) * width;
+    // patch (gy, gx) of image b sits in row b * rows_per_image + gy * grid_pitch + gx of patch_out: dense
+    // (pitch = grid, rows = grid^2) after the im2col GEMM, 8 x 8-padded after the direct patch-embedding GEMM
+    const int p = s - 1;
+    const T *src = s == 0 ? cls : patch_out + (b * rows_per_image + (p / grid) * grid_pitch + p % grid) * width;
     float v[kChunks][8];
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
@@ -543,14 +546,15 @@ static int launch_layernorm(const T *x, int64_t rows, int64_t row_stride, const 
 }
 
 template <typename T>
-static int launch_assemble(const T *po, const T *cls, const T *pos, const float *g, const float *b, T *x, int64_t B, int S, int width, float2 *st, cudaStream_t s)
+static int launch_assemble(const T *po, const T *cls, const T *pos, const float *g, const float *b, T *x, int64_t B, int S, int width, float2 *st,
+                           int pg, int pitch, int rpi, cudaStream_t s)
 {
     const unsigned grid = (unsigned)((B * S * 32 + 255) / 256);
     switch (width / 256) {
-        case 1: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 1>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st)); break;
-        case 2: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 2>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st)); break;
-        case 3: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 3>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st)); break;
-        case 4: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 4>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st)); break;
+        case 1: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 1>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st, pg, pitch, rpi)); break;
+        case 2: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 2>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st, pg, pitch, rpi)); break;
+        case 3: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 3>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st, pg, pitch, rpi)); break;
+        case 4: LL_CUDA_CHECK(launch_pdl(assemble_lnpre_kernel<T, 4>, dim3(grid), dim3(256), 0, s, po, cls, pos, g, b, x, B, S, st, pg, pitch, rpi)); break;
         default: return fail(LL_ERR_INVALID, "assemble: width %d unsupported", width);
     }
     LL_LAUNCH_CHECK();
@@ -611,6 +615,8 @@ struct ll_vit {
     std::vector<const float *> in_proj_b, out_proj_b, fc_b, cproj_b, ln1_w, ln1_b, ln2_w, ln2_b;
     // fused LayerNorm (default): ln_1 / ln_2 folded into in_proj / c_fc at create time -- library-owned copies
     bool fuse_ln = true;
+    // patch-embedding GEMM reads the images directly (5-D TMA map) instead of an im2col copy, when the input dtype allows
+    bool direct_patch = true;
     std::vector<void *> in_proj_wf, fc_wf;
     std::vector<float *> in_proj_bf, fc_bf;
     std::vector<void *> owned;
@@ -660,8 +666,8 @@ Workspace carve(const ll_vit *v, int64_t n, uint8_t *base)
         off += align256(bytes);
         return p;
     };
-    ws.patch_a = take(Mp * v->kpatch * 2);
-    ws.patch_o = take(Mp * W * 2);
+    ws.patch_a = take(Mp * v->kpatch * 2);  // im2col copy: only touched on the fallback path
+    ws.patch_o = take(std::max(Mp, n * (int64_t)kPatchRowsPerImage) * W * 2);
     ws.x = take(M * W * 2);
     ws.h = take(M * W * 2);
     ws.qkv = take(M * 3 * W * 2);
@@ -697,8 +703,21 @@ int forward_chunk(ll_vit *v, const void *x, int x_dtype, int64_t n, void *z, con
         }
         return timed(0, [&] { return gemm_launch(A, Wt, bias, res, D, m, N, K, dt, act, s); });
     };
-    if ((rc = timed(3, [&] { return launch_patchify<T>(x, x_dtype, (T *)ws.patch_a, n, c.res, c.patch, s); }))) return rc;
-    if ((rc = gemm(ws.patch_a, v->w.conv1_w, nullptr, nullptr, ws.patch_o, Mp, W, v->kpatch, 0))) return rc;
+    // patch embedding: straight from the NCHW batch when it already has the model's 16-bit type (the hub path:
+    // x.to(device).half()), else through the converting im2col copy
+    const bool direct = v->direct_patch && x_dtype == dt && c.patch == 32 && v->grid <= kPatchGridPitch &&
+                        (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (direct) {
+        if (v->profiling) {
+            v->prof_flops += 2.0 * (double)Mp * W * v->kpatch;  // algorithmic FLOPs: the padding rows are not counted
+            v->prof_launches += 1;
+        }
+        if ((rc = timed(0, [&] { return gemm_patch_launch(x, v->w.conv1_w, ws.patch_o, n, W, c.res, c.patch, dt, s); }))) return rc;
+    } else {
+        if ((rc = timed(3, [&] { return launch_patchify<T>(x, x_dtype, (T *)ws.patch_a, n, c.res, c.patch, s); }))) return rc;
+        if ((rc = gemm(ws.patch_a, v->w.conv1_w, nullptr, nullptr, ws.patch_o, Mp, W, v->kpatch, 0))) return rc;
+    }
+    const int pgrid = v->grid, ppitch = direct ? kPatchGridPitch : v->grid, prows = direct ? kPatchRowsPerImage : v->grid * v->grid;
     auto gemm_ln = [&](const void *A, const void *Wt, const float *bias, const void *res, void *D, int64_t m, int N, int K, int act,
                        const void *st_in, int parts_in, void *st_out) {
         if (v->profiling) {
@@ -708,7 +727,7 @@ int forward_chunk(ll_vit *v, const void *x, int x_dtype, int64_t n, void *z, con
         return timed(0, [&] { return gemm_launch_ln(A, Wt, bias, res, D, m, N, K, dt, act, st_in, parts_in, st_out, W, s); });
     };
     float2 *st1 = v->fuse_ln ? (float2 *)ws.stats1 : nullptr;
-    if ((rc = timed(3, [&] { return launch_assemble<T>((const T *)ws.patch_o, (const T *)v->w.class_emb, (const T *)v->w.pos_emb, v->w.ln_pre_w, v->w.ln_pre_b, (T *)ws.x, n, S, W, st1, s); }))) return rc;
+    if ((rc = timed(3, [&] { return launch_assemble<T>((const T *)ws.patch_o, (const T *)v->w.class_emb, (const T *)v->w.pos_emb, v->w.ln_pre_w, v->w.ln_pre_b, (T *)ws.x, n, S, W, st1, pgrid, ppitch, prows, s); }))) return rc;
     if (v->fuse_ln) {
         // x -> [rstd(x) * x W''qkv + b'] -> attention -> out-proj (+x, row stats) -> [rstd * x W''fc + b', GELU]
         //   -> c_proj (+x, row stats): the LayerNorm launches and the h round trip through L2 are gone
@@ -819,6 +838,13 @@ extern "C" int ll_vit_set_fuse_layernorm(ll_vit_t *v, int on)
     return LL_OK;
 }
 
+extern "C" int ll_vit_set_direct_patch(ll_vit_t *v, int on)
+{
+    LL_REQUIRE(v != nullptr, "vit_set_direct_patch: null handle");
+    v->direct_patch = on != 0;
+    return LL_OK;
+}
+
 extern "C" int64_t ll_vit_workspace_bytes(const ll_vit_t *v, int64_t batch)
 {
     if (!v || batch <= 0) return 0;
@@ -830,7 +856,9 @@ extern "C" int64_t ll_vit_launches(const ll_vit_t *v, int64_t batch)
 {
     if (!v || batch <= 0) return 0;
     const int64_t passes = (batch + v->chunk - 1) / v->chunk;
-    return passes * (5 + (v->fuse_ln ? 5 : 7) * (int64_t)v->cfg.layers);
+    // patch embedding (+ im2col copy on the fallback path; the count assumes the 16-bit direct path when it is on),
+    // token assembly + ln_pre, ln_post, proj; per block 4 GEMMs + attention (+ 2 LayerNorms when not fused)
+    return passes * ((v->direct_patch ? 4 : 5) + (v->fuse_ln ? 5 : 7) * (int64_t)v->cfg.layers);
 }
 
 extern "C" int ll_vit_forward(ll_vit_t *v, const void *x, int x_dtype, int64_t batch, void *z, void *workspace,

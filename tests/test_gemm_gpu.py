@@ -205,3 +205,27 @@ def test_gemm_tn_weight_gradient_shape(cuda_device, dtype, Kt, Mo, No, pair):
     assert (D.float() - ref).abs().max().item() < tol * ref.abs().max().item()
     with pytest.raises(N.NativeError):
         N.call("ll_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(D), Kt, Mo + 8, No, N.dtype_code(A), N.stream())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n", [1, 2, 3, 130, 301])
+def test_gemm_patch_embed_reads_images_directly(cuda_device, dtype, n):
+    """ll_gemm_patch_embed: CLIP's conv1 (3 -> 768, kernel = stride = 32, no bias) as a GEMM whose A operand is
+    TMA-loaded from the NCHW batch through a 5-D tensor map.  Row b * 64 + gy * 8 + gx of D is patch (gy, gx) of
+    image b; the padding rows (gy or gx == 7) are zero.  Reference: fp32 conv2d; and bit-equality with the im2col
+    copy + plain GEMM on the same 16-bit operands.  n = 130 / 301 take the CTA-pair kernel, odd n leaves half a tile."""
+    from lossyless_b200 import _native as N
+
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, 3, 224, 224, generator=g).to(dtype).to(cuda_device)
+    W = (torch.randn(768, 3, 32, 32, generator=g) * 0.02).to(dtype).to(cuda_device)
+    D = torch.full((n * 64, 768), float("nan"), dtype=dtype, device=cuda_device)
+    N.call("ll_gemm_patch_embed", N.ptr(x), N.ptr(W), N.ptr(D), n, 768, 224, 32, N.dtype_code(x), N.stream())
+    D = D.reshape(n, 8, 8, 768)
+    ref = torch.nn.functional.conv2d(x.float(), W.float(), stride=32).permute(0, 2, 3, 1)  # [n, 7, 7, 768]
+    got = D[:, :7, :7].float()
+    tol = 2e-2 if dtype == torch.bfloat16 else 3e-3
+    assert (got - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    assert float(D[:, 7].float().abs().max()) == 0.0 and float(D[:, :, 7].float().abs().max()) == 0.0
+    A = x.reshape(n, 3, 7, 32, 7, 32).permute(0, 2, 4, 1, 3, 5).reshape(n * 49, 3072).contiguous()
+    assert torch.equal(_gemm(A, W.reshape(768, 3072)).reshape(n, 7, 7, 768), D[:, :7, :7])

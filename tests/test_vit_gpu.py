@@ -87,7 +87,11 @@ def test_vit_b32_vs_golden(cuda_device, golden_dir):
     xb = x.repeat(200, 1, 1, 1)  # 400 images: two internal passes (378-image limit set above) of 200
     zb = vit(xb).float().cpu().numpy()
     assert np.array_equal(zb[0::2], np.repeat(z[:1], 200, 0)) and np.array_equal(zb[1::2], np.repeat(z[1:], 200, 0))
-    assert vit.launches(400) == 2 * (5 + 5 * 12)  # ln_1 / ln_2 are fused into the GEMMs
+    assert vit.launches(400) == 2 * (4 + 5 * 12)  # ln_1 / ln_2 fused into the GEMMs, patch embedding without im2col
+    vit.set_direct_patch(False)  # the im2col copy + plain GEMM give the same bits as the 5-D TMA operand
+    assert vit.launches(400) == 2 * (5 + 5 * 12)
+    assert np.array_equal(vit(xb).float().cpu().numpy(), zb)
+    vit.set_direct_patch(True)
     vit.set_chunk(64)  # many small passes give the same bits
     assert np.array_equal(vit(xb[:130]).float().cpu().numpy(), zb[:130])
 
@@ -100,7 +104,7 @@ def test_vit_fused_layernorm_matches_separate_kernels(cuda_device, golden_dir):
     z_fused = vit(x).float().cpu().numpy()
     assert np.array_equal(z_fused, vit(x).float().cpu().numpy())  # reproducible
     vit.set_fuse_layernorm(False)
-    assert vit.launches(6) == 5 + 7 * 12
+    assert vit.launches(6) == 4 + 7 * 12
     z_sep = vit(x).float().cpu().numpy()
     for z in (z_fused, z_sep):
         err = np.abs(z[:2] - g["z"])
