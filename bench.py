@@ -413,6 +413,8 @@ def run_encode(args):
     for _ in range(args.warmup):
         packed, offsets, lens = step_device()
     barrier()
+    if not bool(torch.isfinite(comp.clip(X[:64]).float()).all()):
+        raise SystemExit("bench.py: the encoder produced non-finite representations; refusing to time a broken path")
     bits_per_img = 8.0 * (float(offsets[-1].item()) / B)  # incl. the 4-byte length prefix, as README's rate
     total_bytes = int(offsets[-1].item())
 

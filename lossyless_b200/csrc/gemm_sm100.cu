@@ -238,20 +238,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                     } else if (patch_mode) {
                         // im2col-free patch embedding: this CTA's 128 A rows are the 8 x 8 (padded) patch grids of two
-                        // images; K block kb = pixel rows [py0, py0 + 2) of channel ch of every patch.  Box (fastest
-                        // first) [32 px][2 py][8 gx][8 gy][1 image-channel] lands as 64 rows x 128 B, K-major.
+                        // images; K block kb = pixel rows py0, py0 + 1 of channel ch of every patch.  One box (fastest
+                        // first: [32 px][8 gx][1 py][8 gy][1 image-channel]) is 64 rows x 64 B, K-major, SWIZZLE_64B;
+                        // the stage holds [pixel row][image][64 rows x 64 B].
                         const int ch = kb / kb_per_channel, py0 = (kb % kb_per_channel) * 2;
                         const int img = m0 / kPatchRowsPerImage;
+                        uint8_t *dst = sm_a + stage * kABytes;
                         if constexpr (kCtas == 2) {
                             const uint32_t lead_bar = ptx::map_to_cta(&full_bar[stage], 0);
                             if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-                            ptx::tma_load_5d_pair(sm_a + stage * kABytes, &tmap_a, lead_bar, 0, py0, 0, 0, 3 * img + ch);
-                            ptx::tma_load_5d_pair(sm_a + stage * kABytes + 8192, &tmap_a, lead_bar, 0, py0, 0, 0, 3 * (img + 1) + ch);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                ptx::tma_load_5d_pair(dst + q * 4096, &tmap_a, lead_bar, 0, 0, py0 + (q >> 1), 0, 3 * (img + (q & 1)) + ch);
                             ptx::tma_load_2d_pair(sm_b + stage * S::kBBytes, &tmap_w, lead_bar, kb * kBK, n0);
                         } else {
                             ptx::mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-                            ptx::tma_load_5d(sm_a + stage * kABytes, &tmap_a, &full_bar[stage], 0, py0, 0, 0, 3 * img + ch);
-                            ptx::tma_load_5d(sm_a + stage * kABytes + 8192, &tmap_a, &full_bar[stage], 0, py0, 0, 0, 3 * (img + 1) + ch);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                ptx::tma_load_5d(dst + q * 4096, &tmap_a, &full_bar[stage], 0, 0, py0 + (q >> 1), 0, 3 * (img + (q & 1)) + ch);
                             ptx::tma_load_2d(sm_b + stage * S::kBBytes, &tmap_w, &full_bar[stage], kb * kBK, n0);
                         }
                     } else if constexpr (kCtas == 2) {
@@ -295,10 +299,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint32_t id = tn ? (idesc | (1u << 15) | (1u << 16)) : idesc;
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
+                        // patch mode: A is two SWIZZLE_64B sub-blocks of 32 K-columns (8192 B apart), two K = 16 steps each
+                        const uint64_t dak = patch_mode ? ptx::make_kmajor_sw64_desc(addr_a + (k >> 1) * 8192) + 2 * (k & 1) : da + kstep * k;
                         if constexpr (kCtas == 2)
-                            ptx::mma_f16_ss_pair(tmem_d, da + kstep * k, db + kstep * k, id, (kb | k) != 0);
+                            ptx::mma_f16_ss_pair(tmem_d, dak, db + kstep * k, id, (kb | k) != 0);
                         else
-                            ptx::mma_f16_ss(tmem_d, da + kstep * k, db + kstep * k, id, (kb | k) != 0);
+                            ptx::mma_f16_ss(tmem_d, dak, db + kstep * k, id, (kb | k) != 0);
                     }
                     // frees the smem stage (in both CTAs) when the MMAs retire
                     if constexpr (kCtas == 2)
@@ -586,8 +592,8 @@ int make_tmap_3d(CUtensorMap *map, const void *base, int dtype, int64_t batch, i
 }
 
 // 5-D map over the image batch x [n, 3, R, R] for the patch-embedding A operand.  Dimensions, fastest first:
-// px [P] (stride 1 element), py [P] (stride R), gx [g] (stride P), gy [g] (stride P R), image-channel [3 n] (stride R R);
-// box [P, 2, 8, 8, 1].  The strides are not monotonic (gx < py): TMA only asks for multiples of 16 bytes.
+// px [P] (stride 1 element), gx [g] (stride P), py [P] (stride R), gy [g] (stride P R), image-channel [3 n] (stride R R);
+// box [P, 8, 1, 8, 1] = 64 rows (gy, gx) x 64 B, SWIZZLE_64B.
 static int make_tmap_patch5d(CUtensorMap *map, const void *x, int dtype, int64_t n, int res, int patch)
 {
     const TmapKey key{x, res, patch, n, 0, dtype, 5};
@@ -596,13 +602,13 @@ static int make_tmap_patch5d(CUtensorMap *map, const void *x, int dtype, int64_t
     if (fn == nullptr) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     LL_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "TMA base pointer must be 16-byte aligned");
     const int g = res / patch;
-    const cuuint64_t dims[5] = {(cuuint64_t)patch, (cuuint64_t)patch, (cuuint64_t)g, (cuuint64_t)g, (cuuint64_t)(3 * n)};
-    const cuuint64_t strides[4] = {(cuuint64_t)res * 2, (cuuint64_t)patch * 2, (cuuint64_t)patch * res * 2, (cuuint64_t)res * res * 2};
-    const cuuint32_t box[5] = {(cuuint32_t)patch, 2, (cuuint32_t)kPatchGridPitch, (cuuint32_t)kPatchGridPitch, 1};
+    const cuuint64_t dims[5] = {(cuuint64_t)patch, (cuuint64_t)g, (cuuint64_t)patch, (cuuint64_t)g, (cuuint64_t)(3 * n)};
+    const cuuint64_t strides[4] = {(cuuint64_t)patch * 2, (cuuint64_t)res * 2, (cuuint64_t)patch * res * 2, (cuuint64_t)res * res * 2};
+    const cuuint32_t box[5] = {(cuuint32_t)patch, (cuuint32_t)kPatchGridPitch, 1, (cuuint32_t)kPatchGridPitch, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUtensorMapDataType dt = dtype == LL_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUresult r = fn(map, dt, 5, const_cast<void *>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(LL_ERR_CUDA, "cuTensorMapEncodeTiled (5-D patch map) failed with CUresult %d", (int)r);
     tmap_cache_put(key, *map);
     return LL_OK;

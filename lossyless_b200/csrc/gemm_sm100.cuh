@@ -27,8 +27,9 @@ int make_tmap_3d(CUtensorMap *map, const void *base, int dtype, int64_t batch, i
 
 // Patch embedding without im2col: D[n * 64, N] = patches(x) @ W[N, 3 P^2]^T with the A operand TMA-loaded straight from
 // the image batch x [n, 3, R, R] (16-bit, `dtype`) through a 5-D tensor map.  P must be 32 (a 64-wide K block = 2 pixel
-// rows of one channel of a patch) and the patch grid g = R / P at most 8: every image occupies 64 rows of D, row
-// gy * 8 + gx for patch (gy, gx); rows with gy >= g or gx >= g are zero (TMA out-of-bounds fill).
+// rows of one channel of a patch, each a 64-byte SWIZZLE_64B sub-block) and the patch grid g = R / P at most 8: every
+// image occupies 64 rows of D, row gy * 8 + gx for patch (gy, gx); rows with gy >= g or gx >= g are zero (TMA
+// out-of-bounds fill).
 int gemm_patch_launch(const void *x, const void *W, void *D, int64_t n_images, int N, int res, int patch, int dtype, cudaStream_t stream);
 constexpr int kPatchRowsPerImage = 64;
 constexpr int kPatchGridPitch = 8;
@@ -272,6 +273,20 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
     d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset: 8 rows x 128 B
     d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
     d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+// K-major operand tile with rows of 32 x 16-bit (64 B), SWIZZLE_64B as written by TMA; 8-row groups 512 B apart.  Used for
+// the patch-embedding A operand, whose contiguous run in memory is one 32-pixel patch row (a TMA box narrower than the
+// swizzle span would be PADDED to the span in shared memory, so a 64 B run cannot be loaded into a 128 B swizzle row).
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512u >> 4) << 32;              // stride byte offset: 8 rows x 64 B
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
     return d;
 }
 
