@@ -410,7 +410,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         if constexpr (kCtas == 2)
                             ptx::mbar_arrive_cluster(tempty_lead[acc]);  // the leader's MMA thread waits for both CTAs
                         else
-                            ptx::mbar_arrive(&tempty_bar[acc]);
+                            ptx::mbar_arrive_relaxed(&tempty_bar[acc]);
                     }
                 }
                 if (has_residual) {

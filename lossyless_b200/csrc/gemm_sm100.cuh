@@ -171,9 +171,18 @@ __device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
     return r;
 }
+// Arrivals that hand the TMEM accumulator back to the MMA thread.  RELAXED on purpose: the only thing they order are
+// this warp's tcgen05.ld reads, which tcgen05.wait::ld has already completed (and tcgen05.fence::before_thread_sync
+// orders against the arrive); nothing in memory is published.  The .release.cluster form compiled to MEMBAR.ALL.GPU +
+// ERRBAR in front of every arrive and, with the bias loads of the column group in flight, stalled each epilogue warp
+// for hundreds of cycles per group (ncu source view: 20 % of all warp samples of the in-projection GEMM).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // CTA-pair TMA load: data lands in this CTA's shared memory, the transaction bytes are signalled on
 // the mbarrier at `bar_cluster_addr` (the pair leader's)  (SASS: UTMALDG with .2CTA)
