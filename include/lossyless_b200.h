@@ -175,6 +175,59 @@ int ll_eb_backward(const void *z, int z_dtype, int64_t rows, int C, const float 
                    const float *g_q, const float *g_zhat, float *gz, float *gparam, float *g_bias,
                    float *g_exp_scale, ll_stream_t stream);
 
+/* ------------------------------------------------ device: native per-block runner (fine-tuning path) */
+
+/* Parameters of one clip.model.ResidualAttentionBlock: 16-bit matrices as nn.Linear stores them ([out, in]), float32
+ * biases and LayerNorm gains / biases. */
+typedef struct {
+    const void *in_proj_w, *out_proj_w, *fc_w, *cproj_w;
+    const float *in_proj_b, *out_proj_b, *fc_b, *cproj_b, *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+} ll_vit_block_params_t;
+
+/* Where the block's parameter gradients go: the matrices' (16-bit) are overwritten, the vectors' (float32) are
+ * ACCUMULATED into (zero them first). */
+typedef struct {
+    void *in_proj_w, *out_proj_w, *fc_w, *cproj_w;
+    float *in_proj_b, *out_proj_b, *fc_b, *cproj_b, *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+} ll_vit_block_grads_t;
+
+/* 16-bit elements of one block's activation record [h1 | qkv | a | x1 | h2 | u | f | x2] (16 * batch * S * width),
+ * the element offset of x2 (the block's output) inside it, and of the scratch one backward call needs. */
+int64_t ll_vit_block_act_elems(int64_t batch, int S, int width);
+int64_t ll_vit_block_x2_offset_elems(int64_t batch, int S, int width);
+int64_t ll_vit_block_backward_scratch_elems(int64_t batch, int S, int width);
+
+/* Forward of one block, x_in [batch * S, width] -> act (all activations the backward needs; x2 is the output).
+ * replaces clip.model.ResidualAttentionBlock.forward under autograd (lossyless/architectures.py:351-354). */
+int ll_vit_block_forward(const ll_vit_block_params_t *w, const void *x_in, void *act, int64_t batch, int S,
+                         int heads, int width, int dtype, ll_stream_t stream);
+/* Its adjoint: g_x holds dL/dx2 on entry and dL/dx_in on return; parameter gradients go to *g. */
+int ll_vit_block_backward(const ll_vit_block_params_t *w, const void *x_in, const void *act, void *g_x,
+                          void *scratch, const ll_vit_block_grads_t *g, int64_t batch, int S, int heads,
+                          int width, int dtype, ll_stream_t stream);
+
+/* ---------------------------------------------- device: flat-buffer optimiser (fine-tuning path) */
+
+/* Everything the training step does to the unfrozen tower's parameters besides the GEMMs, over ONE flat buffer per
+ * dtype.  replaces, for the encoder's parameters, torch.nn.utils.clip_grad_norm_ (config/main.yaml:113
+ * gradient_clip_val), torch.optim.AdamW (config/featurizer/bottleneck_clip_lossyZ.yaml:37-47) and the autocast
+ * weight casts of `precision: 16` as driven by lossyless/learnable_compressors.py:277-303.  All n are element counts,
+ * multiples of 8; all buffers 16-byte aligned. */
+
+/* floats of scratch ll_sumsq needs */
+int ll_sumsq_scratch_floats(void);
+/* out[0] = (accumulate ? out[0] : 0) + sum_i x[i]^2 ; x in `dtype`; fixed summation order (deterministic) */
+int ll_sumsq(const void *x, int64_t n, int dtype, float *scratch, float *out, int accumulate,
+             ll_stream_t stream);
+/* One AdamW step (torch.optim.AdamW semantics, float32 p / m / v) with the gradient g (g_dtype) multiplied by
+ * grad_scale[0] read from DEVICE memory (clip coefficient / world size; NULL = 1).  If w16 != NULL the updated
+ * parameters are also written there in w16_dtype (the 16-bit compute copy: the next forward's autocast cast). */
+int ll_adamw_flat(float *p, const void *g, int g_dtype, float *m, float *v, void *w16, int w16_dtype,
+                  int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int64_t step, const float *grad_scale, ll_stream_t stream);
+/* dst (fp16 / bf16) = src (float32) */
+int ll_cast_flat(const float *src, void *dst, int dst_dtype, int64_t n, ll_stream_t stream);
+
 /* ------------------------------------------------------------ device: CLIP ViT-B/32 */
 
 typedef struct ll_vit ll_vit_t;

@@ -40,6 +40,15 @@ class VitWeights(ctypes.Structure):
     ]
 
 
+class VitBlockParams(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("in_proj_w", "out_proj_w", "fc_w", "cproj_w", "in_proj_b", "out_proj_b", "fc_b", "cproj_b",
+                                        "ln1_w", "ln1_b", "ln2_w", "ln2_b")]
+
+
+class VitBlockGrads(ctypes.Structure):
+    _fields_ = VitBlockParams._fields_
+
+
 _P = c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -60,6 +69,15 @@ _SIGNATURES = {
     "ll_eb_pack_params": (c_int, [POINTER(_P), POINTER(_P), POINTER(_P), c_int, _P, _P]),
     "ll_eb_forward": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P]),
     "ll_eb_backward": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ll_vit_block_act_elems": (c_int64, [c_int64, c_int, c_int]),
+    "ll_vit_block_x2_offset_elems": (c_int64, [c_int64, c_int, c_int]),
+    "ll_vit_block_backward_scratch_elems": (c_int64, [c_int64, c_int, c_int]),
+    "ll_vit_block_forward": (c_int, [POINTER(VitBlockParams), _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "ll_vit_block_backward": (c_int, [POINTER(VitBlockParams), _P, _P, _P, _P, POINTER(VitBlockGrads), c_int64, c_int, c_int, c_int, c_int, _P]),
+    "ll_sumsq_scratch_floats": (c_int, []),
+    "ll_sumsq": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P]),
+    "ll_adamw_flat": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, _P, _P]),
+    "ll_cast_flat": (c_int, [_P, _P, c_int, c_int64, _P]),
     "ll_vit_create": (c_int, [POINTER(VitConfig), POINTER(VitWeights), POINTER(_P)]),
     "ll_vit_destroy": (None, [_P]),
     "ll_vit_workspace_bytes": (c_int64, [_P, c_int64]),

@@ -21,6 +21,7 @@ parameters.  Two execution paths, no CPU path:
   gradients only.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -98,6 +99,7 @@ class VisionTransformer(nn.Module):
         self._native = None
         self._trainable = False
         self._train_dtype = torch.bfloat16
+        self._flat_enabled, self._flat = False, None
         self._train_cache = None
         self.initialize_parameters()
 
@@ -125,6 +127,8 @@ class VisionTransformer(nn.Module):
     # -- native handle ------------------------------------------------------------------
     def _apply(self, fn, *a, **k):
         self._native = None  # device / dtype changes invalidate the kernel-side views
+        self._flat = None    # ... and give every parameter its own storage again (the flat state is rebuilt lazily)
+        self._train_cache = None
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
@@ -236,12 +240,36 @@ class VisionTransformer(nn.Module):
         for p in self.parameters():
             p.requires_grad_(True)
         self._trainable, self._train_dtype, self._train_cache = True, compute_dtype, None
+        import weakref
+
+        ref = weakref.ref(self)
+        for p in self.parameters():
+            p._ll_vit = ref  # lets helpers.get_optimizer find the tower a parameter belongs to
         return self
+
+    def enable_flat_training_(self, on=True):
+        """Flat master / gradient / moment buffers and native optimiser kernels for this tower (``FlatTrainState``);
+        switched on by ``helpers.FlatAdamW``.  In this mode the backward pass leaves the gradients in the flat buffers
+        (``self.flat_state().grad_view(name)``) instead of returning them to autograd, so ``p.grad`` stays ``None``."""
+        self._flat_enabled = bool(on)
+        if not on:
+            self._flat = None
+        self._train_cache = None
+        return self
+
+    def flat_state(self):
+        if not self._flat_enabled:
+            return None
+        if self._flat is None or self._flat.dt != self._train_dtype or self._flat.device != self.proj.device:
+            self._flat = FlatTrainState(self, self._train_dtype)
+            self._train_cache = None
+        return self._flat
 
     def freeze_(self):
         for p in self.parameters():
             p.requires_grad_(False)
         self._trainable, self._train_cache = False, None
+        self._flat_enabled, self._flat = False, None
         return self
 
     def forward(self, x, out=None):
@@ -282,6 +310,130 @@ class VisionTransformer(nn.Module):
         return z
 
 
+# ------------------------------------------------------------------------------ flat training state
+def _is_matrix(name):
+    """Parameters whose gradient is the output of a weight-gradient GEMM (16-bit, as autocast produces it)."""
+    return name in ("proj", "conv1.weight") or name.endswith("in_proj_weight") or (
+        name.endswith(".weight") and any(k in name for k in ("out_proj", "c_fc", "c_proj")))
+
+
+class FlatTrainState:
+    """Flat storage of an unfrozen tower's training state (``helpers.FlatAdamW`` switches it on).
+
+    Every parameter becomes a view into one of two float32 master buffers -- ``mat`` (the GEMM weights, 85 M elements)
+    and ``vec`` (biases, LayerNorm gains / biases, embeddings) -- laid out in the order the backward pass completes
+    them (proj, block L-1 ... block 0, conv1), each tensor starting on a 16-byte boundary.  Alongside: the 16-bit
+    compute copy of ``mat`` (what autocast would cast per call), the 16-bit gradient buffer the weight-gradient GEMMs
+    write straight into, the float32 gradient buffer of ``vec``, and the AdamW moments.  What this buys over per-tensor
+    torch state: one cast / norm / optimiser launch per buffer instead of ~10 per tensor (150 tensors), gradient
+    all-reduces on contiguous slices with no packing, launched block by block from INSIDE the backward pass, and the
+    next step's 16-bit weights written by the optimiser kernel itself."""
+
+    ALIGN = 8  # elements: 16 bytes in the 16-bit buffers
+
+    def __init__(self, vit, dt):
+        params = dict(vit.named_parameters())
+        dev = vit.proj.device
+        order = ["proj", "ln_post.weight", "ln_post.bias"]
+        self.block_first = {}
+        for i in reversed(range(vit.layers)):
+            p = f"transformer.resblocks.{i}."
+            order += [p + "mlp.c_proj.weight", p + "mlp.c_proj.bias", p + "mlp.c_fc.weight", p + "mlp.c_fc.bias", p + "ln_2.weight",
+                      p + "ln_2.bias", p + "attn.out_proj.weight", p + "attn.out_proj.bias", p + "attn.in_proj_weight",
+                      p + "attn.in_proj_bias", p + "ln_1.weight", p + "ln_1.bias"]
+        order += ["ln_pre.weight", "ln_pre.bias", "positional_embedding", "class_embedding", "conv1.weight"]
+        if set(order) != set(params):
+            raise RuntimeError("FlatTrainState: unexpected parameter set")
+        self.dt, self.device = dt, dev
+        self.slots = {}  # name -> (group, offset, numel, shape)
+        sizes = dict(mat=0, vec=0)
+        for n in order:
+            g = "mat" if _is_matrix(n) else "vec"
+            numel = params[n].numel()
+            self.slots[n] = (g, sizes[g], numel, tuple(params[n].shape))
+            sizes[g] += (numel + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.names = order
+        self.master = {g: torch.zeros(sizes[g], dtype=torch.float32, device=dev) for g in sizes}
+        with torch.no_grad():
+            for n in order:
+                v = self.view(self.master, n)
+                v.copy_(params[n].detach().float())
+                params[n].data = v  # the module's parameters now alias the flat master
+        self.w16 = torch.empty(sizes["mat"], dtype=dt, device=dev)
+        self.grad = dict(mat=torch.zeros(sizes["mat"], dtype=dt, device=dev), vec=torch.zeros(sizes["vec"], dtype=torch.float32, device=dev))
+        self.m = self.v = None  # AdamW moments, created by the first step
+        self.step_count = 0
+        self.cast_versions = None
+        self.scratch = torch.empty(int(N.load().ll_sumsq_scratch_floats()), dtype=torch.float32, device=dev)
+        # all-reduce slices of the matrix gradients in completion order: [proj + last block], one per block, conv1
+        cuts = [0]
+        for i in reversed(range(vit.layers)):
+            g, off, numel, _ = self.slots[f"transformer.resblocks.{i}.attn.in_proj_weight"]
+            cuts.append(off + (numel + self.ALIGN - 1) // self.ALIGN * self.ALIGN)
+        cuts.append(sizes["mat"])
+        self.mat_slices = [(a, b) for a, b in zip(cuts[:-1], cuts[1:])]  # L block slices (the first holds proj too) + conv1
+        self.sync, self.sync_group, self.sync_world, self.pending = False, None, 1, []
+        self.has_grads = False
+
+    def view(self, bufs, name):
+        g, off, numel, shape = self.slots[name]
+        buf = bufs[g] if isinstance(bufs, dict) else bufs
+        return buf[off: off + numel].view(shape)
+
+    def grad_view(self, name):
+        return self.view(self.grad, name)
+
+    def refresh_w16(self, versions):
+        """16-bit compute copy of the matrices: rewritten only if something other than ``adamw_step`` touched the
+        parameters since it was last written."""
+        if self.cast_versions != versions:
+            N.call("ll_cast_flat", N.ptr(self.master["mat"]), N.ptr(self.w16), N._DTYPES[self.dt], self.w16.numel(), N.stream())
+            self.cast_versions = versions
+
+    # -- data-parallel gradient exchange, launched from inside the backward pass ------------------------
+    def begin_backward(self):
+        self.grad["vec"].zero_()  # the bias / LayerNorm kernels accumulate with atomics
+        self.pending = []
+        self.has_grads = True
+
+    def reduce_mat_slice(self, k):
+        """Block k (in completion order) of the matrix gradients is final: start its all-reduce (sum) while the
+        backward pass of the earlier blocks keeps the tensor cores busy."""
+        if self.sync:
+            a, b = self.mat_slices[k]
+            self.pending.append(torch.distributed.all_reduce(self.grad["mat"][a:b], group=self.sync_group, async_op=True))
+
+    def reduce_vec(self):
+        if self.sync:
+            self.pending.append(torch.distributed.all_reduce(self.grad["vec"], group=self.sync_group, async_op=True))
+
+    def wait_reductions(self):
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+
+    # -- optimiser ----------------------------------------------------------------------------------------
+    def sumsq(self, out):
+        """out[0] = |grad|^2 over both buffers (before the 1 / world scaling)."""
+        N.call("ll_sumsq", N.ptr(self.grad["mat"]), self.grad["mat"].numel(), N._DTYPES[self.dt], N.ptr(self.scratch), N.ptr(out), 0, N.stream())
+        N.call("ll_sumsq", N.ptr(self.grad["vec"]), self.grad["vec"].numel(), N.LL_F32, N.ptr(self.scratch), N.ptr(out), 1, N.stream())
+        return out
+
+    def adamw_step(self, lr, betas, eps, weight_decay, grad_scale=None):
+        if self.m is None:
+            self.m = {g: torch.zeros_like(self.master[g]) for g in self.master}
+            self.v = {g: torch.zeros_like(self.master[g]) for g in self.master}
+        self.step_count += 1
+        sc = N.ptr(grad_scale) if grad_scale is not None else None
+        N.call("ll_adamw_flat", N.ptr(self.master["mat"]), N.ptr(self.grad["mat"]), N._DTYPES[self.dt], N.ptr(self.m["mat"]), N.ptr(self.v["mat"]),
+               N.ptr(self.w16), N._DTYPES[self.dt], self.master["mat"].numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
+               float(weight_decay), self.step_count, sc, N.stream())
+        N.call("ll_adamw_flat", N.ptr(self.master["vec"]), N.ptr(self.grad["vec"]), N.LL_F32, N.ptr(self.m["vec"]), N.ptr(self.v["vec"]),
+               None, N.LL_BF16, self.master["vec"].numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
+               float(weight_decay), self.step_count, sc, N.stream())
+        self.has_grads = False
+
+
 # ------------------------------------------------------------------------------ fine-tuning path
 def _gemm(A, W, bias=None, residual=None, act=0):
     """D[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual) on the tcgen05 GEMM; 16-bit operands."""
@@ -313,20 +465,23 @@ def _transpose_pad(t):
 WGRAD_IMPL = "tn"
 
 
-def _wgrad(gy, x):
-    """dW [N, K] = gy[M, N]^T @ x[M, K] (16-bit result, as autocast produces it)."""
+def _wgrad(gy, x, out=None):
+    """dW [N, K] = gy[M, N]^T @ x[M, K] (16-bit result, as autocast produces it); ``out`` = where to put it (a view
+    of the flat gradient buffer)."""
     if WGRAD_IMPL == "tn":
-        D = torch.empty((gy.shape[1], x.shape[1]), dtype=gy.dtype, device=gy.device)
+        D = out if out is not None else torch.empty((gy.shape[1], x.shape[1]), dtype=gy.dtype, device=gy.device)
         N.call("ll_gemm_tn", N.ptr(gy), N.ptr(x), N.ptr(D), gy.shape[0], gy.shape[1], x.shape[1], N.dtype_code(gy), N.stream())
         return D
-    return _gemm(_transpose_pad(gy), _transpose_pad(x))
+    D = _gemm(_transpose_pad(gy), _transpose_pad(x))
+    return D if out is None else out.copy_(D)
 
 
-def _wgrad_bias(gy, x):
+def _wgrad_bias(gy, x, out_w=None, out_b=None):
     """(dW, db): the weight gradient as above and db = column sums of gy (float32); on the transposing path the
-    sums are taken while gy is being transposed so that it is read once."""
-    if WGRAD_IMPL == "tn":
-        return _wgrad(gy, x), _colsum(gy)
+    sums are taken while gy is being transposed so that it is read once.  ``out_w`` / ``out_b``: destinations in the
+    flat gradient buffers (``out_b`` is accumulated into: it must be zero on entry)."""
+    if WGRAD_IMPL == "tn" or out_w is not None:
+        return _wgrad(gy, x, out_w), _colsum(gy, out_b)
     R, C = gy.shape
     Rp = (R + 63) // 64 * 64
     gyt = torch.empty((C, Rp), dtype=gy.dtype, device=gy.device)
@@ -335,19 +490,37 @@ def _wgrad_bias(gy, x):
     return _gemm(gyt, _transpose_pad(x)), db
 
 
-def _colsum(t):
-    out = torch.zeros(t.shape[1], dtype=torch.float32, device=t.device)
+def _colsum(t, out=None):
+    if out is None:
+        out = torch.zeros(t.shape[1], dtype=torch.float32, device=t.device)
     N.call("ll_colsum", N.ptr(t), t.shape[0], t.shape[1], N.dtype_code(t), N.ptr(out), N.stream())
     return out
 
 
-def _ln_backward(x, g_h, gamma, g_res=None):
+def _ln_backward(x, g_h, gamma, g_res=None, out_w=None, out_b=None):
     g_x = torch.empty_like(x)
-    g_w = torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
-    g_b = torch.zeros_like(g_w)
+    g_w = out_w if out_w is not None else torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
+    g_b = out_b if out_b is not None else torch.zeros(x.shape[1], dtype=torch.float32, device=x.device)
     N.call("ll_layernorm_backward", N.ptr(x), N.ptr(g_h), N.ptr(gamma), N.ptr(g_res), N.ptr(g_x), N.ptr(g_w), N.ptr(g_b),
            x.shape[0], x.shape[1], N.dtype_code(x), N.stream())
     return g_x, g_w, g_b
+
+
+# Native per-block runner (csrc/vit_train_runner.cu): one call per block and direction instead of ~13 / ~26 Python-issued
+# launches.  False = the Python-sequenced path (kept as a cross-check in the tests and for A/B runs).
+NATIVE_BLOCKS = os.environ.get("LL_NATIVE_BLOCKS", "1") != "0"
+
+_BLOCK_FIELDS = (("in_proj_w", "attn.in_proj_weight"), ("out_proj_w", "attn.out_proj.weight"), ("fc_w", "mlp.c_fc.weight"),
+                 ("cproj_w", "mlp.c_proj.weight"), ("in_proj_b", "attn.in_proj_bias"), ("out_proj_b", "attn.out_proj.bias"),
+                 ("fc_b", "mlp.c_fc.bias"), ("cproj_b", "mlp.c_proj.bias"), ("ln1_w", "ln_1.weight"), ("ln1_b", "ln_1.bias"),
+                 ("ln2_w", "ln_2.weight"), ("ln2_b", "ln_2.bias"))
+
+
+def _block_struct(cls, tensors, i):
+    """ctypes struct of block i's parameter (or gradient) pointers from a name -> tensor mapping / function."""
+    p = f"transformer.resblocks.{i}."
+    get = tensors if callable(tensors) else tensors.__getitem__
+    return cls(**{field: get(p + name).data_ptr() for field, name in _BLOCK_FIELDS})
 
 
 class _VitTrainFn(torch.autograd.Function):
@@ -374,7 +547,21 @@ class _VitTrainFn(torch.autograd.Function):
         tok = (torch.cat([w["class_embedding"].expand(B, 1, Wd), patch.view(B, g * g, Wd)], 1) + w["positional_embedding"]).reshape(M, Wd)
         xs = _ln(tok, w["ln_pre.weight"], w["ln_pre.bias"])
         saved = []
-        for i in range(vit.layers):
+        if NATIVE_BLOCKS:
+            blocks = w.get("_blocks")
+            if blocks is None:
+                blocks = w["_blocks"] = [_block_struct(N.VitBlockParams, w, i) for i in range(vit.layers)]
+            act_elems = int(N.load().ll_vit_block_act_elems(B, S, Wd))
+            x2_off = int(N.load().ll_vit_block_x2_offset_elems(B, S, Wd))
+            arena = torch.empty((vit.layers, act_elems), dtype=dt, device=x.device)  # every block's activation record
+            x_in, code = xs, N.dtype_code(xs)
+            for i in range(vit.layers):
+                N.call("ll_vit_block_forward", ctypes.byref(blocks[i]), N.ptr(x_in), N.ptr(arena[i]), B, S, vit.heads, Wd, code, N.stream())
+                saved.append(x_in)
+                x_in = arena[i, x2_off: x2_off + M * Wd].view(M, Wd)
+            saved.append(arena)
+            xs = x_in
+        for i in range(vit.layers if not NATIVE_BLOCKS else 0):
             p = f"transformer.resblocks.{i}."
             h1 = _ln(xs, w[p + "ln_1.weight"], w[p + "ln_1.bias"])
             qkv = _gemm(h1, w[p + "attn.in_proj_weight"], w[p + "attn.in_proj_bias"])
@@ -392,7 +579,7 @@ class _VitTrainFn(torch.autograd.Function):
         hc = _ln(xc, w["ln_post.weight"], w["ln_post.bias"])
         z = _gemm(hc, w["proj_t"])
         ctx.vit, ctx.names, ctx.w = vit, names, w
-        ctx.state = dict(a_patch=a_patch, tok=tok, saved=saved, xc=xc, hc=hc, B=B, S=S, M=M)
+        ctx.state = dict(a_patch=a_patch, tok=tok, saved=saved, xc=xc, hc=hc, B=B, S=S, M=M, native=NATIVE_BLOCKS)
         ctx.needs = [p.requires_grad for p in params]
         return z.float()
 
@@ -402,65 +589,117 @@ class _VitTrainFn(torch.autograd.Function):
         dt = vit._train_dtype
         B, S, M, Wd = st["B"], st["S"], st["M"], vit.width
         dev = g_z.device
+        # flat mode: every gradient is written where it will be all-reduced and consumed by the optimiser kernel
+        # (16-bit for the GEMM-produced ones, float32 for the vectors); otherwise collected and returned to autograd
+        flat = vit.flat_state() if all(ctx.needs) else None
         G = {}
+        if flat is not None:
+            flat.begin_backward()
+            dst = flat.grad_view
+        else:
+            dst = lambda name: None  # noqa: E731
         gz = g_z.to(dt).contiguous()
         # z = hc @ proj
         g_hc = _gemm(gz, w["proj"])                      # [B, 768] = gz [B,512] @ proj[768,512]^T
-        G["proj"] = _wgrad(st["hc"], gz)                 # [768, 512]
-        g_xc, G["ln_post.weight"], G["ln_post.bias"] = _ln_backward(st["xc"], g_hc, w["ln_post.weight"])
+        G["proj"] = _wgrad(st["hc"], gz, dst("proj"))    # [768, 512]
+        g_xc, G["ln_post.weight"], G["ln_post.bias"] = _ln_backward(st["xc"], g_hc, w["ln_post.weight"], out_w=dst("ln_post.weight"), out_b=dst("ln_post.bias"))
         g_x = torch.zeros((B, S, Wd), dtype=dt, device=dev)
         g_x[:, 0] = g_xc
         g_x = g_x.view(M, Wd)
-        for i in reversed(range(vit.layers)):
+        if st["native"]:
+            blocks, arena = w["_blocks"], st["saved"][vit.layers]
+            scratch = torch.empty(int(N.load().ll_vit_block_backward_scratch_elems(B, S, Wd)), dtype=dt, device=dev)
+            code = N.dtype_code(g_x)
+            for k, i in enumerate(reversed(range(vit.layers))):
+                p = f"transformer.resblocks.{i}."
+                if flat is not None:
+                    grads = _block_struct(N.VitBlockGrads, flat.grad_view, i)
+                else:
+                    for _, name in _BLOCK_FIELDS:
+                        shape = w[p + name].shape
+                        G[p + name] = (torch.empty(shape, dtype=dt, device=dev) if _is_matrix(p + name)
+                                       else torch.zeros(shape, dtype=torch.float32, device=dev))
+                    grads = _block_struct(N.VitBlockGrads, G, i)
+                N.call("ll_vit_block_backward", ctypes.byref(blocks[i]), N.ptr(st["saved"][i]), N.ptr(arena[i]), N.ptr(g_x), N.ptr(scratch),
+                       ctypes.byref(grads), B, S, vit.heads, Wd, code, N.stream())
+                if flat is not None:
+                    flat.reduce_mat_slice(k)  # this block's four weight gradients (and proj, with the last block) are final
+            st["saved"] = None
+        for k, i in enumerate(reversed(range(vit.layers if not st["native"] else 0))):
             p = f"transformer.resblocks.{i}."
             xs, h1, qkv, a, x1, h2, u, f = st["saved"][i]
             wt = vit._train_weights_t(dt, i)
             # x2 = x1 + f @ c_proj^T + b
             g_f = _gemm(g_x, wt["c_proj"])
-            G[p + "mlp.c_proj.weight"], G[p + "mlp.c_proj.bias"] = _wgrad_bias(g_x, f)
+            G[p + "mlp.c_proj.weight"], G[p + "mlp.c_proj.bias"] = _wgrad_bias(g_x, f, dst(p + "mlp.c_proj.weight"), dst(p + "mlp.c_proj.bias"))
             g_u = torch.empty_like(u)
             N.call("ll_quickgelu_backward", N.ptr(u), N.ptr(g_f), N.ptr(g_u), u.numel(), N.dtype_code(u), N.stream())
             del g_f
             g_h2 = _gemm(g_u, wt["c_fc"])
-            G[p + "mlp.c_fc.weight"], G[p + "mlp.c_fc.bias"] = _wgrad_bias(g_u, h2)
+            G[p + "mlp.c_fc.weight"], G[p + "mlp.c_fc.bias"] = _wgrad_bias(g_u, h2, dst(p + "mlp.c_fc.weight"), dst(p + "mlp.c_fc.bias"))
             del g_u
-            g_x1, G[p + "ln_2.weight"], G[p + "ln_2.bias"] = _ln_backward(x1, g_h2, w[p + "ln_2.weight"], g_res=g_x)
+            g_x1, G[p + "ln_2.weight"], G[p + "ln_2.bias"] = _ln_backward(x1, g_h2, w[p + "ln_2.weight"], g_res=g_x, out_w=dst(p + "ln_2.weight"), out_b=dst(p + "ln_2.bias"))
             # x1 = x + a @ out_proj^T + b
             g_a = _gemm(g_x1, wt["out_proj"])
-            G[p + "attn.out_proj.weight"], G[p + "attn.out_proj.bias"] = _wgrad_bias(g_x1, a)
+            G[p + "attn.out_proj.weight"], G[p + "attn.out_proj.bias"] = _wgrad_bias(g_x1, a, dst(p + "attn.out_proj.weight"), dst(p + "attn.out_proj.bias"))
             g_qkv = torch.empty_like(qkv)
             N.call("ll_attention_backward", N.ptr(qkv), N.ptr(g_a), N.ptr(g_qkv), B, S, vit.heads, N.dtype_code(qkv), N.stream())
             g_h1 = _gemm(g_qkv, wt["in_proj"])
-            G[p + "attn.in_proj_weight"], G[p + "attn.in_proj_bias"] = _wgrad_bias(g_qkv, h1)
+            G[p + "attn.in_proj_weight"], G[p + "attn.in_proj_bias"] = _wgrad_bias(g_qkv, h1, dst(p + "attn.in_proj_weight"), dst(p + "attn.in_proj_bias"))
             del g_qkv, g_a
-            g_x, G[p + "ln_1.weight"], G[p + "ln_1.bias"] = _ln_backward(xs, g_h1, w[p + "ln_1.weight"], g_res=g_x1)
+            g_x, G[p + "ln_1.weight"], G[p + "ln_1.bias"] = _ln_backward(xs, g_h1, w[p + "ln_1.weight"], g_res=g_x1, out_w=dst(p + "ln_1.weight"), out_b=dst(p + "ln_1.bias"))
             st["saved"][i] = None
-        g_tok, G["ln_pre.weight"], G["ln_pre.bias"] = _ln_backward(st["tok"], g_x, w["ln_pre.weight"])
+            if flat is not None:
+                flat.reduce_mat_slice(k)  # this block's four weight gradients (and proj, with the last block) are final
+        g_tok, G["ln_pre.weight"], G["ln_pre.bias"] = _ln_backward(st["tok"], g_x, w["ln_pre.weight"], out_w=dst("ln_pre.weight"), out_b=dst("ln_pre.bias"))
         g_tok = g_tok.view(B, S, Wd)
-        G["positional_embedding"] = g_tok.sum(0, dtype=torch.float32)
-        G["class_embedding"] = g_tok[:, 0].sum(0, dtype=torch.float32)
+        if flat is not None:
+            torch.sum(g_tok, 0, dtype=torch.float32, out=dst("positional_embedding"))
+            torch.sum(g_tok[:, 0], 0, dtype=torch.float32, out=dst("class_embedding"))
+        else:
+            G["positional_embedding"] = g_tok.sum(0, dtype=torch.float32)
+            G["class_embedding"] = g_tok[:, 0].sum(0, dtype=torch.float32)
         g_patch = g_tok[:, 1:].reshape(B * (S - 1), Wd).contiguous()
-        G["conv1.weight"] = _wgrad(g_patch, st["a_patch"]).view(vit.conv1.weight.shape)
+        conv_dst = dst("conv1.weight")
+        G["conv1.weight"] = _wgrad(g_patch, st["a_patch"], conv_dst.view(Wd, -1) if conv_dst is not None else None).view(vit.conv1.weight.shape)
         if vit._native is not None:
             vit._native["stale"] = True  # an optimiser step is about to change the parameters
-        grads = tuple(G[n].float() if need else None for n, need in zip(ctx.names, ctx.needs))
         ctx.state = None
+        if flat is not None:
+            flat.reduce_mat_slice(vit.layers)  # conv1
+            flat.reduce_vec()
+            return (None, None, None) + (None,) * len(ctx.names)
+        grads = tuple(G[n].float() if need else None for n, need in zip(ctx.names, ctx.needs))
         return (None, None, None) + grads
 
 
 def _train_weights(self, dt):
     """16-bit compute copies of the float32 master parameters (the autocast casts), rebuilt when an
-    optimiser step bumped a parameter's version.  LayerNorm gains / biases and linear biases stay fp32."""
-    key = (dt, tuple(p._version for p in self.parameters()), self.proj.device)
+    optimiser step bumped a parameter's version.  LayerNorm gains / biases and linear biases stay fp32.
+    Flat mode: the matrices' copies are views of one flat 16-bit buffer that the optimiser kernel itself keeps up to
+    date (``FlatTrainState.adamw_step``), the float32 vectors are the master views themselves -- no per-tensor casts."""
+    flat = self.flat_state()
+    versions = tuple(p._version for p in self.parameters())
+    key = (dt, versions, self.proj.device, flat.step_count if flat is not None else -1)
     if self._train_cache is not None and self._train_cache["key"] == key:
         return self._train_cache["w"]
     w = {}
     with torch.no_grad():
-        for n, p in self.named_parameters():
-            if n.endswith("bias") or "ln_" in n:
-                w[n] = p.detach().float().contiguous()
-            else:
-                w[n] = p.detach().to(dt).contiguous()
+        if flat is not None:
+            flat.refresh_w16(versions)
+            for n in flat.names:
+                if _is_matrix(n):
+                    w[n] = flat.view(flat.w16, n)
+                elif n in ("class_embedding", "positional_embedding"):
+                    w[n] = flat.view(flat.master, n).to(dt)
+                else:
+                    w[n] = flat.view(flat.master, n)
+        else:
+            for n, p in self.named_parameters():
+                if n.endswith("bias") or "ln_" in n:
+                    w[n] = p.detach().float().contiguous()
+                else:
+                    w[n] = p.detach().to(dt).contiguous()
         w["conv1.weight"] = w["conv1.weight"].reshape(self.width, -1)
         w["proj_t"] = w["proj"].t().contiguous()
     self._train_cache = dict(key=key, w=w, wt={})

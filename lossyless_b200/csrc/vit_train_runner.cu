@@ -1,0 +1,123 @@
+// Native per-block runner of the fine-tuning path (sm_100a): ONE call sequences the forward pass of a CLIP
+// ResidualAttentionBlock (keeping the activations its backward needs), and ONE call its hand-written adjoint,
+// instead of ~13 / ~26 Python-issued launches with their tensor allocations in between.  With the flat training state
+// the training step was bound by the HOST (746 launches + torch bookkeeping per 27 ms step, GPU kernels summing to 24 ms):
+// a step is now ~100 host calls.
+//
+// Replaces torch autograd through clip.model.ResidualAttentionBlock.forward (x += attn(ln_1(x)); x += mlp(ln_2(x))) as
+// reached from lossyless/architectures.py:351-354 under lossyless/learnable_compressors.py:277-303.  Every dense
+// contraction (forward, data gradient, weight gradient) is the tcgen05 GEMM of gemm_sm100.cu; the rest are the kernels
+// of vit.cu / vit_train.cu.  The caller (clip_vit._VitTrainFn) owns all memory and launches the data-parallel
+// all-reduce of a block's gradients between two backward calls.
+//
+// Activation record of one block, 16-bit, M = batch * tokens rows each, in this order:
+//   h1 [M,W] ln_1(x) | qkv [M,3W] | a [M,W] attention output | x1 [M,W] | h2 [M,W] ln_2(x1) | u [M,4W] | f [M,4W] QuickGELU(u)
+//   | x2 [M,W] block output
+#include "gemm_sm100.cuh"
+
+using namespace ll;
+
+namespace {
+
+struct ActView {
+    uint8_t *h1, *qkv, *a, *x1, *h2, *u, *f, *x2;
+};
+
+inline ActView act_view(void *act, int64_t M, int W)
+{
+    uint8_t *p = static_cast<uint8_t *>(act);
+    ActView v;
+    const int64_t row = 2;  // bytes per element
+    v.h1 = p, p += M * W * row;
+    v.qkv = p, p += M * 3 * W * row;
+    v.a = p, p += M * W * row;
+    v.x1 = p, p += M * W * row;
+    v.h2 = p, p += M * W * row;
+    v.u = p, p += M * 4 * W * row;
+    v.f = p, p += M * 4 * W * row;
+    v.x2 = p;
+    return v;
+}
+
+}  // namespace
+
+extern "C" int64_t ll_vit_block_act_elems(int64_t batch, int S, int width) { return batch * S * (int64_t)width * 16; }
+
+extern "C" int64_t ll_vit_block_x2_offset_elems(int64_t batch, int S, int width) { return batch * S * (int64_t)width * 15; }
+
+// scratch of one backward call: g_f / g_u [M,4W], g_h2 [M,W], g_x1 [M,W], g_a [M,W], g_qkv [M,3W], g_h1 [M,W], then the four
+// transposed weight copies (12 W^2 elements)
+extern "C" int64_t ll_vit_block_backward_scratch_elems(int64_t batch, int S, int width)
+{
+    return batch * S * (int64_t)width * 11 + 12LL * width * width;
+}
+
+extern "C" int ll_vit_block_forward(const ll_vit_block_params_t *w, const void *x_in, void *act, int64_t batch, int S, int heads,
+                                    int width, int dtype, ll_stream_t stream)
+{
+    LL_REQUIRE(w && x_in && act && batch > 0 && S > 0 && heads > 0 && width > 0, "vit_block_forward: bad arguments");
+    LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "vit_block_forward: dtype must be LL_F16 or LL_BF16");
+    const int64_t M = batch * S;
+    const int W = width;
+    const ActView v = act_view(act, M, W);
+    int rc;
+    if ((rc = ll_layernorm(x_in, M, W, w->ln1_w, w->ln1_b, v.h1, dtype, stream))) return rc;
+    if ((rc = ll_gemm(v.h1, w->in_proj_w, w->in_proj_b, nullptr, v.qkv, M, 3 * W, W, dtype, 0, stream))) return rc;
+    if ((rc = ll_attention(v.qkv, v.a, batch, S, heads, dtype, stream))) return rc;
+    if ((rc = ll_gemm(v.a, w->out_proj_w, w->out_proj_b, x_in, v.x1, M, W, W, dtype, 0, stream))) return rc;
+    if ((rc = ll_layernorm(v.x1, M, W, w->ln2_w, w->ln2_b, v.h2, dtype, stream))) return rc;
+    if ((rc = ll_gemm(v.h2, w->fc_w, w->fc_b, nullptr, v.u, M, 4 * W, W, dtype, 0, stream))) return rc;
+    if ((rc = ll_quickgelu_forward(v.u, v.f, M * 4 * (int64_t)W, dtype, stream))) return rc;
+    if ((rc = ll_gemm(v.f, w->cproj_w, w->cproj_b, v.x1, v.x2, M, W, 4 * W, dtype, 0, stream))) return rc;
+    return LL_OK;
+}
+
+extern "C" int ll_vit_block_backward(const ll_vit_block_params_t *w, const void *x_in, const void *act, void *g_x, void *scratch,
+                                     const ll_vit_block_grads_t *g, int64_t batch, int S, int heads, int width, int dtype,
+                                     ll_stream_t stream)
+{
+    LL_REQUIRE(w && x_in && act && g_x && scratch && g && batch > 0 && S > 0, "vit_block_backward: bad arguments");
+    LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "vit_block_backward: dtype must be LL_F16 or LL_BF16");
+    LL_REQUIRE(width % 64 == 0, "vit_block_backward: width must be a multiple of 64");
+    const int64_t M = batch * S;
+    const int W = width;
+    const ActView v = act_view(const_cast<void *>(act), M, W);
+    uint8_t *p = static_cast<uint8_t *>(scratch);
+    uint8_t *g_u = p;     p += M * 4 * W * 2;  // holds g_f first, g_u in place after the QuickGELU backward
+    uint8_t *g_h2 = p;    p += M * W * 2;
+    uint8_t *g_x1 = p;    p += M * W * 2;
+    uint8_t *g_a = p;     p += M * W * 2;
+    uint8_t *g_qkv = p;   p += M * 3 * W * 2;
+    uint8_t *g_h1 = p;    p += M * W * 2;
+    // transposed 16-bit weight copies: dX = dY @ W is the K-major GEMM D = A Wt^T with Wt = W^T [in, out]
+    uint8_t *cproj_t = p; p += (int64_t)4 * W * W * 2;
+    uint8_t *fc_t = p;    p += (int64_t)4 * W * W * 2;
+    uint8_t *out_t = p;   p += (int64_t)W * W * 2;
+    uint8_t *in_t = p;
+    int rc;
+    // W [out, in] -> Wt [in, out]  (transpose_pad(src [R, C]) -> [C, Rpad]; R = out is a multiple of 64 here)
+    if ((rc = ll_transpose_pad(w->cproj_w, cproj_t, W, 4 * W, W, stream))) return rc;
+    if ((rc = ll_transpose_pad(w->fc_w, fc_t, 4 * W, W, 4 * W, stream))) return rc;
+    if ((rc = ll_transpose_pad(w->out_proj_w, out_t, W, W, W, stream))) return rc;
+    if ((rc = ll_transpose_pad(w->in_proj_w, in_t, 3 * W, W, 3 * W, stream))) return rc;
+    // x2 = x1 + f @ c_proj^T + b
+    if ((rc = ll_gemm(g_x, cproj_t, nullptr, nullptr, g_u, M, 4 * W, W, dtype, 0, stream))) return rc;      // g_f
+    if ((rc = ll_gemm_tn(g_x, v.f, g->cproj_w, M, W, 4 * W, dtype, stream))) return rc;
+    if ((rc = ll_colsum(g_x, M, W, dtype, g->cproj_b, stream))) return rc;
+    if ((rc = ll_quickgelu_backward(v.u, g_u, g_u, M * 4 * (int64_t)W, dtype, stream))) return rc;         // g_u (in place)
+    if ((rc = ll_gemm(g_u, fc_t, nullptr, nullptr, g_h2, M, W, 4 * W, dtype, 0, stream))) return rc;
+    if ((rc = ll_gemm_tn(g_u, v.h2, g->fc_w, M, 4 * W, W, dtype, stream))) return rc;
+    if ((rc = ll_colsum(g_u, M, 4 * W, dtype, g->fc_b, stream))) return rc;
+    if ((rc = ll_layernorm_backward(v.x1, g_h2, w->ln2_w, g_x, g_x1, g->ln2_w, g->ln2_b, M, W, dtype, stream))) return rc;
+    // x1 = x + a @ out_proj^T + b
+    if ((rc = ll_gemm(g_x1, out_t, nullptr, nullptr, g_a, M, W, W, dtype, 0, stream))) return rc;
+    if ((rc = ll_gemm_tn(g_x1, v.a, g->out_proj_w, M, W, W, dtype, stream))) return rc;
+    if ((rc = ll_colsum(g_x1, M, W, dtype, g->out_proj_b, stream))) return rc;
+    if ((rc = ll_attention_backward(v.qkv, g_a, g_qkv, batch, S, heads, dtype, stream))) return rc;
+    if ((rc = ll_gemm(g_qkv, in_t, nullptr, nullptr, g_h1, M, W, 3 * W, dtype, 0, stream))) return rc;
+    if ((rc = ll_gemm_tn(g_qkv, v.h1, g->in_proj_w, M, 3 * W, W, dtype, stream))) return rc;
+    if ((rc = ll_colsum(g_qkv, M, 3 * W, dtype, g->in_proj_b, stream))) return rc;
+    // dL/dx_in = LN1 backward + the residual branch (g_x1); overwrites g_x, whose old value is dead by now
+    if ((rc = ll_layernorm_backward(x_in, g_h1, w->ln1_w, g_x1, g_x, g->ln1_w, g->ln1_b, M, W, dtype, stream))) return rc;
+    return LL_OK;
+}

@@ -582,7 +582,16 @@ def _packed_params(eb, device):
 
 
 def _bound(eb):
-    return float(eb.likelihood_lower_bound.bound.item()) if eb.use_likelihood_bound else 0.0
+    """The LowerBound value as a host float, read back from the (checkpointed) buffer once per buffer version: a
+    `.item()` per call is a stream synchronisation in the middle of every training step."""
+    if not eb.use_likelihood_bound:
+        return 0.0
+    buf = eb.likelihood_lower_bound.bound
+    key = (buf.data_ptr(), buf._version)
+    cache = getattr(eb, "_bound_cache", None)
+    if cache is None or cache[0] != key:
+        cache = eb._bound_cache = (key, float(buf.item()))
+    return cache[1]
 
 
 class _EBRate(torch.autograd.Function):

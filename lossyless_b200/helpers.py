@@ -7,6 +7,8 @@ import time
 from functools import reduce
 from numbers import Number
 
+import os
+
 import torch
 import torch.nn as nn
 from torch.distributions import Distribution, constraints
@@ -121,8 +123,15 @@ class Delta(Distribution):
     arg_constraints = {"loc": constraints.real, "log_density": constraints.real}
     support = constraints.real
 
-    def __init__(self, loc, log_density=0.0, validate_args=None):
-        self.loc, self.log_density = broadcast_all(loc, log_density)
+    def __init__(self, loc, log_density=0.0, validate_args=False):
+        # No argument validation and no host scalar on the way in: torch's default (`validate_args=None` -> check that
+        # loc is real -> `.all()` read back by the host) and `broadcast_all(loc, 0.0)` (a pageable host-to-device copy
+        # of the scalar) each synchronise the stream, once per encoder call and per `.detach()` of the training step.
+        if torch.is_tensor(loc) and isinstance(log_density, Number):
+            self.loc = loc
+            self.log_density = loc.new_full((), float(log_density)).expand(loc.shape)
+        else:
+            self.loc, self.log_density = broadcast_all(loc, log_density)
         batch_shape = torch.Size() if isinstance(loc, Number) else self.loc.size()
         super().__init__(batch_shape, validate_args=validate_args)
 
@@ -201,6 +210,82 @@ class GatherFromGpus(torch.autograd.Function):
 gather_from_gpus = GatherFromGpus.apply
 
 
+class FlatAdamW(torch.optim.AdamW):
+    """``torch.optim.AdamW`` whose share of an unfrozen CLIP tower runs on the flat-buffer kernels (csrc/optim.cu).
+
+    Constructed like AdamW with ALL the parameters of the optimiser (so ``param_groups``, ``lr`` and the schedulers
+    behave as usual).  Parameters that belong to a ``clip_vit.VisionTransformer`` in fine-tuning mode are handled
+    natively: the tower is switched to its flat training state (``FlatTrainState``), whose backward pass leaves the
+    gradients in two flat buffers instead of ``p.grad``; ``step()`` then runs torch's fused AdamW on the remaining
+    parameters (``p.grad is None`` skips the tower's) and ONE native AdamW launch per flat buffer, which also writes
+    next step's 16-bit weights.  ``clip_grad_norm_`` is the global-norm clip over both kinds of gradients, computed on
+    the device (no host synchronisation) and applied to the flat ones through the kernel's ``grad_scale`` operand --
+    together with the 1 / world_size of the data-parallel mean, whose all-reduces (sum) were launched block by block
+    from inside the backward pass."""
+
+    def __init__(self, params, **kwargs):
+        params = list(params)
+        self._towers = []
+        for p in params:
+            ref = getattr(p, "_ll_vit", None)
+            vit = ref() if ref is not None else None
+            if vit is not None and vit._trainable and all(vit is not t for t in self._towers):
+                self._towers.append(vit)
+        super().__init__(params, **kwargs)
+        for vit in self._towers:
+            vit.enable_flat_training_(True)
+        self._grad_scale = None
+
+    def flat_states(self):
+        return [f for f in (vit.flat_state() for vit in self._towers) if f is not None]
+
+    def prepare_backward(self, sync=False, group=None, world=1):
+        """Before ``loss.backward()``: whether (and over which process group) the towers all-reduce their gradient
+        slices from inside the backward pass."""
+        for f in self.flat_states():
+            f.sync, f.sync_group, f.sync_world = bool(sync), group, int(world)
+        self._world = int(world) if sync else 1
+        self._grad_scale = None
+
+    def finish_backward(self):
+        for f in self.flat_states():
+            f.wait_reductions()
+
+    @torch.no_grad()
+    def clip_grad_norm_(self, max_norm):
+        """Global-norm clipping over every gradient of this optimiser; returns the total norm (a device tensor)."""
+        world = getattr(self, "_world", 1)
+        others = [p.grad for g in self.param_groups for p in g["params"] if p.grad is not None]
+        dev = others[0].device if others else self.flat_states()[0].device
+        total = torch.zeros(1, dtype=torch.float32, device=dev)
+        if others:
+            total += torch.stack([n.float() ** 2 for n in torch._foreach_norm(others)]).sum()
+        for f in self.flat_states():
+            if f.has_grads:
+                sq = torch.empty(1, dtype=torch.float32, device=dev)
+                total += f.sumsq(sq) / float(world * world)  # the flat gradients still hold the SUM over ranks
+        norm = total.sqrt()
+        coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+        if others:
+            torch._foreach_mul_(others, coef.reshape(()))
+        self._grad_scale = (coef / float(world)).float().contiguous()
+        return norm
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = super().step(closure)
+        g = self.param_groups[0]
+        world = getattr(self, "_world", 1)
+        scale = self._grad_scale
+        if scale is None and world > 1:
+            scale = torch.full((1,), 1.0 / world, dtype=torch.float32, device=self.flat_states()[0].device)
+        for f in self.flat_states():
+            if f.has_grads:
+                f.adamw_step(g["lr"], g["betas"], g["eps"], g["weight_decay"], scale)
+        self._grad_scale = None
+        return loss
+
+
 def get_optimizer(parameters, mode, **kwargs):
     Optimizer = getattr(torch.optim, mode)
     kwargs = dict(kwargs)
@@ -210,6 +295,9 @@ def get_optimizer(parameters, mode, **kwargs):
     if mode in ("Adam", "AdamW", "SGD") and "fused" not in kwargs and "foreach" not in kwargs and parameters \
             and all(p.is_cuda and torch.is_floating_point(p) for p in parameters):
         kwargs["fused"] = True  # same update rule, one multi-tensor kernel instead of ~10 per step
+    if mode == "AdamW" and not kwargs.get("amsgrad", False) and os.environ.get("LL_FLAT_OPTIMIZER", "1") != "0" \
+            and any(getattr(p, "_ll_vit", None) is not None for p in parameters):
+        return FlatAdamW(parameters, **kwargs)  # an unfrozen CLIP tower among the parameters: flat-buffer kernels
     return Optimizer(parameters, **kwargs)
 
 

@@ -296,17 +296,30 @@ class LearnableCompressor(nn.Module):
         self._trainer_state = None
 
     def _fit_loop(self, batches, optimizers, max_steps, grad_clip, is_dist, process_group, grad_comm_dtype):
+        from .helpers import FlatAdamW
+
+        world = torch.distributed.get_world_size(process_group) if is_dist else 1
         for batch_idx, batch in enumerate(batches):
             if max_steps is not None and self.global_step >= max_steps:
                 break
             for oi, opt in enumerate(optimizers):
+                flat = isinstance(opt, FlatAdamW)
                 opt.zero_grad(set_to_none=True)
+                if flat:
+                    # an unfrozen CLIP tower: its gradient slices are all-reduced from INSIDE the backward pass, block
+                    # by block, under the GEMMs of the remaining blocks
+                    opt.prepare_backward(sync=is_dist, group=process_group, world=world)
                 loss = self.training_step(batch, batch_idx, optimizer_idx=oi)
                 loss.backward()
                 params = [p for g in opt.param_groups for p in g["params"] if p.grad is not None]
                 if is_dist and params:
-                    allreduce_mean_(params, process_group, comm_dtype=grad_comm_dtype)
-                if grad_clip:
+                    # (the tower's own gradients are 16-bit already; the few small float32 ones left here stay float32)
+                    allreduce_mean_(params, process_group, comm_dtype=None if flat else grad_comm_dtype)
+                if flat:
+                    opt.finish_backward()
+                    if grad_clip:
+                        opt.clip_grad_norm_(grad_clip)
+                elif grad_clip:
                     torch.nn.utils.clip_grad_norm_(params, grad_clip)
                 opt.step()
             self.global_step += 1

@@ -155,6 +155,7 @@ def test_weight_gradient_paths_agree(cuda_device, monkeypatch):
     grads = {}
     for impl in ("tn", "transpose"):
         monkeypatch.setattr(clip_vit, "WGRAD_IMPL", impl)
+        monkeypatch.setattr(clip_vit, "NATIVE_BLOCKS", impl == "tn")  # the native block runner always takes ll_gemm_tn
         vit, sd, cfg = _trainable_vit(cuda_device, 2, torch.bfloat16)
         gen = torch.Generator().manual_seed(5)
         x = torch.randn(3, 3, 224, 224, generator=gen).to(cuda_device)
@@ -220,3 +221,176 @@ def test_rd_step_with_unfrozen_encoder(cuda_device, distortion):
         assert sum(float(p.grad.abs().sum()) for p in enc.values()) > 0
     assert model.rate_estimator.entropy_bottleneck._matrix0.grad is not None
     assert math.isfinite(float(loss))
+
+
+# ---------------------------------------------------------------------------------------------- flat training state
+@pytest.mark.parametrize("g_dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_flat_optimizer_kernels_vs_torch(cuda_device, g_dtype):
+    """ll_sumsq / ll_adamw_flat / ll_cast_flat against torch: |g|^2, three AdamW steps (torch.optim.AdamW semantics,
+    gradient scale read from device memory) and the 16-bit compute copy the kernel writes alongside."""
+    from lossyless_b200 import _native as N
+
+    n = 8 * 12345
+    gen = torch.Generator().manual_seed(0)
+    p0 = torch.randn(n, generator=gen)
+    p = p0.clone().to(cuda_device)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    w16 = torch.empty(n, dtype=torch.bfloat16, device=cuda_device)
+    ref = torch.nn.Parameter(p0.clone().to(cuda_device))
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=3e-2, betas=(0.9, 0.999), eps=1e-8)
+    scratch = torch.empty(int(N.load().ll_sumsq_scratch_floats()), dtype=torch.float32, device=cuda_device)
+    scale = torch.tensor([0.37], device=cuda_device)
+    for step in range(1, 4):
+        g = (torch.randn(n, generator=gen) * 0.1).to(g_dtype).to(cuda_device)
+        out = torch.full((1,), 5.0, device=cuda_device)
+        N.call("ll_sumsq", N.ptr(g), n, N.dtype_code(g), N.ptr(scratch), N.ptr(out), 0, N.stream())
+        assert float(out) == pytest.approx(float(g.double().square().sum()), rel=1e-5)
+        N.call("ll_sumsq", N.ptr(g), n, N.dtype_code(g), N.ptr(scratch), N.ptr(out), 1, N.stream())
+        assert float(out) == pytest.approx(2 * float(g.double().square().sum()), rel=1e-5)
+        N.call("ll_adamw_flat", N.ptr(p), N.ptr(g), N.dtype_code(g), N.ptr(m), N.ptr(v), N.ptr(w16), N.LL_BF16, n,
+               1e-3, 0.9, 0.999, 1e-8, 3e-2, step, N.ptr(scale), N.stream())
+        ref.grad = g.float() * 0.37
+        opt.step()
+        assert torch.allclose(p, ref.detach(), rtol=2e-6, atol=2e-7), (p - ref.detach()).abs().max()
+        assert torch.equal(w16, p.bfloat16())
+    st = opt.state[ref]
+    assert torch.allclose(m, st["exp_avg"], rtol=1e-5, atol=1e-8) and torch.allclose(v, st["exp_avg_sq"], rtol=1e-5, atol=1e-10)
+    h = torch.empty(n, dtype=torch.float16, device=cuda_device)
+    N.call("ll_cast_flat", N.ptr(p), N.ptr(h), N.LL_F16, n, N.stream())
+    assert torch.equal(h, p.half())
+
+
+def test_flat_mode_gradients_equal_autograd_mode(cuda_device):
+    """Flat training state: the backward pass writes every gradient into the flat buffers (16-bit for the GEMM-produced
+    ones); they are the values the autograd-returning mode yields, the parameters alias the flat master, and the
+    16-bit compute views alias the flat 16-bit buffer."""
+    vit, sd, cfg = _trainable_vit(cuda_device, 2, torch.bfloat16)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 3, 224, 224, generator=gen).to(cuda_device)
+    r = torch.randn(3, 512, generator=gen).to(cuda_device)
+    z_ref = vit(x)
+    (z_ref * r).sum().backward()
+    want = {n: p.grad.clone() for n, p in vit.named_parameters()}
+    vit.zero_grad(set_to_none=True)
+    vit.enable_flat_training_(True)
+    z = vit(x)
+    assert torch.equal(z, z_ref)
+    (z * r).sum().backward()
+    flat = vit.flat_state()
+    assert all(p.grad is None for p in vit.parameters())
+    for n, p in vit.named_parameters():
+        got = flat.grad_view(n).float()
+        assert got.shape == p.shape
+        if flat.slots[n][0] == "mat":
+            assert torch.equal(got, want[n]), n          # same GEMM, same 16-bit result
+        else:
+            assert _rel(got, want[n]) < 1e-4, n         # float32 atomics: order may differ
+        assert p.data_ptr() == flat.view(flat.master, n).data_ptr()
+    # a second backward overwrites (does not accumulate)
+    (vit(x) * r).sum().backward()
+    assert _rel(flat.grad_view("ln_pre.weight"), want["ln_pre.weight"]) < 1e-4
+    vit.enable_flat_training_(False)
+    (vit(x) * r).sum().backward()
+    assert _rel(vit.ln_pre.weight.grad, want["ln_pre.weight"]) < 1e-4
+
+
+def test_flat_adamw_matches_torch_adamw(cuda_device):
+    """helpers.FlatAdamW (native flat-buffer AdamW + device-side global-norm clip for the tower, torch's fused AdamW for
+    the other parameters) against torch.optim.AdamW + torch clip_grad_norm_ on the same model, three steps."""
+    from lossyless_b200.helpers import FlatAdamW, get_optimizer
+
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(4, 3, 224, 224, generator=gen).to(cuda_device)
+    r = torch.randn(4, 512, generator=gen).to(cuda_device)
+    results = {}
+    for kind in ("torch", "flat"):
+        vit, sd, cfg = _trainable_vit(cuda_device, 2, torch.bfloat16)
+        head = torch.nn.Linear(512, 512).to(cuda_device)
+        with torch.no_grad():
+            head.weight.copy_(torch.eye(512, device=cuda_device) * 0.5), head.bias.zero_()
+        params = list(vit.parameters()) + list(head.parameters())
+        if kind == "torch":
+            opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=3e-8)
+        else:
+            opt = get_optimizer(params, "AdamW", lr=1e-3, weight_decay=3e-8)
+            assert isinstance(opt, FlatAdamW) and vit._flat_enabled
+        norms, first = [], None
+        for it in range(3):
+            opt.zero_grad(set_to_none=True)
+            if kind == "flat":
+                opt.prepare_backward(sync=False)
+            (head(vit(x)) * r).sum().backward()
+            if kind == "torch":
+                norms.append(float(torch.nn.utils.clip_grad_norm_(params, 3.0)))
+            else:
+                opt.finish_backward()
+                norms.append(float(opt.clip_grad_norm_(3.0)))
+            opt.step()
+            if it == 0:
+                first = {n: p.detach().clone() for n, p in list(vit.named_parameters()) + [("head.weight", head.weight)]}
+        with torch.no_grad():
+            results[kind] = (norms, {n: p.detach().clone() for n, p in vit.named_parameters()}, head.weight.detach().clone(), vit(x).float(), first)
+    (na, pa, ha, za, p1a), (nb, pb, hb, zb, p1b) = results["torch"], results["flat"]
+    assert na[0] == pytest.approx(nb[0], rel=1e-4) and na[0] > 3.0  # same global norm, and the clip was active
+    # after ONE step (identical gradients in both runs) the parameters agree to float32 rounding
+    for n in p1a:
+        assert _rel(p1a[n], p1b[n]) < 2e-6, n
+    # later steps see 16-bit weights that may differ in the last bit, and Adam turns a near-zero gradient entry's noise
+    # into a full +-lr step: compare against the distance travelled (3 steps x lr = 3e-3)
+    assert na == pytest.approx(nb, rel=5e-3)
+    for n in pa:
+        assert (pa[n] - pb[n]).abs().max().item() < 2.5e-3, n
+    assert (ha - hb).abs().max().item() < 2.5e-3
+    assert _rel(za, zb) < 3e-2
+
+
+def test_fit_with_unfrozen_tower_uses_flat_optimizer(cuda_device):
+    """LearnableCompressor.fit on config 3 (tower unfrozen): the main optimiser is a FlatAdamW, two fit() calls keep
+    its state, the loss is finite and the tower's parameters move."""
+    from lossyless_b200.helpers import FlatAdamW
+    from lossyless_b200.learnable_compressors import LearnableCompressor, default_clip_hparams
+
+    hp = default_clip_hparams(distortion="BINCE", beta=1e-2, max_steps=100, n_data=5000, is_frozen=False)
+    torch.manual_seed(0)
+    model = LearnableCompressor(hp)
+    enc = model.p_ZlX.mapper.encoder
+    del enc.transformer.resblocks[2:]
+    enc.layers = 2
+    model = model.to(cuda_device).train()
+    w0 = enc.transformer.resblocks[1].mlp.c_fc.weight.detach().clone()
+    gen = torch.Generator().manual_seed(1)
+    batch = (torch.randn(4, 3, 224, 224, generator=gen).to(cuda_device), (None, torch.randn(4, 3, 224, 224, generator=gen).to(cuda_device)))
+    logged = model.fit([batch, batch])
+    assert isinstance(model._trainer_state["optimizers"][0], FlatAdamW)
+    assert math.isfinite(logged["train/feat/loss"])
+    flat = enc.flat_state()
+    assert flat.step_count == 2
+    model.fit([batch])
+    assert flat.step_count == 3 and enc.flat_state() is flat
+    assert (enc.transformer.resblocks[1].mlp.c_fc.weight.detach() - w0).abs().max().item() > 0
+    with torch.no_grad():  # the frozen runner sees the trained weights
+        z = enc(batch[0])
+    assert torch.isfinite(z.float()).all()
+
+
+def test_native_block_runner_equals_python_sequencing(cuda_device, monkeypatch):
+    """ll_vit_block_forward / ll_vit_block_backward (one native call per block and direction) against the same kernels
+    sequenced from Python: identical output, identical matrix gradients, vector gradients equal up to atomics order."""
+    from lossyless_b200 import clip_vit
+
+    out = {}
+    for native in (True, False):
+        monkeypatch.setattr(clip_vit, "NATIVE_BLOCKS", native)
+        vit, sd, cfg = _trainable_vit(cuda_device, 3, torch.bfloat16)
+        gen = torch.Generator().manual_seed(11)
+        x = torch.randn(5, 3, 224, 224, generator=gen).to(cuda_device)
+        r = torch.randn(5, 512, generator=gen).to(cuda_device)
+        z = vit(x)
+        (z * r).sum().backward()
+        out[native] = (z.detach().clone(), {n: p.grad.clone() for n, p in vit.named_parameters()})
+    assert torch.equal(out[True][0], out[False][0])
+    for n, g in out[True][1].items():
+        if clip_vit._is_matrix(n):
+            assert torch.equal(g, out[False][1][n]), n
+        else:
+            assert _rel(g, out[False][1][n]) < 1e-4, n

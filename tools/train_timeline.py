@@ -1,0 +1,100 @@
+"""Where a training step's time goes: GPU kernel time (CUPTI timestamps through torch.profiler) against the step's span on the
+device, the largest idle gaps between consecutive kernels, and the host-side enqueue time per step.
+
+    python tools/train_timeline.py [--batch 256] [--steps 3]
+"""
+import argparse
+import os
+import sys
+import time
+import warnings
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+warnings.filterwarnings("ignore")
+from lossyless_b200.learnable_compressors import LearnableCompressor, default_clip_hparams  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=3)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    hp = default_clip_hparams(distortion="BINCE", beta=1e-2, max_steps=1000, n_data=50000, is_frozen=False)
+    model = LearnableCompressor(hp).to(dev).train()
+    B = args.batch
+    batch = (torch.randn(B, 3, 224, 224, device=dev), (None, torch.randn(B, 3, 224, 224, device=dev)))
+    model.fit([batch] * 3)
+    torch.cuda.synchronize()
+    # host enqueue time vs device time of one step (no profiler)
+    opts = model._trainer_state["optimizers"]
+    model._defer_log_sync = True
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    host = []
+    e[0].record()
+    for i in range(args.steps):
+        t0 = time.perf_counter()
+        model._fit_loop([batch], opts, None, 3.0, False, None, None)
+        host.append(time.perf_counter() - t0)
+        e[i + 1].record()
+    torch.cuda.synchronize()
+    print("host enqueue ms per step:", [round(1e3 * h, 2) for h in host])
+    print("device ms per step      :", [round(e[i].elapsed_time(e[i + 1]), 2) for i in range(args.steps)])
+    # every host synchronisation of one step, with the Python line that caused it
+    import traceback
+    import collections
+
+    sites = collections.Counter()
+    orig = warnings.showwarning
+
+    def show(message, category, filename, lineno, file=None, line=None):
+        if "synchroniz" in str(message):
+            st = [f for f in traceback.extract_stack() if "/lossyless_b200/" in f.filename or "/tools/" in f.filename]
+            sites[" <- ".join(f"{os.path.basename(f.filename)}:{f.lineno}" for f in reversed(st[-4:]))] += 1
+
+    warnings.showwarning = show
+    warnings.simplefilter("always")
+    torch.cuda.set_sync_debug_mode(1)
+    model._fit_loop([batch], opts, None, 3.0, False, None, None)
+    torch.cuda.set_sync_debug_mode(0)
+    warnings.showwarning = orig
+    warnings.filterwarnings("ignore")
+    print("synchronising calls in one step:", sum(sites.values()))
+    for k, v in sites.most_common(30):
+        print(f"  {v:3d} x {k}")
+    from torch.profiler import ProfilerActivity, profile
+
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        model._fit_loop([batch] * args.steps, opts, None, 3.0, False, None, None)
+        torch.cuda.synchronize()
+    ev = [x for x in prof.events() if x.device_type == torch.autograd.DeviceType.CUDA and x.time_range is not None]
+    ev.sort(key=lambda x: x.time_range.start)
+    t0, t1 = ev[0].time_range.start, max(x.time_range.end for x in ev)
+    busy = sum(x.time_range.end - x.time_range.start for x in ev)
+    print(f"{len(ev)} device activities over {args.steps} steps: span {(t1 - t0) / 1e3 / args.steps:.2f} ms/step, busy {busy / 1e3 / args.steps:.2f} ms/step")
+    gaps = []
+    end = ev[0].time_range.end
+    for a in ev[1:]:
+        if a.time_range.start > end:
+            gaps.append((a.time_range.start - end, a.name[:60]))
+        end = max(end, a.time_range.end)
+    gaps.sort(reverse=True)
+    print("idle total ms/step:", round(sum(g for g, _ in gaps) / 1e3 / args.steps, 2), " gaps > 20 us:", sum(1 for g, _ in gaps if g > 20) // args.steps, "per step")
+    for g, n in gaps[:25]:
+        print(f"  {g:8.1f} us before {n}")
+    agg = {}
+    for x in ev:
+        k = x.name.split("(")[0].replace("void ", "")[:60]
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += x.time_range.end - x.time_range.start
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
+        print(f"{t / 1e3 / args.steps:9.3f} ms {c // args.steps:5d}  {k}")
+    print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=35, max_name_column_width=60))
+
+
+if __name__ == "__main__":
+    main()
