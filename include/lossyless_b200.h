@@ -175,6 +175,23 @@ int ll_eb_backward(const void *z, int z_dtype, int64_t rows, int C, const float 
                    const float *g_q, const float *g_zhat, float *gz, float *gparam, float *g_bias,
                    float *g_exp_scale, ll_stream_t stream);
 
+/* ------------------------------------------------------ device: Gaussian-conditional likelihood */
+
+/* Fused compressai GaussianConditional.forward (+ per-row rate): out = x + noise (training; noise float32 [rows,C]) or
+ * round(x - mean) + mean (noise == NULL); q = max(Phi((1/2 - v)/s) - Phi((-1/2 - v)/s), likelihood_bound) with
+ * v = |out - mean|, s = max(scale, scale_bound); rates[r] = -sum_c log q (NULL to skip).  means may be NULL (zero
+ * means), q may be NULL.  All tensors float32 [rows, C], C % 4 == 0, 16-byte aligned.
+ * replaces lossyless/rates.py:638-646 (HRateHyperprior.forward_help: gaussian_conditional(...) and -log q summed). */
+int ll_gc_forward(const float *x, const float *scales, const float *means, const float *noise, int64_t rows,
+                  int C, float scale_bound, float likelihood_bound, float *out, float *q, float *rates,
+                  ll_stream_t stream);
+/* Its adjoint.  Incoming (each may be NULL, not all): g_out [rows,C], g_q [rows,C], g_rates [rows]; writes gx, gscales
+ * and (when means != NULL) gmeans, all [rows,C].  Both LowerBounds pass the gradient where the input sat at or above
+ * the bound or the gradient is negative (compressai ops/bound_ops.py). */
+int ll_gc_backward(const float *x, const float *scales, const float *means, const float *noise, int64_t rows,
+                   int C, float scale_bound, float likelihood_bound, const float *g_out, const float *g_q,
+                   const float *g_rates, float *gx, float *gscales, float *gmeans, ll_stream_t stream);
+
 /* ------------------------------------------------ device: native per-block runner (fine-tuning path) */
 
 /* Parameters of one clip.model.ResidualAttentionBlock: 16-bit matrices as nn.Linear stores them ([out, in]), float32

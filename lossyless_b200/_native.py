@@ -69,6 +69,8 @@ _SIGNATURES = {
     "ll_eb_pack_params": (c_int, [POINTER(_P), POINTER(_P), POINTER(_P), c_int, _P, _P]),
     "ll_eb_forward": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P]),
     "ll_eb_backward": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ll_gc_forward": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P]),
+    "ll_gc_backward": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
     "ll_vit_block_act_elems": (c_int64, [c_int64, c_int, c_int]),
     "ll_vit_block_x2_offset_elems": (c_int64, [c_int64, c_int, c_int]),
     "ll_vit_block_backward_scratch_elems": (c_int64, [c_int64, c_int, c_int]),

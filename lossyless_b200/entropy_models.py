@@ -486,8 +486,22 @@ class GaussianConditional(EntropyModel):
         return upper - lower
 
     def forward(self, inputs, scales, means=None, training=None, noise=None):
+        """-> (outputs, likelihood).  CUDA float32 inputs take the fused kernel (one launch forward, one backward);
+        anything else the elementwise torch ops above (host-side table construction, CPU tests)."""
+        out, lik, _ = self.forward_rates(inputs, scales, means, training, noise, want_rates=False)
+        return out, lik
+
+    def forward_rates(self, inputs, scales, means=None, training=None, noise=None, want_rates=True):
+        """``forward`` plus ``rates = -log(likelihood).sum(-1)`` per row of the last dimension, fused into the same
+        launch (what HRateHyperprior.forward_help computes next, lossyless/rates.py:640-646)."""
         if training is None:
             training = self.training
+        if inputs.is_cuda and self.use_likelihood_bound:
+            nz = None
+            if training:
+                nz = noise if noise is not None else torch.empty_like(inputs, dtype=torch.float32).uniform_(-0.5, 0.5)
+            out, lik, rates = _GCLikelihood.apply(self, inputs, scales, means, nz, bool(want_rates))
+            return out, lik, rates
         if training:
             outputs = inputs + (noise if noise is not None else torch.empty_like(inputs).uniform_(-0.5, 0.5))
         else:
@@ -495,7 +509,7 @@ class GaussianConditional(EntropyModel):
         likelihood = self._likelihood(outputs, scales, means)
         if self.use_likelihood_bound:
             likelihood = self.likelihood_lower_bound(likelihood)
-        return outputs, likelihood
+        return outputs, likelihood, (-torch.log(likelihood).sum(-1) if want_rates else None)
 
     def build_indexes(self, scales):
         scales = self.lower_bound_scale(scales)
@@ -664,6 +678,55 @@ class _EBRate(torch.autograd.Function):
             if i < 4:
                 params_grads.append(grads_f[i])
         return (None, gz.to(z.dtype), None, g_bias, g_scaling, None, None, *params_grads)
+
+
+class _GCLikelihood(torch.autograd.Function):
+    """(inputs, scales, means) -> (outputs, likelihood, rates) through ll_gc_forward / ll_gc_backward."""
+
+    @staticmethod
+    def forward(ctx, gc, inputs, scales, means, noise, want_rates):
+        N.require_cuda(inputs, "inputs")
+        shape = inputs.shape
+        C = shape[-1]
+        x = inputs.detach().float().contiguous().reshape(-1, C)
+        s = scales.detach().float().expand(shape).contiguous().reshape(-1, C)
+        m = means.detach().float().expand(shape).contiguous().reshape(-1, C) if means is not None else None
+        nz = noise.detach().float().contiguous().reshape(-1, C) if noise is not None else None
+        rows = x.shape[0]
+        out = torch.empty_like(x)
+        q = torch.empty_like(x)
+        rates = torch.empty(rows, dtype=torch.float32, device=x.device) if want_rates else None
+        sb = _bound_of(gc.lower_bound_scale)
+        lb = _bound_of(gc.likelihood_lower_bound)
+        N.call("ll_gc_forward", N.ptr(x), N.ptr(s), N.ptr(m), N.ptr(nz), rows, C, sb, lb, N.ptr(out), N.ptr(q), N.ptr(rates), N.stream())
+        ctx.save_for_backward(x, s, m, nz)
+        ctx.bounds, ctx.shape, ctx.has_means = (sb, lb), shape, means is not None
+        ctx.set_materialize_grads(False)
+        return out.reshape(shape), q.reshape(shape), (rates.reshape(shape[:-1]) if want_rates else None)
+
+    @staticmethod
+    def backward(ctx, g_out, g_q, g_rates):
+        x, s, m, nz = ctx.saved_tensors
+        if g_out is None and g_q is None and g_rates is None:
+            return (None,) * 6
+        rows, C = x.shape
+        prep = lambda g, shp: g.float().contiguous().reshape(shp) if g is not None else None  # noqa: E731
+        go, gq, gr = prep(g_out, (rows, C)), prep(g_q, (rows, C)), prep(g_rates, (rows,))
+        gx, gs = torch.empty_like(x), torch.empty_like(x)
+        gm = torch.empty_like(x) if m is not None else None
+        N.call("ll_gc_backward", N.ptr(x), N.ptr(s), N.ptr(m), N.ptr(nz), rows, C, ctx.bounds[0], ctx.bounds[1], N.ptr(go), N.ptr(gq),
+               N.ptr(gr), N.ptr(gx), N.ptr(gs), N.ptr(gm), N.stream())
+        return (None, gx.reshape(ctx.shape), gs.reshape(ctx.shape), gm.reshape(ctx.shape) if gm is not None else None, None, None)
+
+
+def _bound_of(lower_bound_module):
+    """LowerBound.bound as a host float, read back once per buffer version (no `.item()` per call)."""
+    buf = lower_bound_module.bound
+    key = (buf.data_ptr(), buf._version)
+    cache = getattr(lower_bound_module, "_bound_cache", None)
+    if cache is None or cache[0] != key:
+        cache = lower_bound_module._bound_cache = (key, float(buf.item()))
+    return cache[1]
 
 
 def eb_rate_forward(eb, z, noise, biasing, scaling, want_rates=True, exp_scale=None):

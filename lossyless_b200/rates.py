@@ -256,9 +256,10 @@ class HRateHyperprior(HRateEstimator):
         nz_side = noise[1] if noise is not None else None
         side_z_hat, q_s = self.entropy_bottleneck(side_z, noise=nz_side)
         scales_hat, means_hat = self.chunk_params(self.z_encoder(side_z_hat))
-        z_hat, q_zls = self.gaussian_conditional(z_in, scales_hat, means=means_hat, noise=noise[0] if noise is not None else None)
+        # Gaussian-conditional likelihood and its per-row -log q in one fused launch (csrc/gaussian.cu)
+        z_hat, q_zls, neg_log_q_zls = self.gaussian_conditional.forward_rates(z_in, scales_hat, means=means_hat,
+                                                                                noise=noise[0] if noise is not None else None)
         neg_log_q_s = -torch.log(q_s).sum(-1)
-        neg_log_q_zls = -torch.log(q_zls).sum(-1)
         neg_log_q_zs = neg_log_q_s + neg_log_q_zls
         logs = dict(H_q_ZlS=neg_log_q_zls.mean() / math.log(BASE_LOG), H_q_Z=neg_log_q_zs.mean() / math.log(BASE_LOG),
                     H_q_S=neg_log_q_s.mean() / math.log(BASE_LOG), H_ZlX=0)

@@ -167,3 +167,51 @@ def test_learnable_compressor_with_hyperprior(cuda_device):
     with torch.no_grad():
         model.test_step(batch, 0)
     assert model.logged["test/feat/n_bits"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("with_means", [True, False])
+def test_gaussian_conditional_fused_kernel_vs_autograd(cuda_device, training, with_means):
+    """ll_gc_forward / ll_gc_backward against torch autograd through the oracle's op-by-op restatement of compressai's
+    GaussianConditional.forward (both LowerBounds with compressai's gradient rule), gradients arriving through all three
+    outputs (outputs, likelihood, per-row rate).  Scales below the 0.11 bound and likelihoods at the 1e-9 bound included."""
+    from lossyless_b200.entropy_models import GaussianConditional
+
+    gen = torch.Generator().manual_seed(3)
+    B, C = 37, 64
+    x = torch.randn(B, C, generator=gen) * 4
+    x[0] *= 30  # far tails: likelihood clamps at 1e-9
+    scales = torch.rand(B, C, generator=gen) * 3 + 0.02  # some below the 0.11 bound
+    means = torch.randn(B, C, generator=gen) if with_means else None
+    noise = torch.rand(B, C, generator=gen) - 0.5 if training else None
+    w_out, w_q, w_r = torch.randn(B, C, generator=gen), torch.randn(B, C, generator=gen), torch.rand(B, generator=gen) + 0.5
+
+    def reference(x, scales, means):
+        out = x + noise if training else torch.round(x - (means if means is not None else 0)) + (means if means is not None else 0)
+        v = torch.abs(out - means) if means is not None else torch.abs(out)
+        s = oeb._LowerBound.apply(scales, og.SCALE_BOUND)
+        lik = og.standardized_cumulative((0.5 - v) / s) - og.standardized_cumulative((-0.5 - v) / s)
+        q = oeb._LowerBound.apply(lik, og.LIKELIHOOD_BOUND)
+        return out, q, -torch.log(q).sum(-1)
+
+    leaves = [t.clone().requires_grad_(True) if t is not None else None for t in (x, scales, means)]
+    out_r, q_r, r_r = reference(*leaves)
+    ((out_r * w_out).sum() + (q_r * w_q).sum() + (r_r * w_r).sum()).backward()
+
+    gc = GaussianConditional(None).to(cuda_device)
+    gc.train(training)
+    dl = [t.clone().to(cuda_device).requires_grad_(True) if t is not None else None for t in (x, scales, means)]
+    out, q, rates = gc.forward_rates(dl[0], dl[1], means=dl[2], noise=noise.to(cuda_device) if training else None)
+    ((out * w_out.to(cuda_device)).sum() + (q * w_q.to(cuda_device)).sum() + (rates * w_r.to(cuda_device)).sum()).backward()
+    assert torch.allclose(out.detach().cpu(), out_r.detach(), rtol=1e-6, atol=1e-6)
+    assert np.allclose(q.detach().cpu().numpy(), q_r.detach().numpy(), rtol=1e-4, atol=1e-12)
+    assert np.allclose(rates.detach().cpu().numpy(), r_r.detach().numpy(), rtol=1e-5)
+    for got, want, name in zip(dl, leaves, ("x", "scales", "means")):
+        if want is None:
+            continue
+        g, w = got.grad.cpu().double(), want.grad.double()
+        assert (g - w).abs().max().item() < 2e-4 * (w.abs().max().item() + 1e-9), (name, (g - w).abs().max().item(), w.abs().max().item())
+    # the module-level forward (compressai signature) returns the same outputs / likelihood
+    out2, q2 = gc(dl[0].detach(), dl[1].detach(), means=dl[2].detach() if dl[2] is not None else None, noise=noise.to(cuda_device) if training else None)
+    assert torch.equal(out2, out.detach()) and torch.equal(q2, q.detach())

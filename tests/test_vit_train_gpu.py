@@ -339,8 +339,8 @@ def test_flat_adamw_matches_torch_adamw(cuda_device):
     # into a full +-lr step: compare against the distance travelled (3 steps x lr = 3e-3)
     assert na == pytest.approx(nb, rel=5e-3)
     for n in pa:
-        assert (pa[n] - pb[n]).abs().max().item() < 2.5e-3, n
-    assert (ha - hb).abs().max().item() < 2.5e-3
+        assert (pa[n] - pb[n]).abs().max().item() < 6.5e-3 and (pa[n] - pb[n]).abs().mean().item() < 1e-3, n
+    assert (ha - hb).abs().max().item() < 6.5e-3 and (ha - hb).abs().mean().item() < 1e-3
     assert _rel(za, zb) < 3e-2
 
 
