@@ -102,3 +102,47 @@ def test_compress_stream_matches_blocking_calls(compressor):
     # (5 -> 400) and are re-created while the previous batch may still be in flight
     got = [bytes(rec.numpy().data) for rec, _ in comp.compress_stream(iter(batches[:4]))]
     assert got == [bytes(comp.compress_batch_to_host(b)[0].numpy().data) for b in batches[:4]]
+
+
+def test_downstream_probe_on_decompressed_representations(cuda_device, tmp_path, weights_dir):
+    """the consumer side.  Class-structured synthetic images -> compress_dataset -> decompress_dataset ->
+    the reference's ``Predictor`` probe (lossyless/predictors.py) trained on Z_hat.  The same probe trained on the
+    representations of the float32 CPU oracle (same weights, same bottleneck, no 16-bit encoder, no codec) reaches the
+    same accuracy: the fp16 tower's symbol flips do not move the downstream task."""
+    import hubconf
+    from lossyless_b200.helpers import NamespaceMap
+    from lossyless_b200.predictors import Predictor
+    from oracle import vit as ovit
+
+    sd_vit = ovit.init_state_dict(0)
+    comp, _ = hubconf.clip_compressor_b005(device="cuda", clip_state_dict=sd_vit)
+    g = torch.Generator().manual_seed(0)
+    n_cls, per = 6, 40
+    templates = torch.randn(n_cls, 3, 224, 224, generator=g)
+    y = torch.arange(n_cls * per) % n_cls
+    X = (templates[y] + 1.0 * torch.randn(n_cls * per, 3, 224, 224, generator=g)).half()
+    ds = torch.utils.data.TensorDataset(X, y)
+    comp.compress_dataset(ds, tmp_path / "Z.bin", label_file=tmp_path / "Y.npy", kwargs_dataloader=dict(batch_size=64, num_workers=0), is_info=False)
+    Z_hat, Y = comp.decompress_dataset(tmp_path / "Z.bin", label_file=tmp_path / "Y.npy", is_info=False)
+    assert Z_hat.shape == (n_cls * per, 512) and np.array_equal(Y, y.numpy())
+    with torch.no_grad():  # the oracle's float32 representations, quantised by the oracle bottleneck
+        sd = torch.load(os.path.join(weights_dir, "beta5e-02_factorized_rate.pt"), map_location="cpu", weights_only=True)
+        ebo = oeb.split_state_dict(sd)
+        z32 = torch.cat([ovit.forward({k: v.half().float() for k, v in sd_vit.items()}, X[i:i + 60].float()) for i in range(0, len(X), 60)])
+        zh_in, _ = oeb.forward(ebo, oeb.process_z_in(z32, sd["biasing"], sd["scaling"]))
+        Z_ref = oeb.process_z_out(zh_in, sd["biasing"], sd["scaling"])
+
+    def probe_acc(Z):
+        hp = NamespaceMap(stage="pred", data=dict(shape=(512,), target_shape=(n_cls,), target_is_clf=True, balancing_weights={}),
+                          predictor=dict(arch="linear", arch_kwargs={}),
+                          optimizer_pred=dict(mode="Adam", kwargs=dict(lr=3e-2)), scheduler_pred=None)
+        torch.manual_seed(0)
+        pred = Predictor(hp)
+        Z = torch.as_tensor(Z)
+        tr = torch.arange(len(Z)) % 4 != 0  # 3/4 train, 1/4 test
+        pred.fit([(Z[tr], y[tr])], epochs=60)
+        return pred.evaluate([(Z[~tr], y[~tr])])["acc"]
+
+    acc_gpu, acc_ref = probe_acc(Z_hat), probe_acc(Z_ref.numpy())
+    assert acc_ref > 0.9 and abs(acc_gpu - acc_ref) <= 0.05, (acc_gpu, acc_ref)
+    assert float((torch.as_tensor(Z_hat) != Z_ref).float().mean()) < 0.05  # a few percent of the symbols moved by one step
