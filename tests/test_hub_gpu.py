@@ -146,3 +146,31 @@ def test_downstream_probe_on_decompressed_representations(cuda_device, tmp_path,
     acc_gpu, acc_ref = probe_acc(Z_hat), probe_acc(Z_ref.numpy())
     assert acc_ref > 0.9 and abs(acc_gpu - acc_ref) <= 0.05, (acc_gpu, acc_ref)
     assert float((torch.as_tensor(Z_hat) != Z_ref).float().mean()) < 0.05  # a few percent of the symbols moved by one step
+
+
+def test_container_v2_indexed_format(compressor, tmp_path):
+    """the indexed container (magic LLZ2, streams back to back, 16-bit length table at the end) holds the
+    SAME per-image rANS streams as the reference's v1 file, is 2 bytes per image smaller, and decompress_dataset reads
+    either; a truncated / inconsistent v2 file raises."""
+    comp, transform = compressor
+    ds = _Synthetic(70, transform)
+    f1, f2, lf = tmp_path / "Z1.bin", tmp_path / "Z2.bin", tmp_path / "Y.npy"
+    comp.compress_dataset(ds, f1, label_file=lf, kwargs_dataloader=dict(batch_size=32, num_workers=0), is_info=False)
+    comp.compress_dataset(ds, f2, label_file=lf, kwargs_dataloader=dict(batch_size=32, num_workers=0), is_info=False, container="v2")
+    b1, b2 = f1.read_bytes(), f2.read_bytes()
+    assert b2[:4] == b"LLZ2" and struct.unpack(">II", b2[4:12]) == (70, 512)
+    assert len(b2) == len(b1) + 8 - 2 * 70
+    # same streams: walk v1's records and compare with v2's payload + length table
+    lens = np.frombuffer(b2[len(b2) - 140:], dtype="<u2").astype(np.int64) * 4
+    pos1, pos2 = 4, 12
+    for n in lens:
+        assert struct.unpack(">I", b1[pos1: pos1 + 4])[0] == n and b1[pos1 + 4: pos1 + 4 + n] == b2[pos2: pos2 + n]
+        pos1, pos2 = pos1 + 4 + n, pos2 + n
+    Z1 = comp.decompress_dataset(f1, is_info=False)
+    Z2, Y = comp.decompress_dataset(f2, label_file=lf, is_info=False)
+    assert np.array_equal(Z1, Z2) and Y.tolist() == [i % 10 for i in range(70)]
+    (tmp_path / "bad2.bin").write_bytes(b2[:-3])
+    with pytest.raises(ValueError):
+        comp.decompress_dataset(tmp_path / "bad2.bin")
+    with pytest.raises(ValueError):
+        comp.compress_dataset(ds, tmp_path / "x.bin", container="v3")
