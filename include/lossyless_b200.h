@@ -140,8 +140,11 @@ int ll_rans_decode_indexed(const uint8_t *data, const int64_t *offsets, const in
 /* ------------------------------------------------------- device: EntropyBottleneck */
 
 /* Derived per-channel parameters (softplus(matrix), tanh(factor)) packed for the likelihood
- * kernels: float32 [LL_EB_NPARAM, C].  Only filters = (3,3,3,3) (the reference's setting,
- * hub/compressor.py:49-51, config/rate/H_factorized.yaml) is supported. */
+ * kernels: float32 [2 * LL_EB_NPARAM, C] -- rows [0, 58) as derived (the backward kernel and
+ * the gradient chain use them), rows [58, 116) the same pre-scaled by 2 log2(e) where the
+ * forward kernel wants them (biases and factors times c, last-layer matrix divided by c).
+ * Only filters = (3,3,3,3) (the reference's setting, hub/compressor.py:49-51,
+ * config/rate/H_factorized.yaml) is supported. */
 #define LL_EB_NPARAM 58
 int ll_eb_pack_params(const float *const *matrices /*5*/, const float *const *biases /*5*/,
                       const float *const *factors /*4*/, int C, float *packed, ll_stream_t stream);

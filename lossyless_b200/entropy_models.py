@@ -590,7 +590,8 @@ def _packed_params(eb, device):
     ms = [getattr(eb, f"_matrix{i}").detach().float().contiguous() for i in range(5)]
     bs = [getattr(eb, f"_bias{i}").detach().float().contiguous() for i in range(5)]
     fs = [getattr(eb, f"_factor{i}").detach().float().contiguous() for i in range(4)]
-    packed = torch.empty((N.LL_EB_NPARAM, eb.channels), dtype=torch.float32, device=device)
+    # [2 * 58, C]: the derived parameters, then their exponent-scaled twins the forward kernel reads (ll_eb_pack_params)
+    packed = torch.empty((2 * N.LL_EB_NPARAM, eb.channels), dtype=torch.float32, device=device)
     N.call("ll_eb_pack_params", N.ptr_array(ms), N.ptr_array(bs), N.ptr_array(fs), eb.channels, N.ptr(packed), N.stream())
     return packed, (ms, bs, fs)
 
