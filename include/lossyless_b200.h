@@ -248,6 +248,19 @@ int ll_adamw_flat(float *p, const void *g, int g_dtype, float *m, float *v, void
 /* dst (fp16 / bf16) = src (float32) */
 int ll_cast_flat(const float *src, void *dst, int dst_dtype, int64_t n, ll_stream_t stream);
 
+/* Chain rule from ll_eb_backward's gparam [LL_EB_NPARAM, C] (gradients w.r.t. softplus(matrix), bias, tanh(factor)) to
+ * the raw parameters, in their own layouts (matrices [C, f_out, f_in], biases / factors [C, f_out, 1]): one launch for
+ * all 14 tensors.  m / g_m / g_b: 5 pointers, f / g_f: 4 pointers. */
+int ll_eb_unpack_grads(const float *gparam, const float *const *m, const float *const *f, int C,
+                       float *const *g_m, float *const *g_b, float *const *g_f, ll_stream_t stream);
+
+/* compressai EntropyBottleneck.loss() = sum |logits_cumulative(quantiles) - target| with the parameters detached (the
+ * "coder" optimiser's objective; lossyless/rates.py:426, learnable_compressors.py:293-295), forward AND the gradient
+ * w.r.t. quantiles [C, 1, 3] in one launch.  `loss` (1 float) is accumulated into: zero it first.  `packed` as produced
+ * by ll_eb_pack_params. */
+int ll_eb_aux_loss(const float *quantiles, const float *packed, const float *target, int C, float *loss,
+                   float *g_quantiles, ll_stream_t stream);
+
 /* ------------------------------------------------------------ device: CLIP ViT-B/32 */
 
 typedef struct ll_vit ll_vit_t;

@@ -80,6 +80,8 @@ _SIGNATURES = {
     "ll_sumsq": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P]),
     "ll_adamw_flat": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, _P, _P]),
     "ll_cast_flat": (c_int, [_P, _P, c_int, c_int64, _P]),
+    "ll_eb_unpack_grads": (c_int, [_P, POINTER(_P), POINTER(_P), c_int, POINTER(_P), POINTER(_P), POINTER(_P), _P]),
+    "ll_eb_aux_loss": (c_int, [_P, _P, _P, c_int, _P, _P, _P]),
     "ll_vit_create": (c_int, [POINTER(VitConfig), POINTER(VitWeights), POINTER(_P)]),
     "ll_vit_destroy": (None, [_P]),
     "ll_vit_workspace_bytes": (c_int64, [_P, c_int64]),

@@ -226,6 +226,62 @@ __global__ void eb_pack_params_kernel(const float *m0, const float *m1, const fl
     ps[kB4 * C + c] = packed[kB4 * C + c];
 }
 
+// Chain rule from the derived parameters back to the raw ones, all 14 tensors in ONE launch (it was ~60 tiny torch ops
+// per backward call, 2.6 ms of host time per training step): g_matrix = g_softplus * sigmoid(matrix), g_factor = g_tanh *
+// (1 - tanh(factor)^2), g_bias as is; outputs in the parameters' own layouts ([C, f_out, f_in] / [C, f_out, 1]).
+__global__ void eb_unpack_grads_kernel(const float *__restrict__ gparam, const float *m0, const float *m1, const float *m2,
+                                       const float *m3, const float *m4, const float *f0, const float *f1, const float *f2,
+                                       const float *f3, int C, float *gm0, float *gm1, float *gm2, float *gm3, float *gm4, float *gb0,
+                                       float *gb1, float *gb2, float *gb3, float *gb4, float *gf0, float *gf1, float *gf2, float *gf3)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    auto dsoftplus = [](float x) { return 1.f / (1.f + expf(-x)); };
+    auto dtanh = [](float x) { const float t = tanhf(x); return 1.f - t * t; };
+    const float *M[4] = {m0, m1, m2, m3};
+    const float *F[4] = {f0, f1, f2, f3};
+    float *GM[4] = {gm0, gm1, gm2, gm3};
+    float *GB[4] = {gb0, gb1, gb2, gb3};
+    float *GF[4] = {gf0, gf1, gf2, gf3};
+    for (int j = 0; j < 3; ++j) gm0[c * 3 + j] = gparam[(kM0 + j) * C + c] * dsoftplus(m0[c * 3 + j]);
+    for (int k = 1; k < 4; ++k)
+        for (int e = 0; e < 9; ++e) GM[k][c * 9 + e] = gparam[(kMOff[k] + e) * C + c] * dsoftplus(M[k][c * 9 + e]);
+    for (int k = 0; k < 4; ++k)
+        for (int j = 0; j < 3; ++j) {
+            GB[k][c * 3 + j] = gparam[(kBOff[k] + j) * C + c];
+            GF[k][c * 3 + j] = gparam[(kFOff[k] + j) * C + c] * dtanh(F[k][c * 3 + j]);
+        }
+    for (int i = 0; i < 3; ++i) gm4[c * 3 + i] = gparam[(kM4 + i) * C + c] * dsoftplus(m4[c * 3 + i]);
+    gb4[c] = gparam[kB4 * C + c];
+}
+
+// compressai EntropyBottleneck.loss() (the "coder" optimiser's objective, lossyless/rates.py:426 aux_loss):
+//   sum_c sum_k | logits_cumulative(quantiles[c, k]) - target[k] |   with the parameters detached,
+// forward and the gradient w.r.t. the quantiles in one launch (thread per channel, 3 points each): ~90 tiny torch
+// launches of forward + autograd otherwise.
+__global__ void eb_aux_loss_kernel(const float *__restrict__ quantiles, const float *__restrict__ packed, const float *__restrict__ target,
+                                   int C, float *__restrict__ loss, float *__restrict__ g_quantiles)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    float part = 0.f;
+    if (c < C) {
+        float P[kNP], G[kNP];
+#pragma unroll
+        for (int i = 0; i < kNP; ++i) P[i] = packed[i * C + c], G[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float v = quantiles[c * 3 + k];
+            Trace tr;
+            const float d = logits_fwd(P, v, tr) - target[k];
+            part += fabsf(d);
+            const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+            g_quantiles[c * 3 + k] = logits_bwd(P, v, tr, sg, G);
+        }
+    }
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss, part);
+}
+
 constexpr int kEbThreads = 128;
 
 template <typename T>
@@ -453,6 +509,28 @@ extern "C" int ll_eb_backward(const void *z, int z_dtype, int64_t rows, int C, c
         case LL_BF16: eb_backward_kernel<__nv_bfloat16><<<grid, kEbThreads, 0, s>>>((const __nv_bfloat16 *)z, rows, C, rpc, noise, bias, exp_scale, medians, packed, bound, g_rates, g_q, g_zhat, gz, gparam, g_bias, g_exp_scale); break;
         default: return fail(LL_ERR_INVALID, "eb_backward: unknown dtype %d", z_dtype);
     }
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+extern "C" int ll_eb_unpack_grads(const float *gparam, const float *const *m, const float *const *f, int C, float *const *g_m,
+                                  float *const *g_b, float *const *g_f, ll_stream_t stream)
+{
+    LL_REQUIRE(gparam && m && f && g_m && g_b && g_f && C > 0, "eb_unpack_grads: bad arguments");
+    for (int i = 0; i < 5; ++i) LL_REQUIRE(m[i] && g_m[i] && g_b[i], "eb_unpack_grads: null matrix / gradient %d", i);
+    for (int i = 0; i < 4; ++i) LL_REQUIRE(f[i] && g_f[i], "eb_unpack_grads: null factor / gradient %d", i);
+    eb_unpack_grads_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(gparam, m[0], m[1], m[2], m[3], m[4], f[0], f[1], f[2], f[3], C,
+                                                                        g_m[0], g_m[1], g_m[2], g_m[3], g_m[4], g_b[0], g_b[1], g_b[2],
+                                                                        g_b[3], g_b[4], g_f[0], g_f[1], g_f[2], g_f[3]);
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+extern "C" int ll_eb_aux_loss(const float *quantiles, const float *packed, const float *target, int C, float *loss,
+                              float *g_quantiles, ll_stream_t stream)
+{
+    LL_REQUIRE(quantiles && packed && target && loss && g_quantiles && C > 0, "eb_aux_loss: bad arguments");
+    eb_aux_loss_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(quantiles, packed, target, C, loss, g_quantiles);
     LL_LAUNCH_CHECK();
     return LL_OK;
 }

@@ -348,6 +348,10 @@ class EntropyBottleneck(EntropyModel):
         return True
 
     def loss(self):
+        """``sum |logits_cumulative(quantiles) - target|`` with the parameters detached (compressai's auxiliary loss).
+        On a B200 with the reference's filters: forward and the gradient w.r.t. the quantiles in one native launch."""
+        if self.quantiles.is_cuda and self.filters == (3, 3, 3, 3):
+            return _EBAuxLoss.apply(self, self.quantiles)
         logits = self._logits_cumulative(self.quantiles, stop_gradient=True)
         return torch.abs(logits - self.target).sum()
 
@@ -658,19 +662,13 @@ class _EBRate(torch.autograd.Function):
         gh = g_zhat.contiguous().float() if g_zhat is not None else None
         N.call("ll_eb_backward", N.ptr(z), N.dtype_code(z), rows, C, N.ptr(nz), N.ptr(b), N.ptr(es), N.ptr(med), N.ptr(packed),
                _bound(eb), N.ptr(g_r), N.ptr(g_qc), N.ptr(gh), N.ptr(gz), N.ptr(gparam), N.ptr(gb), N.ptr(ges), N.stream())
-        # chain rule from the derived parameters back to the raw ones (58 x C elementwise, torch)
-        grads_m, grads_b, grads_f = [], [], []
-        offs_m, offs_b, offs_f = [0, 9, 24, 39, 54], [3, 18, 33, 48, 57], [6, 21, 36, 51]
+        # chain rule from the derived parameters back to the raw ones: ONE launch for the 14 tensors
         shapes_m = [(3, 1), (3, 3), (3, 3), (3, 3), (1, 3)]
-        for i in range(5):
-            fo, fi = shapes_m[i]
-            g = gparam[offs_m[i]: offs_m[i] + fo * fi].t().reshape(C, fo, fi)
-            grads_m.append(g * torch.sigmoid(ms[i]))  # d softplus(x)/dx
-            nb = fo
-            grads_b.append(gparam[offs_b[i]: offs_b[i] + nb].t().reshape(C, nb, 1))
-        for i in range(4):
-            g = gparam[offs_f[i]: offs_f[i] + 3].t().reshape(C, 3, 1)
-            grads_f.append(g * (1 - torch.tanh(fs[i]) ** 2))
+        grads_m = [torch.empty((C, fo, fi), dtype=torch.float32, device=dev) for fo, fi in shapes_m]
+        grads_b = [torch.empty((C, fo, 1), dtype=torch.float32, device=dev) for fo, _ in shapes_m]
+        grads_f = [torch.empty((C, 3, 1), dtype=torch.float32, device=dev) for _ in range(4)]
+        N.call("ll_eb_unpack_grads", N.ptr(gparam), N.ptr_array(list(ms)), N.ptr_array(list(fs)), C, N.ptr_array(grads_m),
+               N.ptr_array(grads_b), N.ptr_array(grads_f), N.stream())
         g_bias = gb if ctx.has_affine else None
         g_scaling = ges * es if ctx.has_affine else None  # d exp(s)/ds
         params_grads = []
@@ -679,6 +677,26 @@ class _EBRate(torch.autograd.Function):
             if i < 4:
                 params_grads.append(grads_f[i])
         return (None, gz.to(z.dtype), None, g_bias, g_scaling, None, None, *params_grads)
+
+
+class _EBAuxLoss(torch.autograd.Function):
+    """quantiles [C, 1, 3] -> scalar auxiliary loss through ll_eb_aux_loss (value + d/d quantiles in one launch)."""
+
+    @staticmethod
+    def forward(ctx, eb, quantiles):
+        packed, _ = _packed_params(eb, quantiles.device)
+        q = quantiles.detach().float().contiguous()
+        loss = torch.zeros(1, dtype=torch.float32, device=q.device)
+        gq = torch.empty_like(q)
+        N.call("ll_eb_aux_loss", N.ptr(q), N.ptr(packed), N.ptr(eb.target.detach().float().contiguous()), eb.channels, N.ptr(loss),
+               N.ptr(gq), N.stream())
+        ctx.save_for_backward(gq)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (gq,) = ctx.saved_tensors
+        return None, gq * g
 
 
 class _GCLikelihood(torch.autograd.Function):
