@@ -368,6 +368,16 @@ int ll_gemm_patch_embed(const void *x, const void *W, void *D, int64_t n_images,
  * gradients -- no transposed copies.  A, B, D in `dtype` (LL_F16 / LL_BF16), fp32 accumulation.
  * Mo % 128 == 0, No % 64 == 0, Kt arbitrary (rows past Kt are zero-filled by TMA). */
 int ll_gemm_tn(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, ll_stream_t stream);
+
+/* ll_gemm_tn with split-K: when the output is only a fraction of a round of tiles (a [768..3072]^2 weight gradient is
+ * 36-144 tiles for a 25 600-deep reduction) the reduction is split 2-4 ways over otherwise idle SMs, every split leaves a
+ * float32 partial in `workspace` (ll_gemm_tn_workspace_bytes(Mo, No) bytes, 16-byte aligned) and a second kernel adds
+ * them with one rounding to the 16-bit result.  Falls back to ll_gemm_tn's single pass when splitting does not help.
+ * ll_gemm_set_splitk(0) switches the splitting off (A/B knob). */
+int64_t ll_gemm_tn_workspace_bytes(int Mo, int No);
+int ll_gemm_tn_splitk(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype,
+                      void *workspace, int64_t workspace_bytes, ll_stream_t stream);
+int ll_gemm_set_splitk(int on);
 /* Force the GEMM's tile width (64/128/192/256; 0 = automatic wave-aware choice). Tests, tuning. */
 int ll_gemm_set_tile_n(int bn);
 /* CTA-pair (tcgen05 cta_group::2, 256-row tiles) policy: -1 automatic, 0 never, 1 always. */

@@ -207,16 +207,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // patch-embedding mode: A is the image batch itself (5-D map); bits 16.. of `act` hold the K blocks per channel
     const bool patch_mode = (act & 0x8000) != 0;
     const int kb_per_channel = act >> 16;
+    // split-K (act bit 0x10000; weight gradients: few output tiles, a very deep reduction): work item = (tile, split),
+    // split s reduces K blocks [s nkb / S, (s + 1) nkb / S) and leaves a float32 partial tile in the workspace
+    // (passed through the stats_out pointer, S through stats_in_parts); a second kernel adds the partials
+    const bool splitk = (act & 0x10000) != 0 && !patch_mode;
+    const int splits = splitk ? stats_in_parts : 1;
+    const int num_work = num_tiles * splits;
 
     if (warp == kProducerWarp) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+            for (int work = worker; work < num_work; work += num_workers) {
+                const int tile = work % num_tiles, sp = work / num_tiles;
                 const int m0 = (tile / num_n) * kTileM + (int)cta_rank * kBM;
                 const int n0 = (tile % num_n) * BN + (int)cta_rank * S::kBRows;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_begin = (int)((int64_t)sp * num_kb / splits), kb_end = (int)((int64_t)(sp + 1) * num_kb / splits);
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (tn) {
                         // TN operands (D = A^T B, weight gradients): A is [K rows, M columns], B is [K rows, N columns];
@@ -281,13 +289,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+            for (int work = worker; work < num_work; work += num_workers, ++it) {
+                const int sp = work / num_tiles;
+                const int kb_begin = (int)((int64_t)sp * num_kb / splits), kb_end = (int)((int64_t)(sp + 1) * num_kb / splits);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * S::kAccStride;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t addr_a = ptx::smem_u32(sm_a + stage * kABytes), addr_b = ptx::smem_u32(sm_b + stage * S::kBBytes);
@@ -302,9 +312,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         // patch mode: A is two SWIZZLE_64B sub-blocks of 32 K-columns (8192 B apart), two K = 16 steps each
                         const uint64_t dak = patch_mode ? ptx::make_kmajor_sw64_desc(addr_a + (k >> 1) * 8192) + 2 * (k & 1) : da + kstep * k;
                         if constexpr (kCtas == 2)
-                            ptx::mma_f16_ss_pair(tmem_d, dak, db + kstep * k, id, (kb | k) != 0);
+                            ptx::mma_f16_ss_pair(tmem_d, dak, db + kstep * k, id, ((kb - kb_begin) | k) != 0);
                         else
-                            ptx::mma_f16_ss(tmem_d, dak, db + kstep * k, id, (kb | k) != 0);
+                            ptx::mma_f16_ss(tmem_d, dak, db + kstep * k, id, ((kb - kb_begin) | k) != 0);
                     }
                     // frees the smem stage (in both CTAs) when the MMAs retire
                     if constexpr (kCtas == 2)
@@ -338,7 +348,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int it = 0;
         const uint32_t tempty_lead[2] = {kCtas == 2 ? ptx::map_to_cta(&tempty_bar[0], 0) : 0,
                                          kCtas == 2 ? ptx::map_to_cta(&tempty_bar[1], 0) : 0};
-        for (int tile = worker; n_own > 0 && tile < num_tiles; tile += num_workers, ++it) {
+        for (int work = worker; n_own > 0 && work < num_work; work += num_workers, ++it) {
+            const int tile = work % num_tiles, sp = work / num_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m0 = (tile / num_n) * kTileM + (int)cta_rank * kBM + quarter * 32;
@@ -356,7 +367,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // (sum, sum of squares) partials the producing kernel's epilogue left, one [M] plane per part, added in
             // a fixed order (no atomics: the encoder's bytes stay reproducible run to run)
             float row_scale = 1.f;
-            if (stats_in != nullptr) {
+            if (stats_in != nullptr && !splitk) {
                 const int r = m0 + lane;
                 if (r < M) {
                     // all (<= 16) part loads in flight together, then a fixed-order sum
@@ -417,6 +428,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ptx::mbar_wait(&rbar[g], rphase);
                 } else {
                     __syncwarp();  // orders lane 0's wait_group.read before the overwrite of buffer g
+                }
+                if (splitk) {
+                    // float32 partial of this split: row m0 + lane, 64 consecutive columns, straight from the registers
+                    if (m0 + lane < M) {
+                        float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(stats_out) + ((size_t)sp * M + (m0 + lane)) * N + n0 + g * kEpiCols);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            dst[j] = make_float4(__uint_as_float(r0[4 * j]), __uint_as_float(r0[4 * j + 1]), __uint_as_float(r0[4 * j + 2]), __uint_as_float(r0[4 * j + 3]));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            dst[8 + j] = make_float4(__uint_as_float(r1[4 * j]), __uint_as_float(r1[4 * j + 1]), __uint_as_float(r1[4 * j + 2]), __uint_as_float(r1[4 * j + 3]));
+                        }
+                    }
+                    continue;
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -631,7 +657,8 @@ static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
         LL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmemBytes));
         configured = true;
     }
-    const int tiles = (int)((M + kBM * kCtas - 1) / (kBM * kCtas)) * (N / BN);
+    int tiles = (int)((M + kBM * kCtas - 1) / (kBM * kCtas)) * (N / BN);
+    if ((act & 0x10000) && !(act & 0x8000)) tiles *= t_stats_in_parts;  // split-K: (tile, split) work items
     const int workers = num_sms() / kCtas;
     const int grid = (tiles < workers ? tiles : workers) * kCtas;
     cudaLaunchConfig_t cfg = {};
@@ -658,6 +685,7 @@ static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
 // 128 x 256 tiles at M = 12 800 is 300 tiles = 3 rounds for 2.03 rounds of work).  Narrower tiles
 // re-read A more often, hence the small penalty.  CTA pairs (256-row tiles on 74 workers) are
 // preferred whenever the problem has at least one full round of them.
+static bool g_splitk_enabled = true;  // ll_gemm_set_splitk (A/B knob)
 static int g_force_bn = 0;    // test / tuning overrides (ll_gemm_set_tile_n, ll_gemm_set_cta_pair)
 static int g_pair_mode = -1;  // -1 auto, 0 never, 1 always
 
@@ -776,10 +804,66 @@ int gemm_patch_launch(const void *x, const void *W, void *D, int64_t n_images, i
     return gemm_launch_tmaps(ta, tw, td, td, bn, ctas, nullptr, 0, M, N, K, dtype, 0x8000 | (kb_per_channel << 16), stream);
 }
 
+// D[i] = T(sum_s ws[s][i]): adds the float32 partials of a split-K launch, one rounding to the 16-bit result
+template <typename T>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float *__restrict__ ws, int splits, int64_t n8, int64_t plane, T *__restrict__ D)
+{
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (int64_t)gridDim.x * 256) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < splits; ++s) {
+            const float4 a = *reinterpret_cast<const float4 *>(ws + s * plane + i * 8), b = *reinterpret_cast<const float4 *>(ws + s * plane + i * 8 + 4);
+            acc[0] += a.x, acc[1] += a.y, acc[2] += a.z, acc[3] += a.w, acc[4] += b.x, acc[5] += b.y, acc[6] += b.z, acc[7] += b.w;
+        }
+        *reinterpret_cast<uint4 *>(D + i * 8) = Pack8<T>::pack(acc);
+    }
+}
+
+// Shape of a split-K weight-gradient launch: CTA pairs or single CTAs, tile width, number of K splits.  Chosen by a small
+// time model (microseconds) whose constants are the measured per-K-block times of the TN kernel at a 25 600-deep
+// reduction: a 256 x 256 pair tile and a 128 x 128 single-CTA tile both take ~0.47 us per 64-deep K block (the single
+// CTA is bound by its operand feed: 64 FLOP per staged byte against 128 for the pair), so pairs do twice the work per SM
+// whenever the splits can fill 74 of them; every extra split costs one float32 partial of the output, written and read
+// once (L2-resident at these sizes: <= 38 MB).
+struct SplitPlan {
+    int ctas, bn, splits;
+    double us;
+};
+
+static SplitPlan plan_splitk(int Mo, int No, int64_t num_kb, int64_t workspace_bytes)
+{
+    const int sms = num_sms();
+    SplitPlan best = {1, 0, 1, 1e30};
+    for (int ctas = 2; ctas >= 1; --ctas) {
+        if (ctas == 2 && (g_pair_mode == 0 || Mo % 256 != 0)) continue;
+        if (ctas == 1 && g_pair_mode == 1) continue;
+        const int workers = sms / ctas;
+        const int bns[3] = {256, 128, 64};
+        for (int bn : bns) {
+            if (No % bn != 0 || (ctas == 2 && bn == 64)) continue;
+            if (g_force_bn && bn != g_force_bn && No % g_force_bn == 0) continue;
+            // per-K-block time of one work item
+            const double t_kb = ctas == 2 ? (bn == 256 ? 0.47 : 0.30) : (bn == 256 ? 0.70 : bn == 128 ? 0.47 : 0.32);
+            const int64_t tiles = (int64_t)(Mo / (kBM * ctas)) * (No / bn);
+            for (int s = 1; s <= 16 && s <= num_kb; ++s) {
+                if (s > 1 && (int64_t)s * Mo * No * (int64_t)sizeof(float) > workspace_bytes) break;
+                const int64_t rounds = (tiles * s + workers - 1) / workers;
+                double us = (double)rounds * (double)((num_kb + s - 1) / s) * t_kb + 4.0 * (double)rounds;
+                if (s > 1) us += 3.0 + (double)s * Mo * No * 8.0 / 5.0e6;  // reduce launch + partials at ~5 TB/s
+                if (us < best.us - 1e-9) best = {ctas, bn, s, us};
+            }
+        }
+    }
+    return best;
+}
+
+int64_t gemm_tn_workspace_bytes(int Mo, int No) { return 8LL * Mo * No * (int64_t)sizeof(float); }
+
 // D[Mo, No] = A[Kt, Mo]^T @ B[Kt, No]: the weight-gradient contraction dW = dY^T X of a linear layer, with the
 // reduction (token) dimension as the ROWS of both operands, i.e. exactly as the activations and their gradients
 // sit in memory.  Same kernel, act bit 0x2000: MN-major shared-memory descriptors, 64 x 64 TMA boxes.
-int gemm_tn_launch(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, cudaStream_t stream)
+int gemm_tn_launch(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, cudaStream_t stream, void *workspace,
+                   int64_t workspace_bytes)
 {
     LL_REQUIRE(A && B && D, "gemm_tn: null pointer");
     LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "gemm_tn: dtype must be LL_F16 or LL_BF16");
@@ -800,6 +884,28 @@ int gemm_tn_launch(const void *A, const void *B, void *D, int64_t Kt, int Mo, in
     if (rc != LL_OK) return rc;
     const int64_t Kpad = (Kt + kBK - 1) / kBK * kBK;
     LL_REQUIRE(Kpad < (1ll << 31), "gemm_tn: Kt too large");
+    // split-K when the output is a fraction of a round of tiles and the caller lent a workspace: a [768..3072]^2 weight
+    // gradient is 9-36 pair tiles of 256 x 256 for a 25 600-deep reduction
+    if (workspace != nullptr && g_splitk_enabled && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && ((int64_t)Mo * No) % 8 == 0) {
+        const SplitPlan plan = plan_splitk(Mo, No, Kpad / kBK, workspace_bytes);
+        if (plan.bn != 0 && plan.splits > 1) {
+            t_stats_in = nullptr;
+            t_stats_in_parts = plan.splits;
+            t_stats_out = static_cast<float2 *>(workspace);
+            rc = gemm_launch_tmaps(ta, tw, td, td, plan.bn, plan.ctas, nullptr, 0, Mo, No, (int)Kpad, dtype, 0x2000 | 0x10000, stream);
+            t_stats_in_parts = 0;
+            t_stats_out = nullptr;
+            if (rc != LL_OK) return rc;
+            const int64_t n8 = (int64_t)Mo * No / 8;
+            const unsigned grid = (unsigned)std::min<int64_t>((n8 + 255) / 256, 8LL * num_sms());
+            if (dtype == LL_F16)
+                splitk_reduce_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const float *>(workspace), plan.splits, n8, (int64_t)Mo * No, static_cast<__half *>(D));
+            else
+                splitk_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const float *>(workspace), plan.splits, n8, (int64_t)Mo * No, static_cast<__nv_bfloat16 *>(D));
+            LL_LAUNCH_CHECK();
+            return LL_OK;
+        }
+    }
     return gemm_launch_tmaps(ta, tw, td, td, bn, ctas, nullptr, 0, Mo, No, (int)Kpad, dtype, 0x2000, stream);
 }
 
@@ -807,7 +913,21 @@ int gemm_tn_launch(const void *A, const void *B, void *D, int64_t Kt, int Mo, in
 
 extern "C" int ll_gemm_tn(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, ll_stream_t stream)
 {
-    return ll::gemm_tn_launch(A, B, D, Kt, Mo, No, dtype, ll::as_stream(stream));
+    return ll::gemm_tn_launch(A, B, D, Kt, Mo, No, dtype, ll::as_stream(stream), nullptr, 0);
+}
+
+extern "C" int64_t ll_gemm_tn_workspace_bytes(int Mo, int No) { return ll::gemm_tn_workspace_bytes(Mo, No); }
+
+extern "C" int ll_gemm_tn_splitk(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, void *workspace,
+                                 int64_t workspace_bytes, ll_stream_t stream)
+{
+    return ll::gemm_tn_launch(A, B, D, Kt, Mo, No, dtype, ll::as_stream(stream), workspace, workspace_bytes);
+}
+
+extern "C" int ll_gemm_set_splitk(int on)
+{
+    ll::g_splitk_enabled = on != 0;
+    return LL_OK;
 }
 
 extern "C" int ll_gemm_patch_embed(const void *x, const void *W, void *D, int64_t n_images, int N, int res, int patch, int dtype,

@@ -46,10 +46,11 @@ extern "C" int64_t ll_vit_block_act_elems(int64_t batch, int S, int width) { ret
 extern "C" int64_t ll_vit_block_x2_offset_elems(int64_t batch, int S, int width) { return batch * S * (int64_t)width * 15; }
 
 // scratch of one backward call: g_f / g_u [M,4W], g_h2 [M,W], g_x1 [M,W], g_a [M,W], g_qkv [M,3W], g_h1 [M,W], then the four
-// transposed weight copies (12 W^2 elements)
+// transposed weight copies (12 W^2 elements), then the split-K workspace of the weight-gradient GEMMs (4 float32
+// partials of the largest gradient, 4 W^2 elements: 32 W^2 16-bit elements)
 extern "C" int64_t ll_vit_block_backward_scratch_elems(int64_t batch, int S, int width)
 {
-    return batch * S * (int64_t)width * 11 + 12LL * width * width;
+    return batch * S * (int64_t)width * 11 + 12LL * width * width + 32LL * width * width;
 }
 
 extern "C" int ll_vit_block_forward(const ll_vit_block_params_t *w, const void *x_in, void *act, int64_t batch, int S, int heads,
@@ -93,7 +94,9 @@ extern "C" int ll_vit_block_backward(const ll_vit_block_params_t *w, const void 
     uint8_t *cproj_t = p; p += (int64_t)4 * W * W * 2;
     uint8_t *fc_t = p;    p += (int64_t)4 * W * W * 2;
     uint8_t *out_t = p;   p += (int64_t)W * W * 2;
-    uint8_t *in_t = p;
+    uint8_t *in_t = p;    p += (int64_t)3 * W * W * 2;
+    void *ws = p;  // split-K workspace (16-byte aligned: every piece above is a multiple of 128 bytes)
+    const int64_t ws_bytes = 64LL * W * W;
     int rc;
     // W [out, in] -> Wt [in, out]  (transpose_pad(src [R, C]) -> [C, Rpad]; R = out is a multiple of 64 here)
     if ((rc = ll_transpose_pad(w->cproj_w, cproj_t, W, 4 * W, W, stream))) return rc;
@@ -102,20 +105,20 @@ extern "C" int ll_vit_block_backward(const ll_vit_block_params_t *w, const void 
     if ((rc = ll_transpose_pad(w->in_proj_w, in_t, 3 * W, W, 3 * W, stream))) return rc;
     // x2 = x1 + f @ c_proj^T + b
     if ((rc = ll_gemm(g_x, cproj_t, nullptr, nullptr, g_u, M, 4 * W, W, dtype, 0, stream))) return rc;      // g_f
-    if ((rc = ll_gemm_tn(g_x, v.f, g->cproj_w, M, W, 4 * W, dtype, stream))) return rc;
+    if ((rc = ll_gemm_tn_splitk(g_x, v.f, g->cproj_w, M, W, 4 * W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_x, M, W, dtype, g->cproj_b, stream))) return rc;
     if ((rc = ll_quickgelu_backward(v.u, g_u, g_u, M * 4 * (int64_t)W, dtype, stream))) return rc;         // g_u (in place)
     if ((rc = ll_gemm(g_u, fc_t, nullptr, nullptr, g_h2, M, W, 4 * W, dtype, 0, stream))) return rc;
-    if ((rc = ll_gemm_tn(g_u, v.h2, g->fc_w, M, 4 * W, W, dtype, stream))) return rc;
+    if ((rc = ll_gemm_tn_splitk(g_u, v.h2, g->fc_w, M, 4 * W, W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_u, M, 4 * W, dtype, g->fc_b, stream))) return rc;
     if ((rc = ll_layernorm_backward(v.x1, g_h2, w->ln2_w, g_x, g_x1, g->ln2_w, g->ln2_b, M, W, dtype, stream))) return rc;
     // x1 = x + a @ out_proj^T + b
     if ((rc = ll_gemm(g_x1, out_t, nullptr, nullptr, g_a, M, W, W, dtype, 0, stream))) return rc;
-    if ((rc = ll_gemm_tn(g_x1, v.a, g->out_proj_w, M, W, W, dtype, stream))) return rc;
+    if ((rc = ll_gemm_tn_splitk(g_x1, v.a, g->out_proj_w, M, W, W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_x1, M, W, dtype, g->out_proj_b, stream))) return rc;
     if ((rc = ll_attention_backward(v.qkv, g_a, g_qkv, batch, S, heads, dtype, stream))) return rc;
     if ((rc = ll_gemm(g_qkv, in_t, nullptr, nullptr, g_h1, M, W, 3 * W, dtype, 0, stream))) return rc;
-    if ((rc = ll_gemm_tn(g_qkv, v.h1, g->in_proj_w, M, 3 * W, W, dtype, stream))) return rc;
+    if ((rc = ll_gemm_tn_splitk(g_qkv, v.h1, g->in_proj_w, M, 3 * W, W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_qkv, M, 3 * W, dtype, g->in_proj_b, stream))) return rc;
     // dL/dx_in = LN1 backward + the residual branch (g_x1); overwrites g_x, whose old value is dead by now
     if ((rc = ll_layernorm_backward(x_in, g_h1, w->ln1_w, g_x1, g_x, g->ln1_w, g->ln1_b, M, W, dtype, stream))) return rc;

@@ -207,6 +207,49 @@ def test_gemm_tn_weight_gradient_shape(cuda_device, dtype, Kt, Mo, No, pair):
         N.call("ll_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(D), Kt, Mo + 8, No, N.dtype_code(A), N.stream())
 
 
+@pytest.mark.parametrize("pair", [-1, 0, 1])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("Kt,Mo,No", [(25600, 768, 3072), (6400, 3072, 768), (12800, 2304, 768), (2500, 768, 768), (137, 768, 768),
+                                      (640, 128, 64)])
+def test_gemm_tn_splitk(cuda_device, dtype, Kt, Mo, No, pair):
+    """ll_gemm_tn_splitk: the weight-gradient contraction with the reduction split over otherwise idle SMs (float32
+    partials in a caller-lent workspace, one rounding in the reduce kernel).  Against torch in fp32, against the
+    single-pass ll_gemm_tn (same operands: equal up to the summation order, i.e. one 16-bit ulp), reproducible run
+    to run (no atomics), and identical to the single pass when no workspace is lent."""
+    from lossyless_b200 import _native as N
+
+    if pair == 1 and (Mo % 256 or No % 128):
+        pytest.skip("forced CTA pairs need 256-row / 128-column output tiles")
+    g = torch.Generator(device=cuda_device).manual_seed(Kt + Mo + 1)
+    A = torch.randn(Kt, Mo, generator=g, device=cuda_device).to(dtype)
+    B = torch.randn(Kt, No, generator=g, device=cuda_device).to(dtype)
+    ws_bytes = N.load().ll_gemm_tn_workspace_bytes(Mo, No)
+    assert ws_bytes >= 4 * Mo * No
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda_device)
+    D, D2, D1, D0 = (torch.full((Mo, No), float("nan"), dtype=dtype, device=cuda_device) for _ in range(4))
+    N.call("ll_gemm_set_cta_pair", pair)
+    try:
+        N.call("ll_gemm_tn_splitk", N.ptr(A), N.ptr(B), N.ptr(D), Kt, Mo, No, N.dtype_code(A), N.ptr(ws), ws_bytes, N.stream())
+        ws.fill_(0xFF)  # NaN partials: every partial the reduce reads must have been rewritten
+        N.call("ll_gemm_tn_splitk", N.ptr(A), N.ptr(B), N.ptr(D2), Kt, Mo, No, N.dtype_code(A), N.ptr(ws), ws_bytes, N.stream())
+        N.call("ll_gemm_tn", N.ptr(A), N.ptr(B), N.ptr(D1), Kt, Mo, No, N.dtype_code(A), N.stream())
+        N.call("ll_gemm_tn_splitk", N.ptr(A), N.ptr(B), N.ptr(D0), Kt, Mo, No, N.dtype_code(A), None, 0, N.stream())
+        N.call("ll_gemm_set_splitk", 0)
+        D3 = torch.full_like(D, float("nan"))
+        N.call("ll_gemm_tn_splitk", N.ptr(A), N.ptr(B), N.ptr(D3), Kt, Mo, No, N.dtype_code(A), N.ptr(ws), ws_bytes, N.stream())
+    finally:
+        N.call("ll_gemm_set_cta_pair", -1)
+        N.call("ll_gemm_set_splitk", 1)
+    ref = A.float().t() @ B.float()
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-3
+    assert torch.isfinite(D.float()).all()
+    assert (D.float() - ref).abs().max().item() < tol * ref.abs().max().item()
+    assert torch.equal(D, D2)
+    assert torch.equal(D0, D1) and torch.equal(D3, D1)
+    # float32 partials added once are at least as close to the fp32 result as the single pass
+    assert (D.float() - ref).abs().mean().item() <= 1.05 * (D1.float() - ref).abs().mean().item() + 1e-6
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("n", [1, 2, 3, 130, 301])
 def test_gemm_patch_embed_reads_images_directly(cuda_device, dtype, n):

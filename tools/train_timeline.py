@@ -20,7 +20,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--splitk", type=int, default=1, help="0: weight gradients in one pass (A/B of ll_gemm_tn_splitk)")
+    ap.add_argument("--brief", action="store_true", help="skip the host-side profiler table")
     args = ap.parse_args()
+    from lossyless_b200 import _native
+
+    _native.call("ll_gemm_set_splitk", args.splitk)
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     hp = default_clip_hparams(distortion="BINCE", beta=1e-2, max_steps=1000, n_data=50000, is_frozen=False)
@@ -93,7 +98,8 @@ def main():
         a[1] += x.time_range.end - x.time_range.start
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
         print(f"{t / 1e3 / args.steps:9.3f} ms {c // args.steps:5d}  {k}")
-    print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=35, max_name_column_width=60))
+    if not args.brief:
+        print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=35, max_name_column_width=60))
 
 
 if __name__ == "__main__":
