@@ -225,6 +225,10 @@ int ll_vit_block_forward(const ll_vit_block_params_t *w, const void *x_in, void 
 int ll_vit_block_backward(const ll_vit_block_params_t *w, const void *x_in, const void *act, void *g_x,
                           void *scratch, const ll_vit_block_grads_t *g, int64_t batch, int S, int heads,
                           int width, int dtype, ll_stream_t stream);
+/* Which fusions ll_vit_block_forward / ll_vit_block_backward use (A/B knob, tests): bit 0 = QuickGELU backward inside
+ * the c_proj data-gradient GEMM's epilogue (ll_gemm act 2) instead of a separate ll_quickgelu_backward pass.
+ * Default: all on.  Returns the previous mask. */
+int ll_vit_block_set_fusion(int mask);
 
 /* ---------------------------------------------- device: flat-buffer optimiser (fine-tuning path) */
 
@@ -339,7 +343,9 @@ int ll_attention_set_impl(int impl);
 
 /* Stand-alone GEMM entry (tests, micro-benchmarks):  D[M,N] = act(A[M,K] @ W[N,K]^T + bias)
  * (+ residual), A/W/D/residual in `dtype`, bias float32 or NULL, act 0 = none,
- * 1 = QuickGELU x*sigmoid(1.702x).  K % 64 == 0, N % 64 == 0. */
+ * 1 = QuickGELU x*sigmoid(1.702x), 2 = D = (A @ W^T + bias) * QuickGELU'(residual): the adjoint of the activation
+ * fused into the data-gradient GEMM that produces its incoming gradient (residual = the pre-activation; required).
+ * K % 64 == 0, N % 64 == 0. */
 int ll_gemm(const void *A, const void *W, const float *bias, const void *residual, void *D,
             int64_t M, int N, int K, int dtype, int act, ll_stream_t stream);
 /* GEMM with the fused-LayerNorm epilogue operands the encoder uses (nn.LayerNorm of

@@ -109,6 +109,7 @@ _SIGNATURES = {
     "ll_gemm_tn_workspace_bytes": (c_int64, [c_int, c_int]),
     "ll_gemm_tn_splitk": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, c_int64, _P]),
     "ll_gemm_set_splitk": (c_int, [c_int]),
+    "ll_vit_block_set_fusion": (c_int, [c_int]),
     "ll_gemm_patch_embed": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "ll_vit_set_direct_patch": (c_int, [_P, c_int]),
     "ll_gemm_ln": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),

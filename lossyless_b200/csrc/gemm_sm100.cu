@@ -115,6 +115,15 @@ __device__ __forceinline__ float quick_gelu(float x)
     return fmaf(hx, t, hx);
 }
 
+// d/dx [x sigmoid(1.702 x)] = s + 1.702 x s (1 - s) with s = 0.5 (1 + tanh(0.851 x)): one MUFU op per element
+__device__ __forceinline__ float quick_gelu_grad(float x)
+{
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+    const float sg = fmaf(0.5f, t, 0.5f);
+    return fmaf(1.702f * x * sg, 1.f - sg, sg);
+}
+
 // QuickGELU on two fp16 values at once, AFTER the rounding to the output type: 2 HMUL2 + 1 MUFU (tanh.approx.f16x2)
 // + 1 HFMA2 per PAIR instead of 3 FP32 ops + 1 MUFU per ELEMENT.  The c_fc epilogue (K = 768: 3.3 us of MMA per
 // tile) was the one epilogue that did not hide behind the tensor pipe (ncu: 66 % tensor-active vs 75-79 % for the
@@ -475,8 +484,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (has_residual) {
                         float rf[8];
                         Pack8<T>::unpack(*slot, rf);
+                        if ((act & 0xff) == 2) {
+                            // QuickGELU backward fused into the data-gradient GEMM of c_proj: the "residual" tile is
+                            // the pre-activation u, the result g_u = g_f * QuickGELU'(u)
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] += rf[e];
+                            for (int e = 0; e < 8; ++e) f[e] *= quick_gelu_grad(rf[e]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] += rf[e];
+                        }
                     }
                     const uint4 packed = Pack8<T>::pack(f);
                     if (!(act & 0x200)) *slot = packed;
@@ -765,6 +781,7 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
     LL_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0 && (!residual || (reinterpret_cast<uintptr_t>(residual) & 15) == 0) &&
                    (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
                "gemm: D / residual / bias must be 16-byte aligned");
+    LL_REQUIRE((act & 0xff) != 2 || (residual != nullptr && residual != D), "gemm: act 2 (QuickGELU backward) needs the pre-activation as `residual`, distinct from D");
     int bn = 0, ctas = 1;
     pick_tile(M, N, bn, ctas);
     CUtensorMap ta, tw, td, tr;

@@ -237,74 +237,105 @@ quickgelu_backward_kernel(const T *__restrict__ u, const T *__restrict__ g_f, T 
 // h = (x - mean) * rstd * gamma + beta (clip/model.py LayerNorm: fp32 statistics, eps 1e-5).
 //   g_x = g_res + rstd * (g_h*gamma - mean_c(g_h*gamma) - xhat * mean_c(g_h*gamma*xhat))
 //   g_gamma += sum_rows g_h * xhat,  g_beta += sum_rows g_h
-// One warp per row (grid-stride); a lane owns 8 contiguous columns in each 256-column block.
+// One warp per row (grid-stride); a lane owns 8 contiguous columns in each 256-column block.  The row's three inputs
+// (x, g_h, g_res) stay PACKED in registers (9 x 16 bytes per lane, all loads in flight together) and are unpacked again
+// in each of the four passes over the row -- the float copies of the first version took the kernel to 190 registers,
+// one 256-thread CTA per SM, and 2.3 TB/s; at <= 128 registers two CTAs are resident.
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4 &raw, float *out)
+{
+    const T *e = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[k] = to_float<T>(e[k]);
+}
+
 template <typename T, int NB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NB <= 3 ? 2 : 1)
 layernorm_backward_kernel(const T *__restrict__ x, const T *__restrict__ g_h, const float *__restrict__ gamma,
                           const T *__restrict__ g_res, T *__restrict__ g_x, float *__restrict__ g_gamma,
                           float *__restrict__ g_beta, int64_t rows)
 {
     constexpr int W = NB * 256;
+    // gamma permuted so that a lane's two float4 pieces of a block are conflict-free: [block][half][lane][4]
+    __shared__ float4 s_gam[NB * 2 * 32];
     __shared__ float s_gg[W], s_gb[W];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < W; i += 256) s_gg[i] = 0.f, s_gb[i] = 0.f;
+    for (int i = threadIdx.x; i < NB * 64; i += 256) {
+        const int b = i / 64, half = (i / 32) & 1, l = i & 31;
+        s_gam[i] = *reinterpret_cast<const float4 *>(gamma + b * 256 + l * 8 + half * 4);
+    }
     __syncthreads();
-    float gam[NB][8], acc_g[NB][8], acc_b[NB][8];
+    float acc_g[NB][8], acc_b[NB][8];
 #pragma unroll
     for (int b = 0; b < NB; ++b)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            gam[b][k] = gamma[b * 256 + lane * 8 + k];
-            acc_g[b][k] = 0.f;
-            acc_b[b][k] = 0.f;
-        }
+        for (int k = 0; k < 8; ++k) acc_g[b][k] = 0.f, acc_b[b][k] = 0.f;
     const int64_t warps_total = (int64_t)gridDim.x * 8;
     for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < rows; r += warps_total) {
-        float xv[NB][8], gv[NB][8];
-        float sum = 0.f;
+        uint4 xr[NB], gr[NB], rr[NB];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const int64_t at = r * W + b * 256 + lane * 8;
-            load8<T>(x + at, xv[b]);
-            load8<T>(g_h + at, gv[b]);
+            xr[b] = *reinterpret_cast<const uint4 *>(x + at);
+            gr[b] = *reinterpret_cast<const uint4 *>(g_h + at);
+            rr[b] = g_res != nullptr ? *reinterpret_cast<const uint4 *>(g_res + at) : make_uint4(0, 0, 0, 0);
+        }
+        float sum = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sum += xv[b][k];
+        for (int b = 0; b < NB; ++b) {
+            float xv[8];
+            unpack8<T>(xr[b], xv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum += xv[k];
         }
         const float mean = warp_sum(sum) * (1.f / W);
         float var = 0.f;
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
+        for (int b = 0; b < NB; ++b) {
+            float xv[8];
+            unpack8<T>(xr[b], xv);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                xv[b][k] -= mean;
-                var += xv[b][k] * xv[b][k];
+                const float d = xv[k] - mean;
+                var += d * d;
             }
+        }
         const float rstd = rsqrtf(warp_sum(var) * (1.f / W) + 1e-5f);
         float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-        for (int b = 0; b < NB; ++b)
+        for (int b = 0; b < NB; ++b) {
+            float xv[8], gv[8];
+            unpack8<T>(xr[b], xv);
+            unpack8<T>(gr[b], gv);
+            const float4 ga = s_gam[(b * 2) * 32 + lane], gb = s_gam[(b * 2 + 1) * 32 + lane];
+            const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                xv[b][k] *= rstd;  // xhat
-                acc_g[b][k] += gv[b][k] * xv[b][k];
-                acc_b[b][k] += gv[b][k];
-                gv[b][k] *= gam[b][k];  // d xhat
-                m1 += gv[b][k];
-                m2 += gv[b][k] * xv[b][k];
+                const float xh = (xv[k] - mean) * rstd;
+                acc_g[b][k] += gv[k] * xh;
+                acc_b[b][k] += gv[k];
+                const float d = gv[k] * gam[k];  // d xhat
+                m1 += d;
+                m2 += d * xh;
             }
+        }
         m1 = warp_sum(m1) * (1.f / W);
         m2 = warp_sum(m2) * (1.f / W);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            const int64_t at = r * W + b * 256 + lane * 8;
-            float res[8], g[8];
-            if (g_res != nullptr) load8<T>(g_res + at, res);
+            float xv[8], gv[8], res[8], g[8];
+            unpack8<T>(xr[b], xv);
+            unpack8<T>(gr[b], gv);
+            unpack8<T>(rr[b], res);
+            const float4 ga = s_gam[(b * 2) * 32 + lane], gb = s_gam[(b * 2 + 1) * 32 + lane];
+            const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                g[k] = rstd * (gv[b][k] - m1 - xv[b][k] * m2);
-                if (g_res != nullptr) g[k] += res[k];
+                const float xh = (xv[k] - mean) * rstd;
+                g[k] = rstd * (gv[k] * gam[k] - m1 - xh * m2) + res[k];
             }
-            store8<T>(g_x + at, g);
+            store8<T>(g_x + r * W + b * 256 + lane * 8, g);
         }
     }
 #pragma unroll
@@ -883,7 +914,7 @@ template <typename T>
 static int launch_ln_bwd(const void *x, const void *g_h, const float *gamma, const void *g_res, void *g_x, float *g_gamma,
                          float *g_beta, int64_t rows, int width, cudaStream_t s)
 {
-    const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)num_sms() * 2);
+    const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)num_sms() * 2);  // two resident CTAs per SM
     auto X = static_cast<const T *>(x), G = static_cast<const T *>(g_h), R = static_cast<const T *>(g_res);
     auto O = static_cast<T *>(g_x);
     switch (width) {

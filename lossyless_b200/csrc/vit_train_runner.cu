@@ -39,7 +39,16 @@ inline ActView act_view(void *act, int64_t M, int W)
     return v;
 }
 
+int g_fusion = 0x7fffffff;  // ll_vit_block_set_fusion
+
 }  // namespace
+
+extern "C" int ll_vit_block_set_fusion(int mask)
+{
+    const int old = g_fusion;
+    g_fusion = mask;
+    return old;
+}
 
 extern "C" int64_t ll_vit_block_act_elems(int64_t batch, int S, int width) { return batch * S * (int64_t)width * 16; }
 
@@ -104,10 +113,13 @@ extern "C" int ll_vit_block_backward(const ll_vit_block_params_t *w, const void 
     if ((rc = ll_transpose_pad(w->out_proj_w, out_t, W, W, W, stream))) return rc;
     if ((rc = ll_transpose_pad(w->in_proj_w, in_t, 3 * W, W, 3 * W, stream))) return rc;
     // x2 = x1 + f @ c_proj^T + b
-    if ((rc = ll_gemm(g_x, cproj_t, nullptr, nullptr, g_u, M, 4 * W, W, dtype, 0, stream))) return rc;      // g_f
+    // g_u = (g_x @ c_proj) * QuickGELU'(u): the activation's adjoint rides in the GEMM's epilogue (u arrives as the
+    // "residual" tile); unfused: g_f first, then a separate elementwise pass in place
+    const bool fuse_gelu_bwd = (g_fusion & 1) != 0;
+    if ((rc = ll_gemm(g_x, cproj_t, nullptr, fuse_gelu_bwd ? v.u : nullptr, g_u, M, 4 * W, W, dtype, fuse_gelu_bwd ? 2 : 0, stream))) return rc;
     if ((rc = ll_gemm_tn_splitk(g_x, v.f, g->cproj_w, M, W, 4 * W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_x, M, W, dtype, g->cproj_b, stream))) return rc;
-    if ((rc = ll_quickgelu_backward(v.u, g_u, g_u, M * 4 * (int64_t)W, dtype, stream))) return rc;         // g_u (in place)
+    if (!fuse_gelu_bwd && (rc = ll_quickgelu_backward(v.u, g_u, g_u, M * 4 * (int64_t)W, dtype, stream))) return rc;  // in place
     if ((rc = ll_gemm(g_u, fc_t, nullptr, nullptr, g_h2, M, W, 4 * W, dtype, 0, stream))) return rc;
     if ((rc = ll_gemm_tn_splitk(g_u, v.h2, g->fc_w, M, 4 * W, W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_u, M, 4 * W, dtype, g->fc_b, stream))) return rc;

@@ -272,3 +272,23 @@ def test_gemm_patch_embed_reads_images_directly(cuda_device, dtype, n):
     assert float(D[:, 7].float().abs().max()) == 0.0 and float(D[:, :, 7].float().abs().max()) == 0.0
     A = x.reshape(n, 3, 7, 32, 7, 32).permute(0, 2, 4, 1, 3, 5).reshape(n * 49, 3072).contiguous()
     assert torch.equal(_gemm(A, W.reshape(768, 3072)).reshape(n, 7, 7, 768), D[:, :7, :7])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(2500, 3072, 768), (25600, 3072, 768), (300, 256, 128)])
+def test_gemm_quickgelu_backward_epilogue(cuda_device, dtype, M, N, K):
+    """act 2: D = (A @ W^T) * QuickGELU'(u) with the pre-activation u arriving as the residual operand -- the adjoint
+    of CLIP's QuickGELU fused into the data-gradient GEMM of c_proj.  Against fp32 torch autograd."""
+    g = torch.Generator(device=cuda_device).manual_seed(M + N)
+    A = torch.randn(M, K, generator=g, device=cuda_device).to(dtype)
+    W = (torch.randn(N, K, generator=g, device=cuda_device) * K ** -0.5).to(dtype)
+    u = (2.0 * torch.randn(M, N, generator=g, device=cuda_device)).to(dtype)
+    D = _gemm(A, W, None, u, act=2)
+    uf = u.float().requires_grad_(True)
+    (uf * torch.sigmoid(1.702 * uf)).backward(A.float() @ W.float().t())
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 3e-3
+    assert (D.float() - uf.grad).abs().max().item() < tol * uf.grad.abs().max().item()
+    from lossyless_b200 import _native as Nn
+
+    with pytest.raises(Nn.NativeError):
+        _gemm(A, W, None, None, act=2)

@@ -376,21 +376,52 @@ def test_fit_with_unfrozen_tower_uses_flat_optimizer(cuda_device):
 def test_native_block_runner_equals_python_sequencing(cuda_device, monkeypatch):
     """ll_vit_block_forward / ll_vit_block_backward (one native call per block and direction) against the same kernels
     sequenced from Python: identical output, identical matrix gradients, vector gradients equal up to atomics order."""
+    from lossyless_b200 import _native as N
     from lossyless_b200 import clip_vit
 
     out = {}
-    for native in (True, False):
-        monkeypatch.setattr(clip_vit, "NATIVE_BLOCKS", native)
-        vit, sd, cfg = _trainable_vit(cuda_device, 3, torch.bfloat16)
-        gen = torch.Generator().manual_seed(11)
-        x = torch.randn(5, 3, 224, 224, generator=gen).to(cuda_device)
-        r = torch.randn(5, 512, generator=gen).to(cuda_device)
-        z = vit(x)
-        (z * r).sum().backward()
-        out[native] = (z.detach().clone(), {n: p.grad.clone() for n, p in vit.named_parameters()})
+    old_mask = N.load().ll_vit_block_set_fusion(0)  # the Python sequencing has no fused epilogues: compare like with like
+    try:
+        for native in (True, False):
+            monkeypatch.setattr(clip_vit, "NATIVE_BLOCKS", native)
+            vit, sd, cfg = _trainable_vit(cuda_device, 3, torch.bfloat16)
+            gen = torch.Generator().manual_seed(11)
+            x = torch.randn(5, 3, 224, 224, generator=gen).to(cuda_device)
+            r = torch.randn(5, 512, generator=gen).to(cuda_device)
+            z = vit(x)
+            (z * r).sum().backward()
+            out[native] = (z.detach().clone(), {n: p.grad.clone() for n, p in vit.named_parameters()})
+    finally:
+        N.load().ll_vit_block_set_fusion(old_mask)
     assert torch.equal(out[True][0], out[False][0])
     for n, g in out[True][1].items():
         if clip_vit._is_matrix(n):
             assert torch.equal(g, out[False][1][n]), n
         else:
             assert _rel(g, out[False][1][n]) < 1e-4, n
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_block_runner_fusions_match_unfused(cuda_device, dtype):
+    """The native block runner with its fused epilogues (QuickGELU backward inside the c_proj data-gradient GEMM, ...)
+    against the same runner with every fusion off: same output, gradients equal up to the 16-bit rounding of the
+    intermediates that no longer exist."""
+    from lossyless_b200 import _native as N
+
+    out = {}
+    for mask in (0x7FFFFFFF, 0):
+        old_mask = N.load().ll_vit_block_set_fusion(mask)
+        try:
+            vit, sd, cfg = _trainable_vit(cuda_device, 3, dtype)
+            gen = torch.Generator().manual_seed(12)
+            x = torch.randn(6, 3, 224, 224, generator=gen).to(cuda_device)
+            r = torch.randn(6, 512, generator=gen).to(cuda_device)
+            z = vit(x)
+            (z * r).sum().backward()
+            out[mask] = (z.detach().clone(), {n: p.grad.float().clone() for n, p in vit.named_parameters()})
+        finally:
+            N.load().ll_vit_block_set_fusion(old_mask)
+    assert (out[0][0].float() - out[0x7FFFFFFF][0].float()).abs().max().item() < (3e-2 if dtype == torch.bfloat16 else 4e-3)
+    tol = 2e-2 if dtype == torch.bfloat16 else 3e-3
+    for n, g in out[0][1].items():
+        assert _rel(out[0x7FFFFFFF][1][n], g) < tol, n
