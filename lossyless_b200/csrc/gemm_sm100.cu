@@ -826,6 +826,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float *__restrict__ ws, int splits, int64_t n8, int64_t plane, T *__restrict__ D)
 {
+    pdl_wait();
+    pdl_launch_dependents();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n8; i += (int64_t)gridDim.x * 256) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int s = 0; s < splits; ++s) {
@@ -916,10 +918,9 @@ int gemm_tn_launch(const void *A, const void *B, void *D, int64_t Kt, int Mo, in
             const int64_t n8 = (int64_t)Mo * No / 8;
             const unsigned grid = (unsigned)std::min<int64_t>((n8 + 255) / 256, 8LL * num_sms());
             if (dtype == LL_F16)
-                splitk_reduce_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const float *>(workspace), plan.splits, n8, (int64_t)Mo * No, static_cast<__half *>(D));
+                LL_CUDA_CHECK(launch_pdl(splitk_reduce_kernel<__half>, dim3(grid), dim3(256), 0, stream, static_cast<const float *>(workspace), plan.splits, n8, (int64_t)Mo * No, static_cast<__half *>(D)));
             else
-                splitk_reduce_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const float *>(workspace), plan.splits, n8, (int64_t)Mo * No, static_cast<__nv_bfloat16 *>(D));
-            LL_LAUNCH_CHECK();
+                LL_CUDA_CHECK(launch_pdl(splitk_reduce_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, static_cast<const float *>(workspace), plan.splits, n8, (int64_t)Mo * No, static_cast<__nv_bfloat16 *>(D)));
             return LL_OK;
         }
     }

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256)
 transpose_pad_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int64_t R, int C, int64_t Rpad,
                      float *__restrict__ colsum)
 {
+    pdl_wait();  // programmatic dependent launch: nothing of global memory is touched before the predecessor is complete
+    pdl_launch_dependents();
     __shared__ uint16_t tile[64][66];
     const int64_t r0 = (int64_t)blockIdx.y * 64;
     const int c0 = blockIdx.x * 64;
@@ -128,6 +130,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(const T *__restrict__ src, int64_t R, int C, int rows_per_cta, float *__restrict__ out)
 {
+    pdl_wait();  // programmatic dependent launch: nothing of global memory is touched before the predecessor is complete
+    pdl_launch_dependents();
     __shared__ float part[8][256 + 8];
     const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 256 + cg * 8;
@@ -168,6 +172,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 quickgelu_forward_kernel(const T *__restrict__ u, T *__restrict__ f, int64_t n)
 {
+    pdl_wait();  // programmatic dependent launch: nothing of global memory is touched before the predecessor is complete
+    pdl_launch_dependents();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n8 = n / 8;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,6 +204,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 quickgelu_backward_kernel(const T *__restrict__ u, const T *__restrict__ g_f, T *__restrict__ g_u, int64_t n)
 {
+    pdl_wait();  // programmatic dependent launch: nothing of global memory is touched before the predecessor is complete
+    pdl_launch_dependents();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n8 = n / 8;
     // d/dx [x s(1.702 x)] = s + 1.702 x s (1 - s)
@@ -261,6 +269,8 @@ layernorm_backward_kernel(const T *__restrict__ x, const T *__restrict__ g_h, co
     __shared__ float s_gg[W], s_gb[W];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < W; i += 256) s_gg[i] = 0.f, s_gb[i] = 0.f;
+    pdl_wait();
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < NB * 64; i += 256) {
         const int b = i / 64, half = (i / 32) & 1, l = i & 31;
         s_gam[i] = *reinterpret_cast<const float4 *>(gamma + b * 256 + l * 8 + half * 4);
@@ -712,6 +722,8 @@ attention_backward_ldsm_kernel(const T *__restrict__ qkv, const T *__restrict__ 
     const int64_t row0 = (int64_t)img * S;
     const int ld = 3 * H * kAbD, ldo = H * kAbD;
     const float scale = 0.125f;
+    pdl_wait();
+    pdl_launch_dependents();
 
     // stage q, k, v, dO with 16-byte accesses (8 chunks of 8 elements per row); token rows >= S are zero
     for (int i = tid; i < 64 * 8; i += 128) {
@@ -857,7 +869,7 @@ extern "C" int ll_transpose_pad(const void *src, void *dst, int64_t R, int C, in
     const bool fast = (C % 2 == 0) && (Rpad % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0;
     if (fast) {
         dim3 grid((unsigned)((C + 63) / 64), (unsigned)((Rpad + 63) / 64));
-        transpose_pad_kernel<__half, false><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), R, C, Rpad, nullptr);
+        LL_CUDA_CHECK(launch_pdl(transpose_pad_kernel<__half, false>, grid, dim3(256), 0, as_stream(stream), static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), R, C, Rpad, (float *)nullptr));
     } else {
         dim3 grid((unsigned)((C + 31) / 32), (unsigned)((Rpad + 31) / 32));
         transpose_pad_scalar_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint16_t *>(src), static_cast<uint16_t *>(dst), R, C, Rpad);
@@ -873,8 +885,8 @@ extern "C" int ll_colsum(const void *src, int64_t R, int C, int dtype, float *ou
     if (C % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         const int rows_per_cta = 64;
         dim3 grid((unsigned)((C + 255) / 256), (unsigned)((R + rows_per_cta - 1) / rows_per_cta));
-        LL_DISPATCH_16(dtype, (colsum_vec_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half *>(src), R, C, rows_per_cta, out)),
-                       (colsum_vec_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(src), R, C, rows_per_cta, out)), "colsum");
+        LL_DISPATCH_16(dtype, LL_CUDA_CHECK(launch_pdl(colsum_vec_kernel<__half>, grid, dim3(256), 0, s, static_cast<const __half *>(src), R, C, rows_per_cta, out)),
+                       LL_CUDA_CHECK(launch_pdl(colsum_vec_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, static_cast<const __nv_bfloat16 *>(src), R, C, rows_per_cta, out)), "colsum");
         LL_LAUNCH_CHECK();
         return LL_OK;
     }
@@ -892,8 +904,8 @@ extern "C" int ll_quickgelu_forward(const void *u, void *f, int64_t n, int dtype
     LL_REQUIRE(((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(f)) & 15) == 0, "quickgelu_forward: tensors must be 16-byte aligned");
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n / 8 + 255) / 256, (int64_t)num_sms() * 16));
     cudaStream_t s = as_stream(stream);
-    LL_DISPATCH_16(dtype, (quickgelu_forward_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half *>(u), static_cast<__half *>(f), n)),
-                   (quickgelu_forward_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(u), static_cast<__nv_bfloat16 *>(f), n)), "quickgelu_forward");
+    LL_DISPATCH_16(dtype, LL_CUDA_CHECK(launch_pdl(quickgelu_forward_kernel<__half>, dim3(grid), dim3(256), 0, s, static_cast<const __half *>(u), static_cast<__half *>(f), n)),
+                   LL_CUDA_CHECK(launch_pdl(quickgelu_forward_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16 *>(u), static_cast<__nv_bfloat16 *>(f), n)), "quickgelu_forward");
     LL_LAUNCH_CHECK();
     return LL_OK;
 }
@@ -904,8 +916,8 @@ extern "C" int ll_quickgelu_backward(const void *u, const void *g_f, void *g_u, 
     LL_REQUIRE(((reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(g_f) | reinterpret_cast<uintptr_t>(g_u)) & 15) == 0, "quickgelu_backward: tensors must be 16-byte aligned");
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n / 8 + 255) / 256, (int64_t)num_sms() * 16));
     cudaStream_t s = as_stream(stream);
-    LL_DISPATCH_16(dtype, (quickgelu_backward_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half *>(u), static_cast<const __half *>(g_f), static_cast<__half *>(g_u), n)),
-                   (quickgelu_backward_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(u), static_cast<const __nv_bfloat16 *>(g_f), static_cast<__nv_bfloat16 *>(g_u), n)), "quickgelu_backward");
+    LL_DISPATCH_16(dtype, LL_CUDA_CHECK(launch_pdl(quickgelu_backward_kernel<__half>, dim3(grid), dim3(256), 0, s, static_cast<const __half *>(u), static_cast<const __half *>(g_f), static_cast<__half *>(g_u), n)),
+                   LL_CUDA_CHECK(launch_pdl(quickgelu_backward_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16 *>(u), static_cast<const __nv_bfloat16 *>(g_f), static_cast<__nv_bfloat16 *>(g_u), n)), "quickgelu_backward");
     LL_LAUNCH_CHECK();
     return LL_OK;
 }
@@ -918,9 +930,9 @@ static int launch_ln_bwd(const void *x, const void *g_h, const float *gamma, con
     auto X = static_cast<const T *>(x), G = static_cast<const T *>(g_h), R = static_cast<const T *>(g_res);
     auto O = static_cast<T *>(g_x);
     switch (width) {
-        case 512: layernorm_backward_kernel<T, 2><<<grid, 256, 0, s>>>(X, G, gamma, R, O, g_gamma, g_beta, rows); break;
-        case 768: layernorm_backward_kernel<T, 3><<<grid, 256, 0, s>>>(X, G, gamma, R, O, g_gamma, g_beta, rows); break;
-        case 1024: layernorm_backward_kernel<T, 4><<<grid, 256, 0, s>>>(X, G, gamma, R, O, g_gamma, g_beta, rows); break;
+        case 512: LL_CUDA_CHECK(launch_pdl(layernorm_backward_kernel<T, 2>, dim3(grid), dim3(256), 0, s, X, G, gamma, R, O, g_gamma, g_beta, rows)); break;
+        case 768: LL_CUDA_CHECK(launch_pdl(layernorm_backward_kernel<T, 3>, dim3(grid), dim3(256), 0, s, X, G, gamma, R, O, g_gamma, g_beta, rows)); break;
+        case 1024: LL_CUDA_CHECK(launch_pdl(layernorm_backward_kernel<T, 4>, dim3(grid), dim3(256), 0, s, X, G, gamma, R, O, g_gamma, g_beta, rows)); break;
         default: return fail(LL_ERR_INVALID, "layernorm_backward: width %d not in {512, 768, 1024}", width);
     }
     LL_LAUNCH_CHECK();
@@ -960,8 +972,8 @@ extern "C" int ll_attention_backward(const void *qkv, const void *g_out, void *g
             attr3_set = true;
         }
         LL_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(g_out)) & 15) == 0, "attention_backward: qkv / g_out must be 16-byte aligned");
-        LL_DISPATCH_16(dtype, (attention_backward_ldsm_kernel<__half><<<grid, 128, kAlSmem, s>>>(static_cast<const __half *>(qkv), static_cast<const __half *>(g_out), static_cast<__half *>(g_qkv), S, H)),
-                       (attention_backward_ldsm_kernel<__nv_bfloat16><<<grid, 128, kAlSmem, s>>>(static_cast<const __nv_bfloat16 *>(qkv), static_cast<const __nv_bfloat16 *>(g_out), static_cast<__nv_bfloat16 *>(g_qkv), S, H)), "attention_backward");
+        LL_DISPATCH_16(dtype, LL_CUDA_CHECK(launch_pdl(attention_backward_ldsm_kernel<__half>, dim3(grid), dim3(128), (size_t)kAlSmem, s, static_cast<const __half *>(qkv), static_cast<const __half *>(g_out), static_cast<__half *>(g_qkv), S, H)),
+                       LL_CUDA_CHECK(launch_pdl(attention_backward_ldsm_kernel<__nv_bfloat16>, dim3(grid), dim3(128), (size_t)kAlSmem, s, static_cast<const __nv_bfloat16 *>(qkv), static_cast<const __nv_bfloat16 *>(g_out), static_cast<__nv_bfloat16 *>(g_qkv), S, H)), "attention_backward");
         LL_LAUNCH_CHECK();
         return LL_OK;
     }

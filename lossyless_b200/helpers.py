@@ -21,17 +21,22 @@ STDS = dict(clip=[0.26862954, 0.26130258, 0.27577711])
 
 
 class Timer:
-    """Context manager measuring wall time; synchronises CUDA on both edges (the reference does
-    not, which is only correct because its `.tolist()` synchronises)."""
+    """Context manager measuring wall time.  With ``sync=True`` CUDA is synchronised on both edges, so the duration is
+    the device time of the enclosed work (the reference does not synchronise, which is only correct where a
+    ``.tolist()`` inside the region does it for it).  ``sync=False`` is the reference's plain host timer: a training
+    step must not drain the device twice for a duration nobody reads."""
+
+    def __init__(self, sync=True):
+        self.sync = sync and torch.cuda.is_available()
 
     def __enter__(self):
-        if torch.cuda.is_available():
+        if self.sync:
             torch.cuda.synchronize()
         self.start = time.perf_counter()
         return self
 
     def __exit__(self, *args):
-        if torch.cuda.is_available():
+        if self.sync:
             torch.cuda.synchronize()
         self.end = time.perf_counter()
         self.duration = self.end - self.start

@@ -84,7 +84,9 @@ class LearnableCompressor(nn.Module):
     def step(self, batch, is_rate_only=False):
         x, targets = batch
         self._view_cache = None
-        with Timer() as encoder_timer:
+        # encoder_time is only reported next to the real coder's n_bits (evaluation): a training step keeps the host
+        # running ahead of the device instead of draining it on both sides of the encoder
+        with Timer(sync=not self.training) as encoder_timer:
             x_pos = targets[1] if isinstance(targets, (tuple, list)) and len(targets) > 1 else None
             if not is_rate_only and self._can_batch_views(x, x_pos):
                 # the contrastive distortion encodes the positive view through `parent(x_pos)` later in this step

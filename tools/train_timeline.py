@@ -57,8 +57,8 @@ def main():
 
     def show(message, category, filename, lineno, file=None, line=None):
         if "synchroniz" in str(message):
-            st = [f for f in traceback.extract_stack() if "/lossyless_b200/" in f.filename or "/tools/" in f.filename]
-            sites[" <- ".join(f"{os.path.basename(f.filename)}:{f.lineno}" for f in reversed(st[-4:]))] += 1
+            st = [f for f in traceback.extract_stack()[:-1] if "/torch/" not in f.filename]
+            sites[" <- ".join(f"{os.path.basename(f.filename)}:{f.lineno}" for f in reversed(st[-6:]))] += 1
 
     warnings.showwarning = show
     warnings.simplefilter("always")
@@ -90,6 +90,28 @@ def main():
     print("idle total ms/step:", round(sum(g for g, _ in gaps) / 1e3 / args.steps, 2), " gaps > 20 us:", sum(1 for g, _ in gaps if g > 20) // args.steps, "per step")
     for g, n in gaps[:25]:
         print(f"  {g:8.1f} us before {n}")
+    # what the host was doing during the three largest gaps (runtime API calls and operators overlapping the window)
+    cpu = [x for x in prof.events() if x.device_type == torch.autograd.DeviceType.CPU and x.time_range is not None]
+    big = []
+    end = ev[0].time_range.end
+    for a in ev[1:]:
+        if a.time_range.start > end:
+            big.append((a.time_range.start - end, end, a.time_range.start))
+        end = max(end, a.time_range.end)
+    big.sort(reverse=True)
+    for g, t_a, t_b in big[:3]:
+        print(f"  host activity during the {g:.0f} us gap:")
+        hits = [(min(c.time_range.end, t_b) - max(c.time_range.start, t_a), c) for c in cpu if c.time_range.start < t_b and c.time_range.end > t_a]
+        hits.sort(key=lambda h: -h[0])
+        for ov, c in hits[:12]:
+            print(f"      {ov:8.1f} us of {c.name[:70]} (total {c.time_range.end - c.time_range.start:.0f} us)")
+    # every synchronising runtime call inside the profiled steps, with the operators enclosing it
+    for c in cpu:
+        if "Synchronize" in c.name or c.name in ("cudaFree", "cudaMalloc", "cudaHostAlloc", "cudaMemcpy"):
+            enc = [o for o in cpu if o is not c and o.time_range.start <= c.time_range.start and o.time_range.end >= c.time_range.end]
+            enc.sort(key=lambda o: o.time_range.end - o.time_range.start)
+            print(f"  {c.name} at +{(c.time_range.start - t0) / 1e3:.2f} ms for {c.time_range.end - c.time_range.start:.0f} us inside: "
+                  + " < ".join(o.name[:40] for o in enc[:4]))
     agg = {}
     for x in ev:
         k = x.name.split("(")[0].replace("void ", "")[:60]
