@@ -283,11 +283,16 @@ class LearnableCompressor(nn.Module):
         self.train()
         # no host synchronisation inside the loop (see log_dict); LL_SYNC_LOGS=1 restores a float() per logged scalar (A/B)
         self._defer_log_sync = os.environ.get("LL_SYNC_LOGS", "0") != "1"
+        self._loss_steps = 0
         try:
             self._fit_loop(batches, optimizers, max_steps, grad_clip, is_dist, process_group, grad_comm_dtype)
         finally:
             self._defer_log_sync = False
             self.logged = {k: (float(v) if torch.is_tensor(v) else v) for k, v in self.logged.items()}
+            if getattr(self, "_loss_host", None) is not None:
+                if torch.cuda.is_available():
+                    torch.cuda.current_stream().synchronize()
+                self.loss_history = self._loss_host[: getattr(self, "_loss_steps", 0)].clone()
         for s in schedulers:
             s["scheduler"].step()
         self.current_epoch += 1
@@ -301,7 +306,7 @@ class LearnableCompressor(nn.Module):
         from .helpers import FlatAdamW
 
         world = torch.distributed.get_world_size(process_group) if is_dist else 1
-        for batch_idx, batch in enumerate(batches):
+        for batch_idx, batch in enumerate(_prefetch_to_device(batches, getattr(next(self.parameters(), None), "device", "cpu"))):
             if max_steps is not None and self.global_step >= max_steps:
                 break
             for oi, opt in enumerate(optimizers):
@@ -312,6 +317,18 @@ class LearnableCompressor(nn.Module):
                     # by block, under the GEMMs of the remaining blocks
                     opt.prepare_backward(sync=is_dist, group=process_group, world=world)
                 loss = self.training_step(batch, batch_idx, optimizer_idx=oi)
+                if oi == 0 and loss.is_cuda:
+                    # the step's loss goes to the host every step -- as an asynchronous copy into pinned memory
+                    # (``loss_history``, valid once fit() returns), not as a float() that would stall the host
+                    hist = getattr(self, "_loss_host", None)
+                    if hist is None or hist.numel() <= batch_idx:
+                        new = torch.zeros(max(1024, 2 * (batch_idx + 1)), dtype=torch.float32).pin_memory()
+                        if hist is not None:
+                            torch.cuda.current_stream().synchronize()
+                            new[: hist.numel()] = hist
+                        hist = self._loss_host = new
+                    hist[batch_idx: batch_idx + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+                    self._loss_steps = batch_idx + 1
                 loss.backward()
                 params = [p for g in opt.param_groups for p in g["params"] if p.grad is not None]
                 if is_dist and params:
@@ -325,6 +342,63 @@ class LearnableCompressor(nn.Module):
                     torch.nn.utils.clip_grad_norm_(params, grad_clip)
                 opt.step()
             self.global_step += 1
+
+
+def _map_tensors(obj, fn):
+    if torch.is_tensor(obj):
+        return fn(obj)
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_map_tensors(o, fn) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _map_tensors(v, fn) for k, v in obj.items()}
+    return obj
+
+
+def _prefetch_to_device(batches, device):
+    """``fit``'s input side: batches whose tensors are already on ``device`` pass through untouched; HOST batches (what a
+    DataLoader hands over -- the reference lets Lightning copy each one synchronously at the top of its step) are
+    copied on a side stream ONE BATCH AHEAD, so the copy of batch i + 1 runs under the kernels of batch i (308 MB of
+    float32 per 2 x 256 images is 5.6 ms of link time against a 21 ms step).  Pinned host memory makes the copy
+    asynchronous; pageable memory still works (the copy then blocks the host, as in the reference)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        yield from batches
+        return
+    side = None
+    it = iter(batches)
+
+    def is_host(b):
+        found = []
+        _map_tensors(b, lambda t: found.append(t.device.type == "cpu") or t)
+        return any(found)
+
+    def stage(b):
+        nonlocal side
+        if not is_host(b):
+            return b, None
+        if side is None:
+            side = torch.cuda.Stream(device)
+        main = torch.cuda.current_stream(device)
+        with torch.cuda.stream(side):
+            moved = _map_tensors(b, lambda t: t.to(device, non_blocking=True))
+            ready = torch.cuda.Event()
+            ready.record(side)
+        _map_tensors(moved, lambda t: t.record_stream(main) or t)
+        return moved, ready
+
+    try:
+        nxt = stage(next(it))
+    except StopIteration:
+        return
+    while nxt is not None:
+        cur, ready = nxt
+        try:
+            nxt = stage(next(it))  # batch i + 1 starts moving before batch i's kernels are enqueued
+        except StopIteration:
+            nxt = None
+        if ready is not None:
+            torch.cuda.current_stream(device).wait_event(ready)
+        yield cur
 
 
 def _plain(d, key=None):

@@ -182,3 +182,25 @@ def test_augmnist_shaped_config(cuda_device):
         # kernel from the device: equal up to the last ulp of that factor)
         assert torch.allclose(z_hat, model(x), rtol=1e-5, atol=1e-6)
     assert len(strings) == 1 and len(strings[0]) == 512 and all(len(s) % 4 == 0 for s in strings[0])
+
+
+def test_fit_prefetches_host_batches(cuda_device):
+    """fit() fed HOST batches (pinned and pageable) copies them one batch ahead on a side stream: same per-step losses
+    as the same batches already on the device, one loss per step in ``loss_history``."""
+    from lossyless_b200.learnable_compressors import LearnableCompressor, default_clip_hparams
+
+    gen = torch.Generator().manual_seed(3)
+    host = [torch.randn(16, 3, 224, 224, generator=gen) for _ in range(4)]
+    host[1], host[3] = host[1].pin_memory(), host[3].pin_memory()
+    hist = {}
+    for where in ("device", "host"):
+        torch.manual_seed(0)
+        model = LearnableCompressor(default_clip_hparams(distortion="lossy_Z", beta=5e-2, max_steps=40, n_data=5000)).to(cuda_device)
+        if where == "device":
+            batches = [(x.to(cuda_device), (None, x.to(cuda_device))) for x in host]
+        else:
+            batches = ((x, (None, x)) for x in host)  # a generator, as a DataLoader would be
+        model.fit(batches)
+        hist[where] = model.loss_history.clone()
+    assert hist["host"].numel() == 4 and torch.isfinite(hist["host"]).all()
+    assert torch.allclose(hist["host"], hist["device"], rtol=1e-5, atol=0)
