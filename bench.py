@@ -9,7 +9,9 @@ i.e. the body of the reference's ``compress_dataset`` loop (hub/compressor.py:18
 Prints ONE JSON line on rank 0 (contract in the task statement):
   value     images/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       same metric through ``ClipCompressor.compress_stream`` (compress_dataset's loop) with pinned HOST
-            buffers: H2D of the images and D2H of the records inside the timed region
+            buffers: H2D of the images and D2H of the records inside the timed region.  The images are CLIP-sized
+            uint8 pixels (ToTensor / Normalize on the GPU, same container bytes: tests/test_preprocess_gpu.py);
+            ``e2e_fp16_feed`` is the same with pre-normalised fp16 tensors (twice the bytes over the host link)
   roofline  the dominant kernel (tcgen05 GEMM): algorithmic FLOPs / event-timed GEMM time,
             against the measured bf16 peak in MEASURED_PEAKS.json
   cpu_baseline  the oracle port of the same path on the host cores, bounded sample (N=1)
@@ -330,6 +332,9 @@ def ncu_traffic():
     return None, None
 
 
+NUMA_BINDING = None
+
+
 def dist_setup():
     import torch
     import torch.distributed as dist
@@ -341,6 +346,12 @@ def dist_setup():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the measured path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host side of the feed: this rank's threads and pinned staging memory on the GPU's own NUMA node (LL_NO_NUMA=1: A/B)
+    global NUMA_BINDING
+    if os.environ.get("LL_NO_NUMA", "0") != "1":
+        from lossyless_b200.parallel import bind_host_to_gpu
+
+        NUMA_BINDING = bind_host_to_gpu(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -433,10 +444,13 @@ def run_encode(args):
     # ---- e2e: pinned host images in, container records out, per step, through compress_dataset's own loop
     # (ClipCompressor.compress_stream: batch i+1 is enqueued before the host waits for batch i's records; every
     # step's H2D copy and records D2H happen inside the timed region)
+    rec_bytes = [0]
+
     def e2e_run(x_host, steps):
         n = 0
         for rec, b in comp.compress_stream(x_host for _ in range(steps)):
             n += b
+            rec_bytes[0] = int(rec.numel())  # bytes of the last batch's records that came back to the host
         return n
 
     e2e_run(X_host, 2)
@@ -475,6 +489,7 @@ def run_encode(args):
     e2e_run(u8_host, args.steps)
     barrier()
     e2e_u8 = world * B * args.steps / max_over_ranks(time.perf_counter() - t0)
+    u8_rec_bytes = rec_bytes[0]
 
     # ---- what the host link gives: a bare pinned H2D copy of one 378-image sub-batch, nothing else running
     probe_dst = torch.empty_like(X[:378])
@@ -555,14 +570,20 @@ def run_encode(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "beta": 0.05, "vit_weights": "seeded random init (no pretrained CLIP offline)",
                    "l2": f"inputs {B * 3 * 224 * 224 * 2 / 1e6:.0f} MB/step > 126 MB L2, no flush needed",
                    "bits_per_img": bits_per_img, "sharding": "independent images per rank, no collective"},
-        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 2, "d2h_bytes_per_step": total_bytes + 8,
-                "input": "pinned host fp16 [B,3,224,224] CLIP-normalised tensors (what the reference's loop body receives)",
-                "api": "ClipCompressor.compress_stream (compress_dataset's loop)", "h2d_link_gbps": h2d_gbps, "h2d_link_gbps_min_over_ranks": h2d_min,
-                "blocking_per_batch_call": e2e_blocking},
+        # headline end-to-end number: the CLIP-sized uint8 feed.  The fp16 feed of round 1 (301 KB per image) is bound by
+        # the host side of the link once eight ranks copy at once (24 GB/s per GPU on this pool's 8-GPU boxes: a VM with
+        # one NUMA node, nothing to bind to); 150 KB of pixels per image, ToTensor / Normalize on the GPU inside the
+        # timed region, is the same container byte for byte and keeps the link under the kernels at every N.
+        "e2e": {"value": e2e_u8, "unit": "img/s", "h2d_bytes_per_step": B * 224 * 224 * 3, "d2h_bytes_per_step": u8_rec_bytes + 8,
+                "input": "pinned host uint8 [B,224,224,3] CLIP-sized pixels (what a DataLoader holds after decode + resize); ToTensor / Normalize "
+                         "on the GPU inside the timed region, then ViT -> bottleneck -> rANS -> records back in pinned host memory",
+                "api": "ClipCompressor.compress_stream (compress_dataset's loop)", "host_numa_binding": NUMA_BINDING,
+                "h2d_link_gbps": h2d_gbps, "h2d_link_gbps_min_over_ranks": h2d_min},
+        "e2e_fp16_feed": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 2, "d2h_bytes_per_step": total_bytes + 8,
+                          "input": "pinned host fp16 [B,3,224,224] CLIP-normalised tensors (round 1's e2e: what the reference's loop body receives)",
+                          "blocking_per_batch_call": e2e_blocking},
         "e2e_raw_uint8": {"value": e2e_raw, "unit": "img/s", "h2d_bytes_per_step": B * 96 * 96 * 3,
                           "input": "pinned host uint8 [B,96,96,3] STL10-shaped images; resize/crop/normalise on the GPU"},
-        "e2e_clip_uint8": {"value": e2e_u8, "unit": "img/s", "h2d_bytes_per_step": B * 224 * 224 * 3,
-                           "input": "pinned host uint8 [B,224,224,3] CLIP-sized pixels; ToTensor/Normalize on the GPU"},
         "decode": decode,
         "gpu_launches": args.steps * (vit_launches + 1 + 2),
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all ViT linears)", "achieved": achieved,

@@ -25,6 +25,48 @@ __all__ = ["shard_range", "gather_record_blobs", "write_container", "compress_da
            "split_records_by_bytes", "gather_rows", "decompress_dataset_sharded"]
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index, sysfs="/sys/bus/pci/devices"):
+    """Pin this process (one rank per GPU) to the CPUs of the NUMA node its GPU hangs off, and prefer that node for its
+    memory, BEFORE it allocates pinned staging buffers: with eight ranks feeding eight GPUs, staging memory that
+    first-touch placed on the other socket crosses the inter-socket link on every host-to-device copy (round 1
+    measured 24 GB/s per GPU with all eight copying against 55 GB/s alone).  Pure sysfs + sched_setaffinity +
+    set_mempolicy(MPOL_PREFERRED); returns ``{"node", "cpus", "pci"}`` or ``None`` when the topology is not exposed
+    (containers without sysfs PCI entries, single-node hosts): then nothing is changed."""
+    import ctypes
+    import os
+
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        pci = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        base = os.path.join(sysfs, pci)
+        node = int(open(os.path.join(base, "numa_node")).read())
+        cpus = _parse_cpulist(open(os.path.join(base, "local_cpulist")).read())
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+    if node < 0 or not cpus:
+        return None
+    allowed = os.sched_getaffinity(0) & cpus
+    if not allowed:
+        return None
+    os.sched_setaffinity(0, allowed)
+    try:  # MPOL_PREFERRED = 1: allocate on `node` when it has room, fall back elsewhere instead of failing
+        mask = ctypes.c_ulong(1 << node)
+        ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
+    except (OSError, AttributeError):
+        pass
+    return {"node": node, "cpus": len(allowed), "pci": pci}
+
+
 def shard_range(n, rank, world):
     """Contiguous [start, end) slice of n units for `rank`; the first n % world ranks get one more."""
     base, extra = divmod(n, world)

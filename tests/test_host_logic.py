@@ -254,3 +254,34 @@ def test_predictor_probe_learns_on_representations():
     ev = pred.evaluate([(Z[1500:], y[1500:])])
     assert ev["acc"] > 0.9, ev
     assert pred(Z[:4], is_logits=False).sum(-1).allclose(torch.ones(4))
+
+
+def test_bind_host_to_gpu_reads_sysfs_topology(tmp_path, monkeypatch):
+    """parallel.bind_host_to_gpu: PCI address from the device properties -> sysfs numa_node / local_cpulist -> CPU
+    affinity restricted to the GPU's node (intersected with what the process may use); missing topology -> None."""
+    import os
+    import types
+
+    import torch
+
+    from lossyless_b200 import parallel
+
+    assert parallel._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    before = os.sched_getaffinity(0)
+    keep = set(sorted(before)[: max(1, len(before) // 2)])
+    monkeypatch.setattr(torch.cuda, "get_device_properties",
+                        lambda i: types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1B, pci_device_id=0))
+    dev = tmp_path / "0000:1b:00.0"
+    dev.mkdir()
+    (dev / "numa_node").write_text("0\n")
+    (dev / "local_cpulist").write_text(",".join(str(c) for c in sorted(keep)) + ",4095\n")  # 4095: not ours to use
+    try:
+        got = parallel.bind_host_to_gpu(0, sysfs=str(tmp_path))
+        assert got == {"node": 0, "cpus": len(keep), "pci": "0000:1b:00.0"}
+        assert os.sched_getaffinity(0) == keep
+    finally:
+        os.sched_setaffinity(0, before)
+    (dev / "numa_node").write_text("-1\n")
+    assert parallel.bind_host_to_gpu(0, sysfs=str(tmp_path)) is None
+    assert parallel.bind_host_to_gpu(0, sysfs=str(tmp_path / "missing")) is None
+    assert os.sched_getaffinity(0) == before

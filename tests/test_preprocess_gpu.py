@@ -49,14 +49,16 @@ def test_matches_pil_torchvision(cuda_device, h, w):
     assert torch.equal(pre(x, dtype=torch.bfloat16), out32.bfloat16())
 
 
-def test_compress_dataset_from_raw_pixels(cuda_device, tmp_path):
-    """STL10-shaped uint8 images (BASELINE config 2): coding the raw pixels with GPU preprocessing gives the
-    same container file, byte for byte, as coding the CPU-transformed tensors."""
+@pytest.mark.parametrize("side", [96, 224])
+def test_compress_dataset_from_raw_pixels(cuda_device, tmp_path, side):
+    """STL10-shaped uint8 images (BASELINE config 2) and CLIP-sized ones (bench.py's e2e feed: Resize / CenterCrop are
+    the identity, ToTensor / Normalize run in clip_normalize_u8_kernel): coding the raw pixels with GPU preprocessing
+    gives the same container file, byte for byte, as coding the CPU-transformed tensors."""
     import hubconf
 
     comp, transform = hubconf.clip_compressor_b005(device="cuda")
     rng = np.random.default_rng(0)
-    raw = rng.integers(0, 256, (50, 96, 96, 3), dtype=np.uint8)
+    raw = rng.integers(0, 256, (50, side, side, 3), dtype=np.uint8)
 
     class Raw(torch.utils.data.Dataset):
         def __len__(self):
