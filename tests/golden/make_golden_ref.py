@@ -76,17 +76,17 @@ def _contrastive(rank_seed=None):
     return d
 
 
-def _w2_worker(rank, port, out):
-    """One real gloo process of the W = 2 contrastive run: the reference's own all_gather + backward."""
+def _w2_worker(rank, port, out, world=2, batch=8):
+    """One real gloo process of the W = `world` contrastive run: the reference's own all_gather + backward."""
     import torch.distributed as dist
 
     warnings.filterwarnings("ignore", category=FutureWarning)
     ref_shim.import_reference()
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=2)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     d = _contrastive()
     g = torch.Generator().manual_seed(100 + rank)
-    z_hat = torch.randn(8, 512, generator=g).requires_grad_(True)
-    z_pos = torch.randn(8, 512, generator=g).requires_grad_(True)
+    z_hat = torch.randn(batch, 512, generator=g).requires_grad_(True)
+    z_pos = torch.randn(batch, 512, generator=g).requires_grad_(True)
     logits = d.compute_logits(z_hat, z_pos, None)
     dd, logs, _ = d(z_hat, z_pos, None, None)
     dd.mean().backward()
@@ -331,6 +331,25 @@ def make_hub():
     out.update(dict(z_f16=z, Z_hat=Z_hat, Y=Y, rate5=float(rate), z_hat5=z_hat5, z_fwd5=z_fwd,
                     lens5=np.array([len(s) for s in strings], dtype=np.int32)))
     npz("ref_hub.npz", out)
+
+
+def make_losses_w8():
+    """SURVEY 8(d) configuration 3 trains on 8 ranks: the reference's ContrastiveDistortion over EIGHT real gloo processes
+    (4 samples per rank: logits [8, 64] per rank, n_negatives = 63).  Its own small fixture (ref_losses_w8.npz) so that
+    ref_losses.npz stays byte for byte what earlier rounds committed."""
+    import torch.multiprocessing as mp
+
+    out = {}  # the module's parameters are ref_losses.npz's "contrastive/*" (same seed)
+    with tempfile.TemporaryDirectory() as tmp:
+        pat = os.path.join(tmp, "r{}.pt")
+        port = 31000 + os.getpid() % 2000
+        mp.spawn(_w2_worker, args=(port, pat, 8, 4), nprocs=8, join=True)
+        for r in range(8):
+            res = torch.load(pat.format(r), weights_only=False)
+            # every rank's inputs, three ranks' results, one rank's (large) projector gradients
+            keep = [k for k in res if r in (0, 3, 7) and (r == 3 or k not in ("g_w1", "g_w2"))] if r in (0, 3, 7) else ["z_hat", "z_pos"]
+            out.update({f"w8/rank{r}/{k}": res[k] for k in keep})
+    npz("ref_losses_w8.npz", out)
 
 
 if __name__ == "__main__":

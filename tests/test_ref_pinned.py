@@ -96,6 +96,40 @@ def test_contrastive_w2_gather_quirk_matches_reference(ref, rank):
         assert (got - w).abs().max() <= 1e-5 * w.abs().max() + 1e-9, want
 
 
+@pytest.mark.parametrize("rank", [0, 3, 7])
+def test_contrastive_w8_matches_reference(ref, golden_dir, rank):
+    """SURVEY 8(d) configuration 3 runs on 8 ranks: the reference's ContrastiveDistortion over EIGHT real gloo processes
+    (ref_losses_w8.npz, 4 samples per rank).  Own tile first, the seven other ranks' self-similarity tiles in rank order
+    to its right, 63 negatives, gradient through the own tile only."""
+    g8 = np.load(os.path.join(golden_dir, "ref_losses_w8.npz"))
+    g = ref["losses"]
+    proj = {k: v.clone().requires_grad_(True) for k, v in _proj(g).items()}
+    ls = T(g["contrastive/logit_scale"]).clone().requires_grad_(True)
+    frozen = {k: v.detach() for k, v in proj.items()}
+    with torch.no_grad():
+        remotes = [olosses.contrastive_local_logits(T(g8[f"w8/rank{r}/z_hat"]), T(g8[f"w8/rank{r}/z_pos"]), frozen)
+                   for r in range(8) if r != rank]
+    zr = T(g8[f"w8/rank{rank}/z_hat"]).clone().requires_grad_(True)
+    zpr = T(g8[f"w8/rank{rank}/z_pos"]).clone().requires_grad_(True)
+    tiles = list(remotes)
+    tiles.insert(rank, olosses.contrastive_local_logits(zr, zpr, proj))
+    logits = olosses.contrastive_gather(tiles, rank)
+    assert logits.shape == (8, 64)
+    assert torch.allclose(logits, T(g8[f"w8/rank{rank}/logits"]), atol=1e-6)
+    d, logs = olosses.contrastive_distortion(zr, zpr, proj, rank=rank, other_tiles=remotes, temperature=0.01, logit_scale=ls,
+                                             effective_batch_size=5000)
+    assert torch.allclose(d, T(g8[f"w8/rank{rank}/distortion"]), rtol=1e-5)
+    assert int(logs["n_negatives"]) == int(g8[f"w8/rank{rank}/n_negatives"]) == 63
+    assert float(logs["I_q_zm"]) == pytest.approx(float(g8[f"w8/rank{rank}/I_q_zm"]), rel=1e-5)
+    d.mean().backward()
+    checks = [(zr.grad, "g_z_hat"), (zpr.grad, "g_z_pos"), (ls.grad, "g_logit_scale")]
+    if rank == 3:
+        checks += [(proj["w1"].grad, "g_w1"), (proj["w2"].grad, "g_w2")]
+    for got, want in checks:
+        w = T(g8[f"w8/rank{rank}/{want}"])
+        assert (got - w).abs().max() <= 1e-5 * w.abs().max() + 1e-9, want
+
+
 def test_lossy_z_matches_reference(ref):
     g = ref["losses"]
     zh = T(g["lossy_z/z_hat"]).requires_grad_(True)

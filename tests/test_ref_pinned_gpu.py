@@ -122,6 +122,44 @@ def test_contrastive_w2_vs_reference(cuda_device, ref, rank, monkeypatch):
     close_grad(m.projector.module[0].weight.grad, g[f"w2/rank{rank}/g_w1"], "w1")
 
 
+@pytest.mark.parametrize("rank", [0, 3, 7])
+def test_contrastive_w8_vs_reference(cuda_device, ref, golden_dir, rank, monkeypatch):
+    """The reference ran W = 8 over real gloo processes (ref_losses_w8.npz); rank `rank`'s view on one GPU, the seven
+    remote tiles handed over through the module's own gather hook: logits [8, 64], 63 negatives, local-only gradient."""
+    import os
+
+    import lossyless_b200.distortions as D
+
+    g8 = np.load(os.path.join(golden_dir, "ref_losses_w8.npz"))
+    g = ref["losses"]
+    m = _contrastive(g, cuda_device)
+    with torch.no_grad():
+        remote = {r: m.compute_logits(T(g8[f"w8/rank{r}/z_hat"]), T(g8[f"w8/rank{r}/z_pos"]), None) for r in range(8) if r != rank}
+
+    def fake_gather(t):
+        return tuple(t if r == rank else remote[r] for r in range(8))
+
+    monkeypatch.setattr(D, "gather_from_gpus", fake_gather)
+    monkeypatch.setattr(torch.distributed, "is_initialized", lambda: True)
+    monkeypatch.setattr(torch.distributed, "get_world_size", lambda *a, **k: 8)
+    monkeypatch.setattr(torch.distributed, "get_rank", lambda *a, **k: rank)
+    z, zp = T(g8[f"w8/rank{rank}/z_hat"]).requires_grad_(True), T(g8[f"w8/rank{rank}/z_pos"]).requires_grad_(True)
+    logits = m.compute_logits(z, zp, None)
+    assert logits.shape == (8, 64)
+    assert torch.allclose(logits.detach().cpu(), torch.from_numpy(g8[f"w8/rank{rank}/logits"]), atol=2e-6)
+    d, logs, _ = m(z, zp, None, None)
+    assert np.allclose(d.detach().cpu().numpy(), g8[f"w8/rank{rank}/distortion"], rtol=1e-4)
+    assert int(logs["n_negatives"]) == 63
+    assert float(logs["I_q_zm"]) == pytest.approx(float(g8[f"w8/rank{rank}/I_q_zm"]), rel=1e-4)
+    d.mean().backward()
+    close_grad(z.grad, g8[f"w8/rank{rank}/g_z_hat"], "z_hat")
+    close_grad(zp.grad, g8[f"w8/rank{rank}/g_z_pos"], "z_pos")
+    close_grad(m.logit_scale.grad, g8[f"w8/rank{rank}/g_logit_scale"], "logit_scale")
+    if rank == 3:
+        close_grad(m.projector.module[0].weight.grad, g8["w8/rank3/g_w1"], "w1")
+        close_grad(m.projector.module[-1].weight.grad, g8["w8/rank3/g_w2"], "w2")
+
+
 def test_lossy_z_vs_reference(cuda_device, ref):
     from lossyless_b200.distortions import LossyZDistortion
     from lossyless_b200.distributions import Deterministic
