@@ -319,6 +319,12 @@ int ll_vit_set_fuse_layernorm(ll_vit_t *v, int on);
  * the model's 16-bit dtype; 0: always go through the im2col copy (patchify kernel).  A/B and fallback knob. */
 int ll_vit_set_direct_patch(ll_vit_t *v, int on);
 
+/* 1 (default): in the LAST ResidualAttentionBlock everything after the attention core runs on the class-token rows only
+ * (batch rows instead of batch * tokens: the out-projection, ln_2 and the MLP are row-wise and
+ * VisionTransformer.forward keeps x[:, 0, :] alone -- clip/model.py, reached from hub/compressor.py:93), which removes
+ * 6 % of the encoder's FLOPs without touching z; 0: every row, as the reference computes it.  A/B knob, tests. */
+int ll_vit_set_cls_last_block(ll_vit_t *v, int on);
+
 /* Per-GEMM device timing for the roofline report: between begin and end every GEMM launch of
  * ll_vit_forward is bracketed by cudaEvents on the launch stream; end synchronises and returns
  * the summed GEMM milliseconds, algorithmic FLOPs (2*M*N*K) and launch count. */

@@ -208,6 +208,11 @@ class VisionTransformer(nn.Module):
         nat = self._native or self._build_native()
         N.call("ll_vit_set_direct_patch", nat["handle"], int(bool(on)))
 
+    def set_cls_last_block(self, on):
+        """Last block's out-projection / ln_2 / MLP on the class-token rows only (default) or on every row (A/B knob)."""
+        nat = self._native or self._build_native()
+        N.call("ll_vit_set_cls_last_block", nat["handle"], int(bool(on)))
+
     def launches(self, batch):
         nat = self._native or self._build_native()
         return int(N.load().ll_vit_launches(nat["handle"], int(batch)))

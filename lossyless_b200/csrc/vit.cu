@@ -526,6 +526,25 @@ attention_tma_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     }
 }
 
+// ------------------------------------------------------------------------- class-token rows of two [B*S, W] tensors
+// The encoder's output is the class token only (clip/model.py VisionTransformer.forward: x[:, 0, :] after the last
+// block).  In the LAST ResidualAttentionBlock everything after the attention core is row-wise, so only the B class-token
+// rows of the attention output and of the residual stream can reach z: they are gathered into two contiguous [B, W]
+// tensors and the out-projection, ln_2, c_fc and c_proj of that block run on B rows instead of B * S.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_cls_rows_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restrict__ a_cls, T *__restrict__ x_cls, int64_t B, int64_t row_stride, int W8)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;  // one 16-byte piece each
+    if (i >= B * W8) return;
+    const int64_t b = i / W8;
+    const int c = (int)(i % W8);
+    reinterpret_cast<uint4 *>(a_cls)[i] = reinterpret_cast<const uint4 *>(a + b * row_stride)[c];
+    reinterpret_cast<uint4 *>(x_cls)[i] = reinterpret_cast<const uint4 *>(x + b * row_stride)[c];
+}
+
 // ------------------------------------------------------------------------- launch helpers
 template <typename T>
 static int launch_layernorm(const T *x, int64_t rows, int64_t row_stride, const float *g, const float *b, T *h, int width, cudaStream_t s)
@@ -617,6 +636,8 @@ struct ll_vit {
     bool fuse_ln = true;
     // patch-embedding GEMM reads the images directly (5-D TMA map) instead of an im2col copy, when the input dtype allows
     bool direct_patch = true;
+    // the last block's row-wise half (out-projection, ln_2, MLP) on the class-token rows only
+    bool cls_last = true;
     std::vector<void *> in_proj_wf, fc_wf;
     std::vector<float *> in_proj_bf, fc_bf;
     std::vector<void *> owned;
@@ -651,7 +672,7 @@ namespace {
 inline int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
 
 struct Workspace {
-    uint8_t *patch_a, *patch_o, *x, *h, *qkv, *f, *cls, *stats1, *stats2;
+    uint8_t *patch_a, *patch_o, *x, *h, *qkv, *f, *cls, *xc, *ac, *stats1, *stats2;
     int64_t total;
 };
 
@@ -673,6 +694,8 @@ Workspace carve(const ll_vit *v, int64_t n, uint8_t *base)
     ws.qkv = take(M * 3 * W * 2);
     ws.f = take(M * 4 * W * 2);
     ws.cls = take(n * W * 2);
+    ws.xc = take(n * W * 2);  // class-token rows of the residual stream / of the attention output (last block)
+    ws.ac = take(n * W * 2);
     ws.stats1 = take((W / 64) * M * (int64_t)sizeof(float2));  // ln_1 / ln_2 row statistics, <= width / 64 parts
     ws.stats2 = take((W / 64) * M * (int64_t)sizeof(float2));
     ws.total = off;
@@ -727,6 +750,15 @@ int forward_chunk(ll_vit *v, const void *x, int x_dtype, int64_t n, void *z, con
         return timed(0, [&] { return gemm_launch_ln(A, Wt, bias, res, D, m, N, K, dt, act, st_in, parts_in, st_out, W, s); });
     };
     float2 *st1 = v->fuse_ln ? (float2 *)ws.stats1 : nullptr;
+    const bool cls_only = v->cls_last;
+    auto gather_cls = [&]() -> int {
+        const int W8 = W / 8;
+        const unsigned grid = (unsigned)((n * W8 + 255) / 256);
+        LL_CUDA_CHECK(launch_pdl(gather_cls_rows_kernel<T>, dim3(grid), dim3(256), 0, s, (const T *)ws.h, (const T *)ws.x, (T *)ws.ac, (T *)ws.xc, n,
+                                 (int64_t)S * W, W8));
+        LL_LAUNCH_CHECK();
+        return LL_OK;
+    };
     if ((rc = timed(3, [&] { return launch_assemble<T>((const T *)ws.patch_o, (const T *)v->w.class_emb, (const T *)v->w.pos_emb, v->w.ln_pre_w, v->w.ln_pre_b, (T *)ws.x, n, S, W, st1, pgrid, ppitch, prows, s); }))) return rc;
     if (v->fuse_ln) {
         // x -> [rstd(x) * x W''qkv + b'] -> attention -> out-proj (+x, row stats) -> [rstd * x W''fc + b', GELU]
@@ -735,6 +767,14 @@ int forward_chunk(ll_vit *v, const void *x, int x_dtype, int64_t n, void *z, con
         for (int l = 0; l < c.layers; ++l) {
             if ((rc = gemm_ln(ws.x, v->in_proj_wf[l], v->in_proj_bf[l], nullptr, ws.qkv, M, 3 * W, W, 0, ws.stats1, parts1, nullptr))) return rc;
             if ((rc = timed(1, [&] { return launch_attention<T>((const T *)ws.qkv, (T *)ws.h, n, S, c.heads, s); }))) return rc;
+            if (cls_only && l == c.layers - 1) {
+                // only the class-token rows can reach z from here on: n rows instead of n * S
+                if ((rc = timed(3, [&] { return gather_cls(); }))) return rc;
+                if ((rc = gemm_ln(ws.ac, v->out_proj_w[l], v->out_proj_b[l], ws.xc, ws.xc, n, W, W, 0, nullptr, 0, ws.stats2))) return rc;
+                if ((rc = gemm_ln(ws.xc, v->fc_wf[l], v->fc_bf[l], nullptr, ws.f, n, 4 * W, W, 1, ws.stats2, W / 64, nullptr))) return rc;
+                if ((rc = gemm_ln(ws.f, v->cproj_w[l], v->cproj_b[l], ws.xc, ws.xc, n, W, 4 * W, 0, nullptr, 0, nullptr))) return rc;
+                break;
+            }
             if ((rc = gemm_ln(ws.h, v->out_proj_w[l], v->out_proj_b[l], ws.x, ws.x, M, W, W, 0, nullptr, 0, ws.stats2))) return rc;
             if ((rc = gemm_ln(ws.x, v->fc_wf[l], v->fc_bf[l], nullptr, ws.f, M, 4 * W, W, 1, ws.stats2, W / 64, nullptr))) return rc;
             if ((rc = gemm_ln(ws.f, v->cproj_w[l], v->cproj_b[l], ws.x, ws.x, M, W, 4 * W, 0, nullptr, 0, ws.stats1))) return rc;
@@ -745,12 +785,24 @@ int forward_chunk(ll_vit *v, const void *x, int x_dtype, int64_t n, void *z, con
         if ((rc = timed(2, [&] { return launch_layernorm<T>((const T *)ws.x, M, W, v->ln1_w[l], v->ln1_b[l], (T *)ws.h, W, s); }))) return rc;
         if ((rc = gemm(ws.h, v->in_proj_w[l], v->in_proj_b[l], nullptr, ws.qkv, M, 3 * W, W, 0))) return rc;
         if ((rc = timed(1, [&] { return launch_attention<T>((const T *)ws.qkv, (T *)ws.h, n, S, c.heads, s); }))) return rc;
+        if (cls_only && l == c.layers - 1) {
+            if ((rc = timed(3, [&] { return gather_cls(); }))) return rc;
+            if ((rc = gemm(ws.ac, v->out_proj_w[l], v->out_proj_b[l], ws.xc, ws.xc, n, W, W, 0))) return rc;
+            if ((rc = timed(2, [&] { return launch_layernorm<T>((const T *)ws.xc, n, W, v->ln2_w[l], v->ln2_b[l], (T *)ws.ac, W, s); }))) return rc;
+            if ((rc = gemm(ws.ac, v->fc_w[l], v->fc_b[l], nullptr, ws.f, n, 4 * W, W, 1))) return rc;
+            if ((rc = gemm(ws.f, v->cproj_w[l], v->cproj_b[l], ws.xc, ws.xc, n, W, 4 * W, 0))) return rc;
+            break;
+        }
         if ((rc = gemm(ws.h, v->out_proj_w[l], v->out_proj_b[l], ws.x, ws.x, M, W, W, 0))) return rc;
         if ((rc = timed(2, [&] { return launch_layernorm<T>((const T *)ws.x, M, W, v->ln2_w[l], v->ln2_b[l], (T *)ws.h, W, s); }))) return rc;
         if ((rc = gemm(ws.h, v->fc_w[l], v->fc_b[l], nullptr, ws.f, M, 4 * W, W, 1))) return rc;
         if ((rc = gemm(ws.f, v->cproj_w[l], v->cproj_b[l], ws.x, ws.x, M, W, 4 * W, 0))) return rc;
     }
-    if ((rc = timed(2, [&] { return launch_layernorm<T>((const T *)ws.x, n, (int64_t)S * W, v->w.ln_post_w, v->w.ln_post_b, (T *)ws.cls, W, s); }))) return rc;
+    if (cls_only) {
+        if ((rc = timed(2, [&] { return launch_layernorm<T>((const T *)ws.xc, n, W, v->w.ln_post_w, v->w.ln_post_b, (T *)ws.cls, W, s); }))) return rc;
+    } else if ((rc = timed(2, [&] { return launch_layernorm<T>((const T *)ws.x, n, (int64_t)S * W, v->w.ln_post_w, v->w.ln_post_b, (T *)ws.cls, W, s); }))) {
+        return rc;
+    }
     if ((rc = gemm(ws.cls, v->w.proj_t, nullptr, nullptr, z, n, c.out_dim, W, 0))) return rc;
     return LL_OK;
 }
@@ -845,6 +897,13 @@ extern "C" int ll_vit_set_direct_patch(ll_vit_t *v, int on)
     return LL_OK;
 }
 
+extern "C" int ll_vit_set_cls_last_block(ll_vit_t *v, int on)
+{
+    LL_REQUIRE(v != nullptr, "vit_set_cls_last_block: null handle");
+    v->cls_last = on != 0;
+    return LL_OK;
+}
+
 extern "C" int64_t ll_vit_workspace_bytes(const ll_vit_t *v, int64_t batch)
 {
     if (!v || batch <= 0) return 0;
@@ -858,7 +917,7 @@ extern "C" int64_t ll_vit_launches(const ll_vit_t *v, int64_t batch)
     const int64_t passes = (batch + v->chunk - 1) / v->chunk;
     // patch embedding (+ im2col copy on the fallback path; the count assumes the 16-bit direct path when it is on),
     // token assembly + ln_pre, ln_post, proj; per block 4 GEMMs + attention (+ 2 LayerNorms when not fused)
-    return passes * ((v->direct_patch ? 4 : 5) + (v->fuse_ln ? 5 : 7) * (int64_t)v->cfg.layers);
+    return passes * ((v->direct_patch ? 4 : 5) + (v->fuse_ln ? 5 : 7) * (int64_t)v->cfg.layers + (v->cls_last ? 1 : 0));
 }
 
 extern "C" int ll_vit_forward(ll_vit_t *v, const void *x, int x_dtype, int64_t batch, void *z, void *workspace,

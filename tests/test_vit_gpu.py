@@ -87,9 +87,9 @@ def test_vit_b32_vs_golden(cuda_device, golden_dir):
     xb = x.repeat(200, 1, 1, 1)  # 400 images: two internal passes (378-image limit set above) of 200
     zb = vit(xb).float().cpu().numpy()
     assert np.array_equal(zb[0::2], np.repeat(z[:1], 200, 0)) and np.array_equal(zb[1::2], np.repeat(z[1:], 200, 0))
-    assert vit.launches(400) == 2 * (4 + 5 * 12)  # ln_1 / ln_2 fused into the GEMMs, patch embedding without im2col
+    assert vit.launches(400) == 2 * (4 + 5 * 12 + 1)  # ln_1 / ln_2 fused into the GEMMs, patch embedding without im2col
     vit.set_direct_patch(False)  # the im2col copy + plain GEMM give the same bits as the 5-D TMA operand
-    assert vit.launches(400) == 2 * (5 + 5 * 12)
+    assert vit.launches(400) == 2 * (5 + 5 * 12 + 1)
     assert np.array_equal(vit(xb).float().cpu().numpy(), zb)
     vit.set_direct_patch(True)
     vit.set_chunk(64)  # many small passes give the same bits
@@ -104,10 +104,28 @@ def test_vit_fused_layernorm_matches_separate_kernels(cuda_device, golden_dir):
     z_fused = vit(x).float().cpu().numpy()
     assert np.array_equal(z_fused, vit(x).float().cpu().numpy())  # reproducible
     vit.set_fuse_layernorm(False)
-    assert vit.launches(6) == 4 + 7 * 12
+    assert vit.launches(6) == 4 + 7 * 12 + 1  # + the class-token gather of the last block
     z_sep = vit(x).float().cpu().numpy()
     for z in (z_fused, z_sep):
         err = np.abs(z[:2] - g["z"])
         assert err.max() < 5e-2 and err.mean() < 8e-3, (err.max(), err.mean())
     d = np.abs(z_fused - z_sep)
     assert d.max() < 4e-2 and d.mean() < 6e-3, (d.max(), d.mean())
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("n", [1, 6, 130])
+def test_vit_cls_only_last_block_is_the_same_function(cuda_device, golden_dir, fused, n):
+    """The last block's out-projection / ln_2 / MLP run on the class-token rows only by default (VisionTransformer.forward
+    returns x[:, 0, :]; those layers are row-wise).  Same z as computing every row: the GEMM's per-element accumulation
+    order over K does not depend on M or on the tile shape, so the comparison is exact."""
+    g = np.load(os.path.join(golden_dir, "vit_b32.npz"))
+    vit, sd, cfg = _product_vit(cuda_device)
+    vit.set_fuse_layernorm(fused)
+    reps = (n + 1) // 2
+    x = torch.from_numpy(g["x_f16"]).to(cuda_device).repeat(reps, 1, 1, 1)[:n]
+    x = x + 0.01 * torch.randn(x.shape, generator=torch.Generator().manual_seed(n)).to(cuda_device).half()
+    z_cls = vit(x).float().cpu().numpy()
+    vit.set_cls_last_block(False)
+    z_all = vit(x).float().cpu().numpy()
+    assert np.array_equal(z_cls, z_all), np.abs(z_cls - z_all).max()
