@@ -225,6 +225,23 @@ int ll_vit_block_forward(const ll_vit_block_params_t *w, const void *x_in, void 
 int ll_vit_block_backward(const ll_vit_block_params_t *w, const void *x_in, const void *act, void *g_x,
                           void *scratch, const ll_vit_block_grads_t *g, int64_t batch, int S, int heads,
                           int width, int dtype, ll_stream_t stream);
+/* The LAST block of the tower: clip.model.VisionTransformer.forward keeps x[:, 0, :] only and a block is row-wise after
+ * its attention core, so the out-projection, ln_2 and the MLP -- forward, data and weight gradients -- run on the
+ * `batch` class-token rows.  Same record slot and scratch size as the all-rows calls; the block's output x2_c
+ * [batch, width] sits at ll_vit_block_cls_x2_offset_elems inside `act`.  Backward: g_x2_c [batch, width] is dL/dx2_c,
+ * g_x [batch * S, width] receives dL/dx_in. */
+int64_t ll_vit_block_cls_x2_offset_elems(int64_t batch, int S, int width);
+int ll_vit_block_forward_cls(const ll_vit_block_params_t *w, const void *x_in, void *act, int64_t batch, int S,
+                             int heads, int width, int dtype, ll_stream_t stream);
+int ll_vit_block_backward_cls(const ll_vit_block_params_t *w, const void *x_in, const void *act, const void *g_x2_c,
+                              void *g_x, void *scratch, const ll_vit_block_grads_t *g, int64_t batch, int S,
+                              int heads, int width, int dtype, ll_stream_t stream);
+/* Row b of a_c / x_c [batch, width] = row b * S of a / x [batch * S, width] (x[:, 0, :] of two tensors at once), and the
+ * reverse into zero-filled full-size tensors.  2-byte elements, width % 8 == 0, 16-byte aligned. */
+int ll_gather_cls_rows(const void *a, const void *x, void *a_c, void *x_c, int64_t batch, int S, int width, int dtype,
+                       ll_stream_t stream);
+int ll_scatter_cls_rows(const void *a_c, const void *x_c, void *a, void *x, int64_t batch, int S, int width, int dtype,
+                        ll_stream_t stream);
 /* Which fusions ll_vit_block_forward / ll_vit_block_backward use (A/B knob, tests): bit 0 = QuickGELU backward inside
  * the c_proj data-gradient GEMM's epilogue (ll_gemm act 2) instead of a separate ll_quickgelu_backward pass.
  * Default: all on.  Returns the previous mask. */

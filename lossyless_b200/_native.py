@@ -76,6 +76,11 @@ _SIGNATURES = {
     "ll_vit_block_backward_scratch_elems": (c_int64, [c_int64, c_int, c_int]),
     "ll_vit_block_forward": (c_int, [POINTER(VitBlockParams), _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "ll_vit_block_backward": (c_int, [POINTER(VitBlockParams), _P, _P, _P, _P, POINTER(VitBlockGrads), c_int64, c_int, c_int, c_int, c_int, _P]),
+    "ll_vit_block_cls_x2_offset_elems": (c_int64, [c_int64, c_int, c_int]),
+    "ll_vit_block_forward_cls": (c_int, [POINTER(VitBlockParams), _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "ll_vit_block_backward_cls": (c_int, [POINTER(VitBlockParams), _P, _P, _P, _P, _P, POINTER(VitBlockGrads), c_int64, c_int, c_int, c_int, c_int, _P]),
+    "ll_gather_cls_rows": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "ll_scatter_cls_rows": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "ll_sumsq_scratch_floats": (c_int, []),
     "ll_sumsq": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P]),
     "ll_adamw_flat": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, _P, _P]),

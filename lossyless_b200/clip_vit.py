@@ -514,6 +514,9 @@ def _ln_backward(x, g_h, gamma, g_res=None, out_w=None, out_b=None):
 # Native per-block runner (csrc/vit_train_runner.cu): one call per block and direction instead of ~13 / ~26 Python-issued
 # launches.  False = the Python-sequenced path (kept as a cross-check in the tests and for A/B runs).
 NATIVE_BLOCKS = os.environ.get("LL_NATIVE_BLOCKS", "1") != "0"
+# The last block's out-projection / ln_2 / MLP (forward, data and weight gradients) on the class-token rows only -- the only
+# rows VisionTransformer.forward keeps (x[:, 0, :]); native runner only.  False = every row (A/B, cross-check).
+CLS_LAST_BLOCK = os.environ.get("LL_CLS_LAST_BLOCK", "1") != "0"
 
 _BLOCK_FIELDS = (("in_proj_w", "attn.in_proj_weight"), ("out_proj_w", "attn.out_proj.weight"), ("fc_w", "mlp.c_fc.weight"),
                  ("cproj_w", "mlp.c_proj.weight"), ("in_proj_b", "attn.in_proj_bias"), ("out_proj_b", "attn.out_proj.bias"),
@@ -560,10 +563,17 @@ class _VitTrainFn(torch.autograd.Function):
             x2_off = int(N.load().ll_vit_block_x2_offset_elems(B, S, Wd))
             arena = torch.empty((vit.layers, act_elems), dtype=dt, device=x.device)  # every block's activation record
             x_in, code = xs, N.dtype_code(xs)
+            cls_last = CLS_LAST_BLOCK
             for i in range(vit.layers):
-                N.call("ll_vit_block_forward", ctypes.byref(blocks[i]), N.ptr(x_in), N.ptr(arena[i]), B, S, vit.heads, Wd, code, N.stream())
                 saved.append(x_in)
-                x_in = arena[i, x2_off: x2_off + M * Wd].view(M, Wd)
+                if cls_last and i == vit.layers - 1:
+                    # the block's output is the [B, width] class-token tensor itself
+                    N.call("ll_vit_block_forward_cls", ctypes.byref(blocks[i]), N.ptr(x_in), N.ptr(arena[i]), B, S, vit.heads, Wd, code, N.stream())
+                    off = int(N.load().ll_vit_block_cls_x2_offset_elems(B, S, Wd))
+                    x_in = arena[i, off: off + B * Wd].view(B, Wd)
+                else:
+                    N.call("ll_vit_block_forward", ctypes.byref(blocks[i]), N.ptr(x_in), N.ptr(arena[i]), B, S, vit.heads, Wd, code, N.stream())
+                    x_in = arena[i, x2_off: x2_off + M * Wd].view(M, Wd)
             saved.append(arena)
             xs = x_in
         for i in range(vit.layers if not NATIVE_BLOCKS else 0):
@@ -580,11 +590,12 @@ class _VitTrainFn(torch.autograd.Function):
             x2 = _gemm(f, w[p + "mlp.c_proj.weight"], w[p + "mlp.c_proj.bias"], residual=x1)
             saved.append((xs, h1, qkv, a, x1, h2, u, f))
             xs = x2
-        xc = xs.view(B, S, Wd)[:, 0].contiguous()
+        cls_rows = NATIVE_BLOCKS and CLS_LAST_BLOCK  # xs is already x[:, 0, :]
+        xc = xs if cls_rows else xs.view(B, S, Wd)[:, 0].contiguous()
         hc = _ln(xc, w["ln_post.weight"], w["ln_post.bias"])
         z = _gemm(hc, w["proj_t"])
         ctx.vit, ctx.names, ctx.w = vit, names, w
-        ctx.state = dict(a_patch=a_patch, tok=tok, saved=saved, xc=xc, hc=hc, B=B, S=S, M=M, native=NATIVE_BLOCKS)
+        ctx.state = dict(a_patch=a_patch, tok=tok, saved=saved, xc=xc, hc=hc, B=B, S=S, M=M, native=NATIVE_BLOCKS, cls_rows=cls_rows)
         ctx.needs = [p.requires_grad for p in params]
         return z.float()
 
@@ -608,9 +619,12 @@ class _VitTrainFn(torch.autograd.Function):
         g_hc = _gemm(gz, w["proj"])                      # [B, 768] = gz [B,512] @ proj[768,512]^T
         G["proj"] = _wgrad(st["hc"], gz, dst("proj"))    # [768, 512]
         g_xc, G["ln_post.weight"], G["ln_post.bias"] = _ln_backward(st["xc"], g_hc, w["ln_post.weight"], out_w=dst("ln_post.weight"), out_b=dst("ln_post.bias"))
-        g_x = torch.zeros((B, S, Wd), dtype=dt, device=dev)
-        g_x[:, 0] = g_xc
-        g_x = g_x.view(M, Wd)
+        if st["cls_rows"]:
+            g_x = torch.empty((M, Wd), dtype=dt, device=dev)  # written by the last block's backward
+        else:
+            g_x = torch.zeros((B, S, Wd), dtype=dt, device=dev)
+            g_x[:, 0] = g_xc
+            g_x = g_x.view(M, Wd)
         if st["native"]:
             blocks, arena = w["_blocks"], st["saved"][vit.layers]
             scratch = torch.empty(int(N.load().ll_vit_block_backward_scratch_elems(B, S, Wd)), dtype=dt, device=dev)
@@ -625,8 +639,12 @@ class _VitTrainFn(torch.autograd.Function):
                         G[p + name] = (torch.empty(shape, dtype=dt, device=dev) if _is_matrix(p + name)
                                        else torch.zeros(shape, dtype=torch.float32, device=dev))
                     grads = _block_struct(N.VitBlockGrads, G, i)
-                N.call("ll_vit_block_backward", ctypes.byref(blocks[i]), N.ptr(st["saved"][i]), N.ptr(arena[i]), N.ptr(g_x), N.ptr(scratch),
-                       ctypes.byref(grads), B, S, vit.heads, Wd, code, N.stream())
+                if st["cls_rows"] and i == vit.layers - 1:
+                    N.call("ll_vit_block_backward_cls", ctypes.byref(blocks[i]), N.ptr(st["saved"][i]), N.ptr(arena[i]), N.ptr(g_xc), N.ptr(g_x),
+                           N.ptr(scratch), ctypes.byref(grads), B, S, vit.heads, Wd, code, N.stream())
+                else:
+                    N.call("ll_vit_block_backward", ctypes.byref(blocks[i]), N.ptr(st["saved"][i]), N.ptr(arena[i]), N.ptr(g_x), N.ptr(scratch),
+                           ctypes.byref(grads), B, S, vit.heads, Wd, code, N.stream())
                 if flat is not None:
                     flat.reduce_mat_slice(k)  # this block's four weight gradients (and proj, with the last block) are final
             st["saved"] = None

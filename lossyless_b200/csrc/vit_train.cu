@@ -841,6 +841,40 @@ static int g_attention_bwd_impl = 0;  // 0 = ldmatrix kernel, 1 = fp32 CUDA-core
 
 using namespace ll;
 
+// ------------------------------------------------------------------------- class-token rows (last block of the tower)
+// gather: row b of the outputs = row b * S of the inputs (two tensors at once); scatter: the reverse into zero-filled
+// [B * S, W] tensors.  16-byte pieces; element type irrelevant (2-byte elements, W % 8 == 0).
+__global__ void __launch_bounds__(256)
+gather_cls2_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ x, uint4 *__restrict__ a_c, uint4 *__restrict__ x_c, int64_t B, int64_t S,
+                   int W8)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= B * W8) return;
+    const int64_t b = i / W8;
+    const int c = (int)(i % W8);
+    a_c[i] = a[b * S * W8 + c];
+    x_c[i] = x[b * S * W8 + c];
+}
+
+__global__ void __launch_bounds__(256)
+scatter_cls2_kernel(const uint4 *__restrict__ a_c, const uint4 *__restrict__ x_c, uint4 *__restrict__ a, uint4 *__restrict__ x, int64_t B, int64_t S,
+                    int W8)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const int64_t total = B * S * W8;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t row = i / W8;
+        const int c = (int)(i % W8);
+        const bool cls = row % S == 0;
+        const int64_t b = row / S;
+        a[i] = cls ? a_c[b * W8 + c] : make_uint4(0, 0, 0, 0);
+        x[i] = cls ? x_c[b * W8 + c] : make_uint4(0, 0, 0, 0);
+    }
+}
+
 #define LL_DISPATCH_16(dtype, CALL_F16, CALL_BF16, name)                                 \
     switch (dtype) {                                                                     \
         case LL_F16: CALL_F16; break;                                                    \
@@ -999,5 +1033,34 @@ extern "C" int ll_attention_backward_set_impl(int impl)
 {
     LL_REQUIRE(impl >= 0 && impl <= 2, "attention_backward_set_impl: 0 = ldmatrix mma.sync kernel, 1 = fp32 CUDA-core kernel, 2 = first mma.sync kernel");
     g_attention_bwd_impl = impl;
+    return LL_OK;
+}
+
+extern "C" int ll_gather_cls_rows(const void *a, const void *x, void *a_c, void *x_c, int64_t batch, int S, int width, int dtype,
+                                  ll_stream_t stream)
+{
+    LL_REQUIRE(a && x && a_c && x_c && batch > 0 && S > 0 && width > 0 && width % 8 == 0, "gather_cls_rows: bad arguments");
+    LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "gather_cls_rows: dtype must be LL_F16 or LL_BF16");
+    LL_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(a_c) | reinterpret_cast<uintptr_t>(x_c)) & 15) == 0,
+               "gather_cls_rows: tensors must be 16-byte aligned");
+    const int W8 = width / 8;
+    const unsigned grid = (unsigned)((batch * W8 + 255) / 256);
+    LL_CUDA_CHECK(launch_pdl(gather_cls2_kernel, dim3(grid), dim3(256), 0, as_stream(stream), static_cast<const uint4 *>(a), static_cast<const uint4 *>(x),
+                             static_cast<uint4 *>(a_c), static_cast<uint4 *>(x_c), batch, (int64_t)S, W8));
+    return LL_OK;
+}
+
+extern "C" int ll_scatter_cls_rows(const void *a_c, const void *x_c, void *a, void *x, int64_t batch, int S, int width, int dtype,
+                                   ll_stream_t stream)
+{
+    LL_REQUIRE(a && x && a_c && x_c && batch > 0 && S > 0 && width > 0 && width % 8 == 0, "scatter_cls_rows: bad arguments");
+    LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "scatter_cls_rows: dtype must be LL_F16 or LL_BF16");
+    LL_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(a_c) | reinterpret_cast<uintptr_t>(x_c)) & 15) == 0,
+               "scatter_cls_rows: tensors must be 16-byte aligned");
+    const int W8 = width / 8;
+    const int64_t total = batch * S * W8;
+    const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 16);
+    LL_CUDA_CHECK(launch_pdl(scatter_cls2_kernel, dim3(grid), dim3(256), 0, as_stream(stream), static_cast<const uint4 *>(a_c), static_cast<const uint4 *>(x_c),
+                             static_cast<uint4 *>(a), static_cast<uint4 *>(x), batch, (int64_t)S, W8));
     return LL_OK;
 }

@@ -381,6 +381,7 @@ def test_native_block_runner_equals_python_sequencing(cuda_device, monkeypatch):
 
     out = {}
     old_mask = N.load().ll_vit_block_set_fusion(0)  # the Python sequencing has no fused epilogues: compare like with like
+    monkeypatch.setattr(clip_vit, "CLS_LAST_BLOCK", False)  # ... and computes every row of the last block
     try:
         for native in (True, False):
             monkeypatch.setattr(clip_vit, "NATIVE_BLOCKS", native)
@@ -425,3 +426,27 @@ def test_block_runner_fusions_match_unfused(cuda_device, dtype):
     tol = 2e-2 if dtype == torch.bfloat16 else 3e-3
     for n, g in out[0][1].items():
         assert _rel(out[0x7FFFFFFF][1][n], g) < tol, n
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_cls_only_last_block_training_matches_all_rows(cuda_device, dtype, monkeypatch):
+    """The last block's out-projection / ln_2 / MLP -- forward, data and weight gradients -- on the class-token rows only
+    (default) against the same runner computing every row: identical z (same per-element accumulation order), every
+    parameter gradient equal up to the summation order of the weight-gradient reductions (B terms instead of B * S
+    with zeros in between)."""
+    from lossyless_b200 import clip_vit
+
+    out = {}
+    for cls in (True, False):
+        monkeypatch.setattr(clip_vit, "CLS_LAST_BLOCK", cls)
+        vit, sd, cfg = _trainable_vit(cuda_device, 3, dtype)
+        gen = torch.Generator().manual_seed(13)
+        x = torch.randn(7, 3, 224, 224, generator=gen).to(cuda_device)
+        r = torch.randn(7, 512, generator=gen).to(cuda_device)
+        z = vit(x)
+        (z * r).sum().backward()
+        out[cls] = (z.detach().clone(), {n: p.grad.float().clone() for n, p in vit.named_parameters()})
+    assert torch.equal(out[True][0], out[False][0])
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-3
+    for n, g in out[False][1].items():
+        assert _rel(out[True][1][n], g) < tol, n
