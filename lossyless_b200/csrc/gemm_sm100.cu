@@ -696,23 +696,35 @@ static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUten
     return LL_OK;
 }
 
-// Tile choice.  The persistent grid runs ceil(tiles / workers) rounds of one tile each, so the cost
-// of a candidate is rounds * BN (the partially filled last round is what hurts: N = 768 with
-// 128 x 256 tiles at M = 12 800 is 300 tiles = 3 rounds for 2.03 rounds of work).  Narrower tiles
-// re-read A more often, hence the small penalty.  CTA pairs (256-row tiles on 74 workers) are
-// preferred whenever the problem has at least one full round of them.
+// Tile choice by a small time model (microseconds): the persistent grid runs ceil(tiles / workers) rounds of one tile
+// each, and a round costs a fixed part (pipeline fill, epilogue drain of the last tile: ~1.5 us) plus K / 64 K-blocks at a
+// per-block time that depends on the tile shape.  The per-block times are measured on this kernel at the encoder's
+// shapes (tools/gemm_bench.py, 32 ... 1512 images per pass, profiles/r02_gemm_small_batches.txt): a CTA of a pair stages
+// half of the W tile, so 256 x 256 pair tiles do the most work per SM and per staged byte; 128 x 64 single-CTA tiles
+// the least.  (Round 1 ranked candidates by rounds x tile width alone and never paired CTAs below one full round of
+// pair tiles: at 128 images that chose 128 x 64 tiles for the two N = 768 GEMMs -- 86 us for c_proj where 256 x 192
+// pair tiles take 45 -- and 7 rounds of 128 x 128 tiles for the in-projection where 4 rounds of 256 x 256 do.)
+// The result does not depend on the choice: an output element's accumulation order over K is the same for every
+// tile shape.
 static bool g_splitk_enabled = true;  // ll_gemm_set_splitk (A/B knob)
 static int g_force_bn = 0;    // test / tuning overrides (ll_gemm_set_tile_n, ll_gemm_set_cta_pair)
 static int g_pair_mode = -1;  // -1 auto, 0 never, 1 always
 
-static void pick_tile(int64_t M, int N, int &bn_out, int &ctas_out)
+static double kblock_us(int ctas, int bn)
+{
+    if (ctas == 2) return bn == 256 ? 0.44 : bn == 192 ? 0.39 : 0.36;
+    return bn == 256 ? 0.51 : bn == 192 ? 0.40 : bn == 128 ? 0.31 : 0.30;
+}
+
+static void pick_tile(int64_t M, int N, int K, int &bn_out, int &ctas_out)
 {
     const int sms = num_sms();
     int best_bn = 0, best_ctas = 1;
     double best_cost = 0.0;
     const int cands[4] = {256, 192, 128, 64};
+    const double num_kb = (double)((K + kBK - 1) / kBK);
     for (int ctas = 2; ctas >= 1; --ctas) {
-        if (ctas == 2 && (g_pair_mode == 0 || (g_pair_mode < 0 && M < 128 * (sms / 2)))) continue;
+        if (ctas == 2 && (g_pair_mode == 0 || (g_pair_mode < 0 && M <= kBM))) continue;  // a pair needs two row blocks
         if (ctas == 1 && g_pair_mode == 1) continue;
         const int64_t mt = (M + kBM * ctas - 1) / (kBM * ctas);
         const int workers = sms / ctas;
@@ -722,9 +734,8 @@ static void pick_tile(int64_t M, int N, int &bn_out, int &ctas_out)
             if (ctas == 2 && bn == 64) continue;  // 32-row W halves are not worth a pair
             const int64_t tiles = mt * (N / bn);
             const int64_t rounds = (tiles + workers - 1) / workers;
-            const double penalty = (bn == 256 ? 1.0 : bn == 192 ? 1.02 : bn == 128 ? 1.06 : 1.2) * (ctas == 2 ? 0.85 : 1.0);
-            const double cost = (double)rounds * bn * penalty;
-            if (best_bn == 0 || cost < best_cost) best_bn = bn, best_ctas = ctas, best_cost = cost;
+            const double cost = (double)rounds * (1.5 + num_kb * kblock_us(ctas, bn));
+            if (best_bn == 0 || cost < best_cost - 1e-9) best_bn = bn, best_ctas = ctas, best_cost = cost;
         }
     }
     bn_out = best_bn;
@@ -783,7 +794,7 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
                "gemm: D / residual / bias must be 16-byte aligned");
     LL_REQUIRE((act & 0xff) != 2 || (residual != nullptr && residual != D), "gemm: act 2 (QuickGELU backward) needs the pre-activation as `residual`, distinct from D");
     int bn = 0, ctas = 1;
-    pick_tile(M, N, bn, ctas);
+    pick_tile(M, N, K, bn, ctas);
     CUtensorMap ta, tw, td, tr;
     int rc = make_tmap_2d(&ta, A, dtype, M, K, kBM);
     if (rc != LL_OK) return rc;
@@ -809,7 +820,7 @@ int gemm_patch_launch(const void *x, const void *W, void *D, int64_t n_images, i
     const int64_t M = n_images * kPatchRowsPerImage;
     const int K = 3 * patch * patch;
     int bn = 0, ctas = 1;
-    pick_tile(M, N, bn, ctas);
+    pick_tile(M, N, K, bn, ctas);
     CUtensorMap ta, tw, td;
     int rc = make_tmap_patch5d(&ta, x, dtype, n_images, res, patch);
     if (rc != LL_OK) return rc;
@@ -889,8 +900,12 @@ int gemm_tn_launch(const void *A, const void *B, void *D, int64_t Kt, int Mo, in
     LL_REQUIRE(Kt > 0 && Mo > 0 && No > 0 && Mo % 128 == 0 && No % 64 == 0, "gemm_tn: need Mo %% 128 == 0 and No %% 64 == 0 (Kt=%lld Mo=%d No=%d)", (long long)Kt, Mo, No);
     LL_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0, "gemm_tn: D must be 16-byte aligned");
     int bn = 0, ctas = 1;
-    pick_tile(Mo, No, bn, ctas);
+    pick_tile(Mo, No, (int)std::min<int64_t>(Kt, 1 << 30), bn, ctas);
     if (ctas == 2 && (bn == 192 || Mo % 256 != 0)) {  // a pair stages BN / 2 columns of B per CTA: whole 64-column atoms only
+        const int saved_mode = g_pair_mode;
+        g_pair_mode = 0;  // the best single-CTA tile instead
+        pick_tile(Mo, No, (int)std::min<int64_t>(Kt, 1 << 30), bn, ctas);
+        g_pair_mode = saved_mode;
         ctas = 1;
         if (g_pair_mode == 1 && No % 256 == 0 && Mo % 256 == 0) ctas = 2, bn = 256;
     }
