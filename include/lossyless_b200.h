@@ -336,6 +336,12 @@ int ll_vit_set_fuse_layernorm(ll_vit_t *v, int on);
  * the model's 16-bit dtype; 0: always go through the im2col copy (patchify kernel).  A/B and fallback knob. */
 int ll_vit_set_direct_patch(ll_vit_t *v, int on);
 
+/* im2col of CLIP's conv1 (kernel = stride = patch) with the cast to the model's 16-bit type in the same pass:
+ * x [n_images, 3, res, res] (x_dtype LL_F32 / LL_F16 / LL_BF16, NCHW) -> A [n_images * (res/patch)^2, 3 * patch^2] (dtype),
+ * row = patch (gy, gx) of image b, columns (channel, py, px).  The fine-tuning forward writes each view of a batch
+ * straight into its slice of one A (no float32 concatenation of the views, no separate cast). */
+int ll_patchify(const void *x, int x_dtype, void *A, int64_t n_images, int res, int patch, int dtype, ll_stream_t stream);
+
 /* 1 (default): in the LAST ResidualAttentionBlock everything after the attention core runs on the class-token rows only
  * (batch rows instead of batch * tokens: the out-projection, ln_2 and the MLP are row-wise and
  * VisionTransformer.forward keeps x[:, 0, :] alone -- clip/model.py, reached from hub/compressor.py:93), which removes

@@ -118,6 +118,7 @@ _SIGNATURES = {
     "ll_gemm_patch_embed": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
     "ll_vit_set_direct_patch": (c_int, [_P, c_int]),
     "ll_vit_set_cls_last_block": (c_int, [_P, c_int]),
+    "ll_patchify": (c_int, [_P, c_int, _P, c_int64, c_int, c_int, c_int, _P]),
     "ll_gemm_ln": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, _P]),
     "ll_gemm_set_tile_n": (c_int, [c_int]),
     "ll_gemm_set_cta_pair": (c_int, [c_int]),

@@ -128,5 +128,12 @@ class PretrainedSSL(nn.Module):
         z = self.encoder(X).float()
         return z.unflatten(dim=-1, sizes=self.out_shape)
 
+    def forward_views(self, Xs):
+        """``forward(torch.cat(Xs))`` without the concatenated copy (CondDist.forward_many: the two views of a step)."""
+        if not hasattr(self.encoder, "forward_views"):
+            return self.forward(torch.cat(list(Xs), dim=0))
+        z = self.encoder.forward_views(Xs).float()
+        return z.unflatten(dim=-1, sizes=self.out_shape)
+
     def reset_parameters(self):
         pass  # pretrained / seeded weights are kept

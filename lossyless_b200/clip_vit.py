@@ -277,6 +277,11 @@ class VisionTransformer(nn.Module):
         self._flat_enabled, self._flat = False, None
         return self
 
+    def forward_views(self, xs):
+        """``forward(torch.cat(xs))`` for a list of image batches (the two views of a contrastive step) without
+        materialising the concatenation: the fine-tuning path patchifies each view straight into its slice."""
+        return self.forward(tuple(xs))
+
     def forward(self, x, out=None):
         """x [B,3,R,R] (fp16 / bf16 / fp32, cuda, CLIP-normalised) -> z [B, output_dim].
         Frozen encoder / no grad: the model's 16-bit dtype (the reference's fp16 ``self.clip(X)``);
@@ -287,6 +292,8 @@ class VisionTransformer(nn.Module):
                 raise ValueError("out= is not supported on the fine-tuning path")
             names, params = zip(*self.named_parameters())
             return _VitTrainFn.apply(self, x, names, *params)
+        if isinstance(x, (tuple, list)):
+            x = torch.cat(list(x), dim=0)
         if self._native is not None and self._native.get("stale"):
             self._native = None  # parameters were updated by an optimiser step since the views were made
         with torch.no_grad():
@@ -538,19 +545,35 @@ class _VitTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, vit, x, names, *params):
-        N.require_cuda(x, "x")
+        views = tuple(x) if isinstance(x, (tuple, list)) else (x,)
         R, P, Wd = vit.input_resolution, vit.patch_size, vit.width
-        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != R or x.shape[3] != R:
-            raise ValueError(f"expected [B,3,{R},{R}] images, got {tuple(x.shape)}")
-        if x.shape[0] == 0:
+        for v in views:
+            N.require_cuda(v, "x")
+            if v.dim() != 4 or v.shape[1] != 3 or v.shape[2] != R or v.shape[3] != R:
+                raise ValueError(f"expected [B,3,{R},{R}] images, got {tuple(v.shape)}")
+        x = views[0]
+        B = sum(int(v.shape[0]) for v in views)
+        if B == 0:
             raise ValueError("the fine-tuning path needs a non-empty batch")
         dt = vit._train_dtype
         w = vit._train_weights(dt)
-        B, g = x.shape[0], R // P
+        g = R // P
         S = g * g + 1
         M = B * S
-        # im2col is pure data movement: [B,3,g,P,g,P] -> [B*g*g, 3*P*P]
-        a_patch = x.to(dt).reshape(B, 3, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(B * g * g, 3 * P * P).contiguous()
+        # im2col is pure data movement: [B,3,g,P,g,P] -> [B*g*g, 3*P*P]; ll_patchify does it together with the cast to the
+        # 16-bit type, one view at a time into its slice (no float32 concatenation of the views, no separate cast)
+        a_patch = torch.empty((B * g * g, 3 * P * P), dtype=dt, device=x.device)
+        row = 0
+        for v in views:
+            if v.shape[0] == 0:
+                continue
+            if v.dtype in (torch.float32, torch.float16, torch.bfloat16) and 3 * P * P % 8 == 0:
+                vc = v.contiguous()
+                N.call("ll_patchify", N.ptr(vc), N.dtype_code(vc), N.ptr(a_patch[row:]), vc.shape[0], R, P, N.dtype_code(a_patch), N.stream())
+            else:
+                n = v.shape[0]
+                a_patch[row: row + n * g * g] = v.to(dt).reshape(n, 3, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(n * g * g, 3 * P * P)
+            row += v.shape[0] * g * g
         patch = _gemm(a_patch, w["conv1.weight"])
         tok = (torch.cat([w["class_embedding"].expand(B, 1, Wd), patch.view(B, g * g, Wd)], 1) + w["positional_embedding"]).reshape(M, Wd)
         xs = _ln(tok, w["ln_pre.weight"], w["ln_pre.bias"])

@@ -897,6 +897,15 @@ extern "C" int ll_vit_set_direct_patch(ll_vit_t *v, int on)
     return LL_OK;
 }
 
+extern "C" int ll_patchify(const void *x, int x_dtype, void *A, int64_t n_images, int res, int patch, int dtype, ll_stream_t stream)
+{
+    LL_REQUIRE(x && A && n_images > 0 && res > 0 && patch > 0 && res % patch == 0 && (3 * patch * patch) % 8 == 0, "patchify: bad arguments");
+    LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "patchify: dtype must be LL_F16 or LL_BF16");
+    LL_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0, "patchify: A must be 16-byte aligned");
+    if (dtype == LL_F16) return launch_patchify<__half>(x, x_dtype, static_cast<__half *>(A), n_images, res, patch, as_stream(stream));
+    return launch_patchify<__nv_bfloat16>(x, x_dtype, static_cast<__nv_bfloat16 *>(A), n_images, res, patch, as_stream(stream));
+}
+
 extern "C" int ll_vit_set_cls_last_block(ll_vit_t *v, int on)
 {
     LL_REQUIRE(v != nullptr, "vit_set_cls_last_block: null handle");

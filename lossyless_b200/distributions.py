@@ -33,7 +33,11 @@ class CondDist(nn.Module):
     def forward_many(self, xs):
         """``[forward(x) for x in xs]`` through ONE mapper call on the concatenated batch.  Only valid for
         mappers that treat samples independently (no batch statistics): the caller checks."""
-        out = self.mapper(torch.cat(list(xs), dim=0))
+        xs = list(xs)
+        if hasattr(self.mapper, "forward_views"):
+            out = self.mapper.forward_views(xs)  # no concatenated copy of the (float32) views
+        else:
+            out = self.mapper(torch.cat(xs, dim=0))
         sizes = [x.shape[0] for x in xs]
         return [self.Family.from_suff_param(o, **self.kwargs) for o in out.split(sizes, dim=0)]
 

@@ -450,3 +450,24 @@ def test_cls_only_last_block_training_matches_all_rows(cuda_device, dtype, monke
     tol = 1e-2 if dtype == torch.bfloat16 else 2e-3
     for n, g in out[False][1].items():
         assert _rel(out[True][1][n], g) < tol, n
+
+
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.float16])
+def test_forward_views_equals_forward_of_the_concatenation(cuda_device, in_dtype):
+    """VisionTransformer.forward_views([x, x_pos]) (ll_patchify per view, straight into one im2col buffer) is
+    forward(torch.cat([x, x_pos])) -- values and gradients -- on the fine-tuning path and on the frozen one."""
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(3, 3, 224, 224, generator=gen).to(cuda_device).to(in_dtype)
+    xp = torch.randn(5, 3, 224, 224, generator=gen).to(cuda_device).to(in_dtype)
+    r = torch.randn(8, 512, generator=gen).to(cuda_device)
+    out = {}
+    for how in ("views", "cat"):
+        vit, sd, cfg = _trainable_vit(cuda_device, 2, torch.bfloat16)
+        z = vit.forward_views([x, xp]) if how == "views" else vit(torch.cat([x, xp]))
+        (z * r).sum().backward()
+        out[how] = (z.detach().clone(), {n: p.grad.float().clone() for n, p in vit.named_parameters()})
+    assert torch.equal(out["views"][0], out["cat"][0])
+    for n, g in out["cat"][1].items():
+        assert torch.equal(out["views"][1][n], g) or _rel(out["views"][1][n], g) < 1e-5, n
+    with torch.no_grad():  # frozen path: a plain concatenation
+        assert torch.equal(vit.forward_views([x, xp]), vit(torch.cat([x, xp])))
