@@ -327,7 +327,7 @@ def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (average over one block's four GEMMs) from the
     committed ncu --set full capture; None if the summary is not in the tree."""
     prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles")
-    for name in ("r02_ncu_vit_gemms_dram_traffic.json", "r01_ncu_vit_gemms_dram_traffic.json"):
+    for name in ("r02_ncu_vit_gemms_dram_traffic_final.json", "r02_ncu_vit_gemms_dram_traffic.json", "r01_ncu_vit_gemms_dram_traffic.json"):
         try:
             with open(os.path.join(prof, name)) as f:
                 return float(json.load(f)["per_launch_dram_bytes_layer_average"]), name
