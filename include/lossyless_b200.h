@@ -243,7 +243,8 @@ int ll_gather_cls_rows(const void *a, const void *x, void *a_c, void *x_c, int64
 int ll_scatter_cls_rows(const void *a_c, const void *x_c, void *a, void *x, int64_t batch, int S, int width, int dtype,
                         ll_stream_t stream);
 /* Which fusions ll_vit_block_forward / ll_vit_block_backward use (A/B knob, tests): bit 0 = QuickGELU backward inside
- * the c_proj data-gradient GEMM's epilogue (ll_gemm act 2) instead of a separate ll_quickgelu_backward pass.
+ * the c_proj data-gradient GEMM's epilogue (ll_gemm act 2) instead of a separate ll_quickgelu_backward pass; bit 1 =
+ * data gradients read from the untransposed weights (ll_gemm_nn) instead of four ll_transpose_pad copies per block.
  * Default: all on.  Returns the previous mask. */
 int ll_vit_block_set_fusion(int mask);
 
@@ -403,6 +404,13 @@ int ll_gemm_patch_embed(const void *x, const void *W, void *D, int64_t n_images,
  * gradients -- no transposed copies.  A, B, D in `dtype` (LL_F16 / LL_BF16), fp32 accumulation.
  * Mo % 128 == 0, No % 64 == 0, Kt arbitrary (rows past Kt are zero-filled by TMA). */
 int ll_gemm_tn(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, ll_stream_t stream);
+
+/* D[M,N] = act(A[M,K] @ B[K,N] + bias) (+ residual) with B ROW-MAJOR [K, N] (an MN-major tcgen05 operand: 64 x 64 TMA
+ * boxes, transpose bit of the instruction descriptor): the data gradient dX = dY @ W of a linear layer straight from the
+ * weight as nn.Linear stores it ([out, in] = [K, N]) -- replaces autograd's `grad_output.matmul(weight)` without a
+ * transposed weight copy.  Same epilogue options as ll_gemm (act 0 / 1 / 2).  K % 64 == 0, N % 64 == 0. */
+int ll_gemm_nn(const void *A, const void *B, const float *bias, const void *residual, void *D, int64_t M, int N, int K,
+               int dtype, int act, ll_stream_t stream);
 
 /* ll_gemm_tn with split-K: when the output is only a fraction of a round of tiles (a [768..3072]^2 weight gradient is
  * 36-144 tiles for a 25 600-deep reduction) the reduction is split 2-4 ways over otherwise idle SMs, every split leaves a

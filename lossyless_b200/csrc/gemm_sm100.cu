@@ -213,6 +213,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int num_tiles = num_m * num_n;
     const int num_kb = K / kBK;
     const bool tn = (act & 0x2000) != 0;  // both operands MN-major (transposed): D = A^T B
+    // B alone MN-major (act bit 0x40000): D = A B with B given as [K, N] row-major -- the data gradient dX = dY W read from
+    // the weight as nn.Linear stores it ([out, in] = [K, N]), no transposed copy
+    const bool bmn = (act & 0x40000) != 0 && !tn;
     // patch-embedding mode: A is the image batch itself (5-D map); bits 16.. of `act` hold the K blocks per channel
     const bool patch_mode = (act & 0x8000) != 0;
     const int kb_per_channel = act >> 16;
@@ -250,6 +253,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             ptx::mbar_expect_tx(&full_bar[stage], S::kStageBytes);
                             for (int h = 0; h < kBM / 64; ++h)
                                 ptx::tma_load_2d(sm_a + stage * kABytes + h * 8192, &tmap_a, &full_bar[stage], m0 + 64 * h, kb * kBK);
+                            for (int h = 0; h < S::kBRows / 64; ++h)
+                                ptx::tma_load_2d(sm_b + stage * S::kBBytes + h * 8192, &tmap_w, &full_bar[stage], n0 + 64 * h, kb * kBK);
+                        }
+                    } else if (bmn) {
+                        // A K-major as usual; B arrives as 64-column x 64-row boxes of the [K, N] matrix, one per 64-element
+                        // N atom (MN-major SWIZZLE_128B layout, as in the TN mode)
+                        if constexpr (kCtas == 2) {
+                            const uint32_t lead_bar = ptx::map_to_cta(&full_bar[stage], 0);
+                            if (cta_rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+                            ptx::tma_load_2d_pair(sm_a + stage * kABytes, &tmap_a, lead_bar, kb * kBK, m0);
+                            for (int h = 0; h < S::kBRows / 64; ++h)
+                                ptx::tma_load_2d_pair(sm_b + stage * S::kBBytes + h * 8192, &tmap_w, lead_bar, n0 + 64 * h, kb * kBK);
+                        } else {
+                            ptx::mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+                            ptx::tma_load_2d(sm_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, m0);
                             for (int h = 0; h < S::kBRows / 64; ++h)
                                 ptx::tma_load_2d(sm_b + stage * S::kBBytes + h * 8192, &tmap_w, &full_bar[stage], n0 + 64 * h, kb * kBK);
                         }
@@ -311,19 +329,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     ptx::tc_fence_after();
                     const uint32_t addr_a = ptx::smem_u32(sm_a + stage * kABytes), addr_b = ptx::smem_u32(sm_b + stage * S::kBBytes);
                     const uint64_t da = tn ? ptx::make_mnmajor_sw128_desc(addr_a) : ptx::make_kmajor_sw128_desc(addr_a);
-                    const uint64_t db = tn ? ptx::make_mnmajor_sw128_desc(addr_b) : ptx::make_kmajor_sw128_desc(addr_b);
+                    const uint64_t db = (tn || bmn) ? ptx::make_mnmajor_sw128_desc(addr_b) : ptx::make_kmajor_sw128_desc(addr_b);
                     // per K=16 step: K-major +32 B inside the 128 B swizzle row (start-address field += 2);
                     // MN-major 16 K rows further down (2048 B, field += 128)
                     const uint64_t kstep = tn ? 128 : 2;
-                    const uint32_t id = tn ? (idesc | (1u << 15) | (1u << 16)) : idesc;
+                    const uint64_t kstep_b = (tn || bmn) ? 128 : 2;
+                    const uint32_t id = tn ? (idesc | (1u << 15) | (1u << 16)) : bmn ? (idesc | (1u << 16)) : idesc;
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
                         // patch mode: A is two SWIZZLE_64B sub-blocks of 32 K-columns (8192 B apart), two K = 16 steps each
                         const uint64_t dak = patch_mode ? ptx::make_kmajor_sw64_desc(addr_a + (k >> 1) * 8192) + 2 * (k & 1) : da + kstep * k;
                         if constexpr (kCtas == 2)
-                            ptx::mma_f16_ss_pair(tmem_d, dak, db + kstep * k, id, ((kb - kb_begin) | k) != 0);
+                            ptx::mma_f16_ss_pair(tmem_d, dak, db + kstep_b * k, id, ((kb - kb_begin) | k) != 0);
                         else
-                            ptx::mma_f16_ss(tmem_d, dak, db + kstep * k, id, ((kb - kb_begin) | k) != 0);
+                            ptx::mma_f16_ss(tmem_d, dak, db + kstep_b * k, id, ((kb - kb_begin) | k) != 0);
                     }
                     // frees the smem stage (in both CTAs) when the MMAs retire
                     if constexpr (kCtas == 2)
@@ -716,7 +735,7 @@ static double kblock_us(int ctas, int bn)
     return bn == 256 ? 0.51 : bn == 192 ? 0.40 : bn == 128 ? 0.31 : 0.30;
 }
 
-static void pick_tile(int64_t M, int N, int K, int &bn_out, int &ctas_out)
+static void pick_tile(int64_t M, int N, int K, int &bn_out, int &ctas_out, bool mn_major_b = false)
 {
     const int sms = num_sms();
     int best_bn = 0, best_ctas = 1;
@@ -732,6 +751,7 @@ static void pick_tile(int64_t M, int N, int K, int &bn_out, int &ctas_out)
             if (N % bn != 0) continue;
             if (g_force_bn && bn != g_force_bn && N % g_force_bn == 0) continue;
             if (ctas == 2 && bn == 64) continue;  // 32-row W halves are not worth a pair
+            if (mn_major_b && ctas == 2 && bn == 192) continue;  // a CTA of a pair stages whole 64-column atoms of an MN-major B
             const int64_t tiles = mt * (N / bn);
             const int64_t rounds = (tiles + workers - 1) / workers;
             const double cost = (double)rounds * (1.5 + num_kb * kblock_us(ctas, bn));
@@ -808,6 +828,35 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
         if (rc != LL_OK) return rc;
     }
     return gemm_launch_tmaps(ta, tw, td, tr, bn, ctas, bias, residual != nullptr, M, N, K, dtype, act, stream);
+}
+
+// D[M, N] = act(A[M, K] @ B[K, N] + bias) (+ residual): B row-major [K, N] (MN-major operand).  The data gradient of a
+// linear layer, dX = dY @ W with W as nn.Linear stores it -- no transposed weight copy.
+int gemm_nn_launch(const void *A, const void *B, const float *bias, const void *residual, void *D, int64_t M, int N, int K, int dtype, int act,
+                   cudaStream_t stream)
+{
+    LL_REQUIRE(A && B && D, "gemm_nn: null pointer");
+    LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "gemm_nn: dtype must be LL_F16 or LL_BF16");
+    LL_REQUIRE(M > 0 && N > 0 && K > 0 && K % kBK == 0 && N % 64 == 0, "gemm_nn: need K %% 64 == 0 and N %% 64 == 0 (M=%lld N=%d K=%d)", (long long)M, N, K);
+    LL_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0 && (!residual || (reinterpret_cast<uintptr_t>(residual) & 15) == 0) &&
+                   (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+               "gemm_nn: D / residual / bias must be 16-byte aligned");
+    LL_REQUIRE((act & 0xff) != 2 || (residual != nullptr && residual != D), "gemm_nn: act 2 (QuickGELU backward) needs the pre-activation as `residual`, distinct from D");
+    int bn = 0, ctas = 1;
+    pick_tile(M, N, K, bn, ctas, true);
+    CUtensorMap ta, tw, td, tr;
+    int rc = make_tmap_2d(&ta, A, dtype, M, K, kBM);
+    if (rc != LL_OK) return rc;
+    rc = make_tmap_2d(&tw, B, dtype, K, N, 64);  // 64-row (K) x 64-column (N) boxes
+    if (rc != LL_OK) return rc;
+    rc = make_tmap_2d(&td, D, dtype, M, N, 32);
+    if (rc != LL_OK) return rc;
+    tr = td;
+    if (residual != nullptr && residual != D) {
+        rc = make_tmap_2d(&tr, residual, dtype, M, N, 32);
+        if (rc != LL_OK) return rc;
+    }
+    return gemm_launch_tmaps(ta, tw, td, tr, bn, ctas, bias, residual != nullptr, M, N, K, dtype, (act & 0xff) | 0x40000, stream);
 }
 
 int gemm_patch_launch(const void *x, const void *W, void *D, int64_t n_images, int N, int res, int patch, int dtype, cudaStream_t stream)
@@ -947,6 +996,12 @@ int gemm_tn_launch(const void *A, const void *B, void *D, int64_t Kt, int Mo, in
 extern "C" int ll_gemm_tn(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, ll_stream_t stream)
 {
     return ll::gemm_tn_launch(A, B, D, Kt, Mo, No, dtype, ll::as_stream(stream), nullptr, 0);
+}
+
+extern "C" int ll_gemm_nn(const void *A, const void *B, const float *bias, const void *residual, void *D, int64_t M, int N, int K, int dtype,
+                          int act, ll_stream_t stream)
+{
+    return ll::gemm_nn_launch(A, B, bias, residual, D, M, N, K, dtype, act, ll::as_stream(stream));
 }
 
 extern "C" int64_t ll_gemm_tn_workspace_bytes(int Mo, int No) { return ll::gemm_tn_workspace_bytes(Mo, No); }

@@ -107,29 +107,38 @@ extern "C" int ll_vit_block_backward(const ll_vit_block_params_t *w, const void 
     void *ws = p;  // split-K workspace (16-byte aligned: every piece above is a multiple of 128 bytes)
     const int64_t ws_bytes = 64LL * W * W;
     int rc;
-    // W [out, in] -> Wt [in, out]  (transpose_pad(src [R, C]) -> [C, Rpad]; R = out is a multiple of 64 here)
-    if ((rc = ll_transpose_pad(w->cproj_w, cproj_t, W, 4 * W, W, stream))) return rc;
-    if ((rc = ll_transpose_pad(w->fc_w, fc_t, 4 * W, W, 4 * W, stream))) return rc;
-    if ((rc = ll_transpose_pad(w->out_proj_w, out_t, W, W, W, stream))) return rc;
-    if ((rc = ll_transpose_pad(w->in_proj_w, in_t, 3 * W, W, 3 * W, stream))) return rc;
+    // data gradients dX = dY @ W: from the weight as stored ([out, in] = [K, N] row-major, ll_gemm_nn), or -- fusion bit 1
+    // off -- as the K-major GEMM D = A Wt^T over a transposed copy Wt = W^T [in, out] made here
+    const bool nn = (g_fusion & 2) != 0;
+    auto dgrad = [&](const void *dY, const void *Wsrc, const void *Wt, const void *res, void *dX, int64_t m, int n_in, int k_out, int act) {
+        return nn ? ll_gemm_nn(dY, Wsrc, nullptr, res, dX, m, n_in, k_out, dtype, act, stream)
+                  : ll_gemm(dY, Wt, nullptr, res, dX, m, n_in, k_out, dtype, act, stream);
+    };
+    if (!nn) {
+        // W [out, in] -> Wt [in, out]  (transpose_pad(src [R, C]) -> [C, Rpad]; R = out is a multiple of 64 here)
+        if ((rc = ll_transpose_pad(w->cproj_w, cproj_t, W, 4 * W, W, stream))) return rc;
+        if ((rc = ll_transpose_pad(w->fc_w, fc_t, 4 * W, W, 4 * W, stream))) return rc;
+        if ((rc = ll_transpose_pad(w->out_proj_w, out_t, W, W, W, stream))) return rc;
+        if ((rc = ll_transpose_pad(w->in_proj_w, in_t, 3 * W, W, 3 * W, stream))) return rc;
+    }
     // x2 = x1 + f @ c_proj^T + b
     // g_u = (g_x @ c_proj) * QuickGELU'(u): the activation's adjoint rides in the GEMM's epilogue (u arrives as the
     // "residual" tile); unfused: g_f first, then a separate elementwise pass in place
     const bool fuse_gelu_bwd = (g_fusion & 1) != 0;
-    if ((rc = ll_gemm(g_x, cproj_t, nullptr, fuse_gelu_bwd ? v.u : nullptr, g_u, M, 4 * W, W, dtype, fuse_gelu_bwd ? 2 : 0, stream))) return rc;
+    if ((rc = dgrad(g_x, w->cproj_w, cproj_t, fuse_gelu_bwd ? v.u : nullptr, g_u, M, 4 * W, W, fuse_gelu_bwd ? 2 : 0))) return rc;
     if ((rc = ll_gemm_tn_splitk(g_x, v.f, g->cproj_w, M, W, 4 * W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_x, M, W, dtype, g->cproj_b, stream))) return rc;
     if (!fuse_gelu_bwd && (rc = ll_quickgelu_backward(v.u, g_u, g_u, M * 4 * (int64_t)W, dtype, stream))) return rc;  // in place
-    if ((rc = ll_gemm(g_u, fc_t, nullptr, nullptr, g_h2, M, W, 4 * W, dtype, 0, stream))) return rc;
+    if ((rc = dgrad(g_u, w->fc_w, fc_t, nullptr, g_h2, M, W, 4 * W, 0))) return rc;
     if ((rc = ll_gemm_tn_splitk(g_u, v.h2, g->fc_w, M, 4 * W, W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_u, M, 4 * W, dtype, g->fc_b, stream))) return rc;
     if ((rc = ll_layernorm_backward(v.x1, g_h2, w->ln2_w, g_x, g_x1, g->ln2_w, g->ln2_b, M, W, dtype, stream))) return rc;
     // x1 = x + a @ out_proj^T + b
-    if ((rc = ll_gemm(g_x1, out_t, nullptr, nullptr, g_a, M, W, W, dtype, 0, stream))) return rc;
+    if ((rc = dgrad(g_x1, w->out_proj_w, out_t, nullptr, g_a, M, W, W, 0))) return rc;
     if ((rc = ll_gemm_tn_splitk(g_x1, v.a, g->out_proj_w, M, W, W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_x1, M, W, dtype, g->out_proj_b, stream))) return rc;
     if ((rc = ll_attention_backward(v.qkv, g_a, g_qkv, batch, S, heads, dtype, stream))) return rc;
-    if ((rc = ll_gemm(g_qkv, in_t, nullptr, nullptr, g_h1, M, W, 3 * W, dtype, 0, stream))) return rc;
+    if ((rc = dgrad(g_qkv, w->in_proj_w, in_t, nullptr, g_h1, M, W, 3 * W, 0))) return rc;
     if ((rc = ll_gemm_tn_splitk(g_qkv, v.h1, g->in_proj_w, M, 3 * W, W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_qkv, M, 3 * W, dtype, g->in_proj_b, stream))) return rc;
     // dL/dx_in = LN1 backward + the residual branch (g_x1); overwrites g_x, whose old value is dead by now
@@ -225,28 +234,35 @@ extern "C" int ll_vit_block_backward_cls(const ll_vit_block_params_t *w, const v
     void *ws = p;
     const int64_t ws_bytes = 64LL * W * W;
     int rc;
-    if ((rc = ll_transpose_pad(w->cproj_w, cproj_t, W, 4 * W, W, stream))) return rc;
-    if ((rc = ll_transpose_pad(w->fc_w, fc_t, 4 * W, W, 4 * W, stream))) return rc;
-    if ((rc = ll_transpose_pad(w->out_proj_w, out_t, W, W, W, stream))) return rc;
-    if ((rc = ll_transpose_pad(w->in_proj_w, in_t, 3 * W, W, 3 * W, stream))) return rc;
+    const bool nn = (g_fusion & 2) != 0;
+    auto dgrad = [&](const void *dY, const void *Wsrc, const void *Wt, const void *res, void *dX, int64_t m, int n_in, int k_out, int act) {
+        return nn ? ll_gemm_nn(dY, Wsrc, nullptr, res, dX, m, n_in, k_out, dtype, act, stream)
+                  : ll_gemm(dY, Wt, nullptr, res, dX, m, n_in, k_out, dtype, act, stream);
+    };
+    if (!nn) {
+        if ((rc = ll_transpose_pad(w->cproj_w, cproj_t, W, 4 * W, W, stream))) return rc;
+        if ((rc = ll_transpose_pad(w->fc_w, fc_t, 4 * W, W, 4 * W, stream))) return rc;
+        if ((rc = ll_transpose_pad(w->out_proj_w, out_t, W, W, W, stream))) return rc;
+        if ((rc = ll_transpose_pad(w->in_proj_w, in_t, 3 * W, W, 3 * W, stream))) return rc;
+    }
     // x2_c = x1_c + f_c @ c_proj^T + b
     const bool fuse_gelu_bwd = (g_fusion & 1) != 0;
-    if ((rc = ll_gemm(g_x2_c, cproj_t, nullptr, fuse_gelu_bwd ? v.u_c : nullptr, g_u_c, B, 4 * W, W, dtype, fuse_gelu_bwd ? 2 : 0, stream))) return rc;
+    if ((rc = dgrad(g_x2_c, w->cproj_w, cproj_t, fuse_gelu_bwd ? v.u_c : nullptr, g_u_c, B, 4 * W, W, fuse_gelu_bwd ? 2 : 0))) return rc;
     if ((rc = ll_gemm_tn_splitk(g_x2_c, v.f_c, g->cproj_w, B, W, 4 * W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_x2_c, B, W, dtype, g->cproj_b, stream))) return rc;
     if (!fuse_gelu_bwd && (rc = ll_quickgelu_backward(v.u_c, g_u_c, g_u_c, B * 4 * (int64_t)W, dtype, stream))) return rc;
-    if ((rc = ll_gemm(g_u_c, fc_t, nullptr, nullptr, g_h2_c, B, W, 4 * W, dtype, 0, stream))) return rc;
+    if ((rc = dgrad(g_u_c, w->fc_w, fc_t, nullptr, g_h2_c, B, W, 4 * W, 0))) return rc;
     if ((rc = ll_gemm_tn_splitk(g_u_c, v.h2_c, g->fc_w, B, 4 * W, W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_u_c, B, 4 * W, dtype, g->fc_b, stream))) return rc;
     if ((rc = ll_layernorm_backward(v.x1_c, g_h2_c, w->ln2_w, g_x2_c, g_x1_c, g->ln2_w, g->ln2_b, B, W, dtype, stream))) return rc;
     // x1_c = x_c + a_c @ out_proj^T + b
-    if ((rc = ll_gemm(g_x1_c, out_t, nullptr, nullptr, g_a_c, B, W, W, dtype, 0, stream))) return rc;
+    if ((rc = dgrad(g_x1_c, w->out_proj_w, out_t, nullptr, g_a_c, B, W, W, 0))) return rc;
     if ((rc = ll_gemm_tn_splitk(g_x1_c, v.a_c, g->out_proj_w, B, W, W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_x1_c, B, W, dtype, g->out_proj_b, stream))) return rc;
     // back to all rows: dL/da and the residual branch are zero outside the class-token rows
     if ((rc = ll_scatter_cls_rows(g_a_c, g_x1_c, g_a, g_x1, batch, S, W, dtype, stream))) return rc;
     if ((rc = ll_attention_backward(v.qkv, g_a, g_qkv, batch, S, heads, dtype, stream))) return rc;
-    if ((rc = ll_gemm(g_qkv, in_t, nullptr, nullptr, g_h1, M, W, 3 * W, dtype, 0, stream))) return rc;
+    if ((rc = dgrad(g_qkv, w->in_proj_w, in_t, nullptr, g_h1, M, W, 3 * W, 0))) return rc;
     if ((rc = ll_gemm_tn_splitk(g_qkv, v.h1, g->in_proj_w, M, 3 * W, W, dtype, ws, ws_bytes, stream))) return rc;
     if ((rc = ll_colsum(g_qkv, M, 3 * W, dtype, g->in_proj_b, stream))) return rc;
     if ((rc = ll_layernorm_backward(x_in, g_h1, w->ln1_w, g_x1, g_x, g->ln1_w, g->ln1_b, M, W, dtype, stream))) return rc;

@@ -292,3 +292,34 @@ def test_gemm_quickgelu_backward_epilogue(cuda_device, dtype, M, N, K):
 
     with pytest.raises(Nn.NativeError):
         _gemm(A, W, None, None, act=2)
+
+
+@pytest.mark.parametrize("pair", [-1, 0, 1])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(25600, 3072, 768), (2500, 768, 3072), (6400, 768, 768), (300, 768, 2304), (7, 256, 64)])
+def test_gemm_nn_reads_the_weight_as_stored(cuda_device, dtype, M, N, K, pair):
+    """ll_gemm_nn: D = A @ B with B row-major [K, N] (MN-major tcgen05 operand) -- the data gradient dX = dY @ W from
+    the untransposed nn.Linear weight.  Against torch in fp32, and bit-equal to the K-major GEMM over the transposed
+    copy (same accumulation order); with the fused QuickGELU adjoint (act 2) as well."""
+    from lossyless_b200 import _native as Nn
+
+    if pair == 1 and (M <= 128 or N % 128):
+        pytest.skip("forced CTA pairs need two row blocks and 128-column output tiles")
+    g = torch.Generator(device=cuda_device).manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, device=cuda_device).to(dtype)
+    B = (torch.randn(K, N, generator=g, device=cuda_device) * K ** -0.5).to(dtype)
+    u = (2.0 * torch.randn(M, N, generator=g, device=cuda_device)).to(dtype)
+    Nn.call("ll_gemm_set_cta_pair", pair)
+    try:
+        D = torch.full((M, N), float("nan"), dtype=dtype, device=cuda_device)
+        Nn.call("ll_gemm_nn", Nn.ptr(A), Nn.ptr(B), None, None, Nn.ptr(D), M, N, K, Nn.dtype_code(A), 0, Nn.stream())
+        D2 = torch.full((M, N), float("nan"), dtype=dtype, device=cuda_device)
+        Nn.call("ll_gemm_nn", Nn.ptr(A), Nn.ptr(B), None, Nn.ptr(u), Nn.ptr(D2), M, N, K, Nn.dtype_code(A), 2, Nn.stream())
+    finally:
+        Nn.call("ll_gemm_set_cta_pair", -1)
+    ref = A.float() @ B.float()
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-3
+    assert torch.isfinite(D.float()).all()
+    assert (D.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    assert torch.equal(D, _gemm(A, B.t().contiguous()))
+    assert torch.equal(D2, _gemm(A, B.t().contiguous(), None, u, act=2))

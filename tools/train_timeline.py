@@ -22,10 +22,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--splitk", type=int, default=1, help="0: weight gradients in one pass (A/B of ll_gemm_tn_splitk)")
     ap.add_argument("--brief", action="store_true", help="skip the host-side profiler table")
+    ap.add_argument("--fusion", type=lambda v: int(v, 0), default=0x7FFFFFFF, help="ll_vit_block_set_fusion mask (A/B)")
     args = ap.parse_args()
     from lossyless_b200 import _native
 
     _native.call("ll_gemm_set_splitk", args.splitk)
+    _native.load().ll_vit_block_set_fusion(args.fusion)
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     hp = default_clip_hparams(distortion="BINCE", beta=1e-2, max_steps=1000, n_data=50000, is_frozen=False)
