@@ -244,7 +244,8 @@ int ll_scatter_cls_rows(const void *a_c, const void *x_c, void *a, void *x, int6
                         ll_stream_t stream);
 /* Which fusions ll_vit_block_forward / ll_vit_block_backward use (A/B knob, tests): bit 0 = QuickGELU backward inside
  * the c_proj data-gradient GEMM's epilogue (ll_gemm act 2) instead of a separate ll_quickgelu_backward pass; bit 1 =
- * data gradients read from the untransposed weights (ll_gemm_nn) instead of four ll_transpose_pad copies per block.
+ * data gradients read from the untransposed weights (ll_gemm_nn) instead of four ll_transpose_pad copies per block; bit 2 =
+ * QuickGELU forward as a second output of the c_fc GEMM (ll_gemm_dual) instead of a separate ll_quickgelu_forward pass.
  * Default: all on.  Returns the previous mask. */
 int ll_vit_block_set_fusion(int mask);
 
@@ -404,6 +405,12 @@ int ll_gemm_patch_embed(const void *x, const void *W, void *D, int64_t n_images,
  * gradients -- no transposed copies.  A, B, D in `dtype` (LL_F16 / LL_BF16), fp32 accumulation.
  * Mo % 128 == 0, No % 64 == 0, Kt arbitrary (rows past Kt are zero-filled by TMA). */
 int ll_gemm_tn(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, ll_stream_t stream);
+
+/* U[M,N] = A[M,K] @ W[N,K]^T + bias and F = QuickGELU(U) (both in `dtype`; F computed from the rounded U) from ONE GEMM
+ * pass: c_fc of the fine-tuning forward keeps the pre-activation for the backward pass and feeds the activation to c_proj
+ * -- replaces `u = c_fc(h); f = QuickGELU(u)` of clip.model.ResidualAttentionBlock.mlp under autograd. */
+int ll_gemm_dual(const void *A, const void *W, const float *bias, void *U, void *F, int64_t M, int N, int K, int dtype,
+                 ll_stream_t stream);
 
 /* D[M,N] = act(A[M,K] @ B[K,N] + bias) (+ residual) with B ROW-MAJOR [K, N] (an MN-major tcgen05 operand: 64 x 64 TMA
  * boxes, transpose bit of the instruction descriptor): the data gradient dX = dY @ W of a linear layer straight from the

@@ -112,6 +112,7 @@ _SIGNATURES = {
     "ll_clip_preprocess_set_impl": (c_int, [c_int]),
     "ll_gemm_tn": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "ll_gemm_nn": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P]),
+    "ll_gemm_dual": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "ll_gemm_tn_workspace_bytes": (c_int64, [c_int, c_int]),
     "ll_gemm_tn_splitk": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, c_int64, _P]),
     "ll_gemm_set_splitk": (c_int, [c_int]),

@@ -146,7 +146,7 @@ __device__ __forceinline__ uint32_t quick_gelu_h2(uint32_t x)
     return *reinterpret_cast<const uint32_t *>(&o);
 }
 
-template <typename T, int BN, int kCtas>
+template <typename T, int BN, int kCtas, bool kDual = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r,
@@ -213,12 +213,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int num_tiles = num_m * num_n;
     const int num_kb = K / kBK;
     const bool tn = (act & 0x2000) != 0;  // both operands MN-major (transposed): D = A^T B
-    // B alone MN-major (act bit 0x40000): D = A B with B given as [K, N] row-major -- the data gradient dX = dY W read from
-    // the weight as nn.Linear stores it ([out, in] = [K, N]), no transposed copy
-    const bool bmn = (act & 0x40000) != 0 && !tn;
     // patch-embedding mode: A is the image batch itself (5-D map); bits 16.. of `act` hold the K blocks per channel
     const bool patch_mode = (act & 0x8000) != 0;
     const int kb_per_channel = act >> 16;
+    // B alone MN-major (act bit 0x40000): D = A B with B given as [K, N] row-major -- the data gradient dX = dY W read from
+    // the weight as nn.Linear stores it ([out, in] = [K, N]), no transposed copy
+    const bool bmn = (act & 0x40000) != 0 && !tn && !patch_mode;
+    // dual output (act bit 0x80000, c_fc of the fine-tuning forward): tmap_d receives the pre-activation u = A W^T + b,
+    // tmap_r (free: no residual in this mode) the activation QuickGELU(u) -- both are needed by the backward pass
+    // (a template parameter: its 32 extra live registers in the epilogue must not cost the other instantiations anything)
+    constexpr bool dual = kDual;
     // split-K (act bit 0x10000; weight gradients: few output tiles, a very deep reduction): work item = (tile, split),
     // split s reduces K blocks [s nkb / S, (s + 1) nkb / S) and leaves a float32 partial tile in the workspace
     // (passed through the stats_out pointer, S through stats_in_parts); a second kernel adds the partials
@@ -472,6 +476,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     continue;
                 }
+                uint4 gp[8];  // dual output: the activation's 8 x 16-byte pieces wait here until the u tile has left the buffer
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float f[8];
@@ -486,7 +491,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     uint4 *slot = reinterpret_cast<uint4 *>(my_row + ((j ^ swz) << 4));
                     if constexpr (std::is_same<T, __half>::value) {
-                        if ((act & 0xff) == 1 && !has_residual && stats_out == nullptr && !(act & 0x4000)) {
+                        if ((act & 0xff) == 1 && !has_residual && stats_out == nullptr && !(act & 0x4000) && !dual) {
                             uint4 packed;
                             packed.x = quick_gelu_h2(cvt_f16x2_satfinite(f[0], f[1]));
                             packed.y = quick_gelu_h2(cvt_f16x2_satfinite(f[2], f[3]));
@@ -495,6 +500,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             if (!(act & 0x200)) *slot = packed;
                             continue;
                         }
+                    }
+                    if (dual) {
+                        // u first (rounded to the output type, as the separate activation pass would read it back)
+                        const uint4 pre = Pack8<T>::pack(f);
+                        *slot = pre;
+                        float uf[8];
+                        Pack8<T>::unpack(pre, uf);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) uf[e] = quick_gelu(uf[e]);
+                        gp[j] = Pack8<T>::pack(uf);
+                        continue;
                     }
                     if ((act & 0xff) == 1) {
 #pragma unroll
@@ -525,6 +541,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             st_sq = fmaf(f[e], f[e], st_sq);
                         }
                     }
+                }
+                if (dual) {
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmap_d, buf0 + g * kEpiBufBytes, n0 + g * kEpiCols, m0);
+                        ptx::tma_store_commit();
+                        ptx::tma_store_wait_read<0>();  // the u tile has been read out of the staging buffer
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4 *>(my_row + ((j ^ swz) << 4)) = gp[j];
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_2d(&tmap_r, buf0 + g * kEpiBufBytes, n0 + g * kEpiCols, m0);
+                        ptx::tma_store_commit();
+                    }
+                    continue;
                 }
                 if (stats_out != nullptr && m0 + lane < M) {
                     // one part per 64-column group -- a single writer per slot and a summation order that does not
@@ -681,13 +716,13 @@ static thread_local float2 *t_stats_out = nullptr;
 static thread_local int t_stats_in_parts = 0;
 static thread_local int t_stat_width = 1;
 
-template <typename T, int BN, int kCtas>
+template <typename T, int BN, int kCtas, bool kDual = false>
 static int launch_impl(const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr,
                        const float *bias, int has_residual, int64_t M, int N, int K, int act, cudaStream_t stream)
 {
     using S = GemmShape<BN, kCtas>;
     static bool configured = false;
-    auto kern = gemm_tcgen05_kernel<T, BN, kCtas>;
+    auto kern = gemm_tcgen05_kernel<T, BN, kCtas, kDual>;
     if (!configured) {
         LL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kSmemBytes));
         configured = true;
@@ -766,6 +801,17 @@ template <typename T, int kCtas>
 static int launch_bn(int bn, const CUtensorMap &ta, const CUtensorMap &tw, const CUtensorMap &td, const CUtensorMap &tr,
                      const float *bias, int has_residual, int64_t M, int N, int K, int act, cudaStream_t stream)
 {
+    if ((act & 0x80000) && !(act & 0x8000)) {  // dual output: its own instantiations
+        if (has_residual) return fail(LL_ERR_INVALID, "gemm: dual output and a residual operand exclude each other");
+        switch (bn) {
+            case 256: return launch_impl<T, 256, kCtas, true>(ta, tw, td, tr, bias, 0, M, N, K, act, stream);
+            case 192: return launch_impl<T, 192, kCtas, true>(ta, tw, td, tr, bias, 0, M, N, K, act, stream);
+            case 128: return launch_impl<T, 128, kCtas, true>(ta, tw, td, tr, bias, 0, M, N, K, act, stream);
+            case 64:
+                if constexpr (kCtas == 1) return launch_impl<T, 64, 1, true>(ta, tw, td, tr, bias, 0, M, N, K, act, stream);
+        }
+        return fail(LL_ERR_INVALID, "gemm: unsupported tile N %d for %d CTA(s)", bn, kCtas);
+    }
     switch (bn) {
         case 256: return launch_impl<T, 256, kCtas>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
         case 192: return launch_impl<T, 192, kCtas>(ta, tw, td, tr, bias, has_residual, M, N, K, act, stream);
@@ -828,6 +874,28 @@ int gemm_launch(const void *A, const void *W, const float *bias, const void *res
         if (rc != LL_OK) return rc;
     }
     return gemm_launch_tmaps(ta, tw, td, tr, bn, ctas, bias, residual != nullptr, M, N, K, dtype, act, stream);
+}
+
+// U = A W^T + bias and F = QuickGELU(U) from ONE pass (c_fc of the fine-tuning forward keeps both).
+int gemm_dual_launch(const void *A, const void *W, const float *bias, void *U, void *F, int64_t M, int N, int K, int dtype, cudaStream_t stream)
+{
+    LL_REQUIRE(A && W && U && F && U != F, "gemm_dual: null pointer / U and F must differ");
+    LL_REQUIRE(dtype == LL_F16 || dtype == LL_BF16, "gemm_dual: dtype must be LL_F16 or LL_BF16");
+    LL_REQUIRE(M > 0 && N > 0 && K > 0 && K % kBK == 0 && N % 64 == 0, "gemm_dual: need K %% 64 == 0 and N %% 64 == 0 (M=%lld N=%d K=%d)", (long long)M, N, K);
+    LL_REQUIRE(((reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(F)) & 15) == 0 && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0),
+               "gemm_dual: U / F / bias must be 16-byte aligned");
+    int bn = 0, ctas = 1;
+    pick_tile(M, N, K, bn, ctas);
+    CUtensorMap ta, tw, td, tr;
+    int rc = make_tmap_2d(&ta, A, dtype, M, K, kBM);
+    if (rc != LL_OK) return rc;
+    rc = make_tmap_2d(&tw, W, dtype, N, K, bn / ctas);
+    if (rc != LL_OK) return rc;
+    rc = make_tmap_2d(&td, U, dtype, M, N, 32);
+    if (rc != LL_OK) return rc;
+    rc = make_tmap_2d(&tr, F, dtype, M, N, 32);
+    if (rc != LL_OK) return rc;
+    return gemm_launch_tmaps(ta, tw, td, tr, bn, ctas, bias, 0, M, N, K, dtype, 1 | 0x80000, stream);
 }
 
 // D[M, N] = act(A[M, K] @ B[K, N] + bias) (+ residual): B row-major [K, N] (MN-major operand).  The data gradient of a
@@ -996,6 +1064,12 @@ int gemm_tn_launch(const void *A, const void *B, void *D, int64_t Kt, int Mo, in
 extern "C" int ll_gemm_tn(const void *A, const void *B, void *D, int64_t Kt, int Mo, int No, int dtype, ll_stream_t stream)
 {
     return ll::gemm_tn_launch(A, B, D, Kt, Mo, No, dtype, ll::as_stream(stream), nullptr, 0);
+}
+
+extern "C" int ll_gemm_dual(const void *A, const void *W, const float *bias, void *U, void *F, int64_t M, int N, int K, int dtype,
+                            ll_stream_t stream)
+{
+    return ll::gemm_dual_launch(A, W, bias, U, F, M, N, K, dtype, ll::as_stream(stream));
 }
 
 extern "C" int ll_gemm_nn(const void *A, const void *B, const float *bias, const void *residual, void *D, int64_t M, int N, int K, int dtype,

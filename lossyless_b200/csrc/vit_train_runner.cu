@@ -76,8 +76,12 @@ extern "C" int ll_vit_block_forward(const ll_vit_block_params_t *w, const void *
     if ((rc = ll_attention(v.qkv, v.a, batch, S, heads, dtype, stream))) return rc;
     if ((rc = ll_gemm(v.a, w->out_proj_w, w->out_proj_b, x_in, v.x1, M, W, W, dtype, 0, stream))) return rc;
     if ((rc = ll_layernorm(v.x1, M, W, w->ln2_w, w->ln2_b, v.h2, dtype, stream))) return rc;
-    if ((rc = ll_gemm(v.h2, w->fc_w, w->fc_b, nullptr, v.u, M, 4 * W, W, dtype, 0, stream))) return rc;
-    if ((rc = ll_quickgelu_forward(v.u, v.f, M * 4 * (int64_t)W, dtype, stream))) return rc;
+    if (g_fusion & 4) {  // u and f = QuickGELU(u) from one GEMM pass
+        if ((rc = ll_gemm_dual(v.h2, w->fc_w, w->fc_b, v.u, v.f, M, 4 * W, W, dtype, stream))) return rc;
+    } else {
+        if ((rc = ll_gemm(v.h2, w->fc_w, w->fc_b, nullptr, v.u, M, 4 * W, W, dtype, 0, stream))) return rc;
+        if ((rc = ll_quickgelu_forward(v.u, v.f, M * 4 * (int64_t)W, dtype, stream))) return rc;
+    }
     if ((rc = ll_gemm(v.f, w->cproj_w, w->cproj_b, v.x1, v.x2, M, W, 4 * W, dtype, 0, stream))) return rc;
     return LL_OK;
 }
@@ -199,8 +203,12 @@ extern "C" int ll_vit_block_forward_cls(const ll_vit_block_params_t *w, const vo
     if ((rc = ll_gather_cls_rows(v.a, x_in, v.a_c, v.x_c, batch, S, W, dtype, stream))) return rc;
     if ((rc = ll_gemm(v.a_c, w->out_proj_w, w->out_proj_b, v.x_c, v.x1_c, B, W, W, dtype, 0, stream))) return rc;
     if ((rc = ll_layernorm(v.x1_c, B, W, w->ln2_w, w->ln2_b, v.h2_c, dtype, stream))) return rc;
-    if ((rc = ll_gemm(v.h2_c, w->fc_w, w->fc_b, nullptr, v.u_c, B, 4 * W, W, dtype, 0, stream))) return rc;
-    if ((rc = ll_quickgelu_forward(v.u_c, v.f_c, B * 4 * (int64_t)W, dtype, stream))) return rc;
+    if (g_fusion & 4) {
+        if ((rc = ll_gemm_dual(v.h2_c, w->fc_w, w->fc_b, v.u_c, v.f_c, B, 4 * W, W, dtype, stream))) return rc;
+    } else {
+        if ((rc = ll_gemm(v.h2_c, w->fc_w, w->fc_b, nullptr, v.u_c, B, 4 * W, W, dtype, 0, stream))) return rc;
+        if ((rc = ll_quickgelu_forward(v.u_c, v.f_c, B * 4 * (int64_t)W, dtype, stream))) return rc;
+    }
     if ((rc = ll_gemm(v.f_c, w->cproj_w, w->cproj_b, v.x1_c, v.x2_c, B, W, 4 * W, dtype, 0, stream))) return rc;
     return LL_OK;
 }

@@ -323,3 +323,24 @@ def test_gemm_nn_reads_the_weight_as_stored(cuda_device, dtype, M, N, K, pair):
     assert (D.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
     assert torch.equal(D, _gemm(A, B.t().contiguous()))
     assert torch.equal(D2, _gemm(A, B.t().contiguous(), None, u, act=2))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(25600, 3072, 768), (2500, 3072, 768), (300, 256, 128), (7, 64, 64)])
+def test_gemm_dual_output(cuda_device, dtype, M, N, K):
+    """ll_gemm_dual: U = A W^T + b and F = QuickGELU(U) from one pass.  U is bit-equal to the plain GEMM; F is
+    QuickGELU of the ROUNDED U (what a separate activation pass would read), within the tanh.approx error."""
+    from lossyless_b200 import _native as Nn
+
+    g = torch.Generator(device=cuda_device).manual_seed(M + N)
+    A = torch.randn(M, K, generator=g, device=cuda_device).to(dtype)
+    W = (2.0 * torch.randn(N, K, generator=g, device=cuda_device) * K ** -0.5).to(dtype)
+    b = torch.randn(N, generator=g, device=cuda_device)
+    U = torch.full((M, N), float("nan"), dtype=dtype, device=cuda_device)
+    F = torch.full((M, N), float("nan"), dtype=dtype, device=cuda_device)
+    Nn.call("ll_gemm_dual", Nn.ptr(A), Nn.ptr(W), Nn.ptr(b), Nn.ptr(U), Nn.ptr(F), M, N, K, Nn.dtype_code(A), Nn.stream())
+    assert torch.equal(U, _gemm(A, W, b))
+    ref = U.float() * torch.sigmoid(1.702 * U.float())
+    tol = 1.2e-2 if dtype == torch.bfloat16 else 2.5e-3
+    assert torch.isfinite(F.float()).all()
+    assert (F.float() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
