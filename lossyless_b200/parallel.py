@@ -60,8 +60,12 @@ def bind_host_to_gpu(device_index, sysfs="/sys/bus/pci/devices"):
         return None
     os.sched_setaffinity(0, allowed)
     try:  # MPOL_PREFERRED = 1: allocate on `node` when it has room, fall back elsewhere instead of failing
-        mask = ctypes.c_ulong(1 << node)
-        ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
+        import platform
+
+        nr = {"x86_64": 238, "aarch64": 237}.get(platform.machine())  # __NR_set_mempolicy
+        if nr is not None and node < 8 * ctypes.sizeof(ctypes.c_ulong):
+            mask = ctypes.c_ulong(1 << node)
+            ctypes.CDLL(None, use_errno=True).syscall(nr, 1, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
     except (OSError, AttributeError):
         pass
     return {"node": node, "cpus": len(allowed), "pci": pci}
