@@ -234,11 +234,13 @@ class ClipCompressor(nn.Module):
                 pipe["ready"][slot].record(pipe["stream"])
             main.wait_event(pipe["ready"][slot])
             xs = pipe["buf"][slot][: i1 - i0]
+            ev = torch.cuda.Event()
             if is_raw:
                 xs = self._gpu_preprocess(xs, chw=chw)
+                ev.record(main)  # raw pixels: the slot is free as soon as the preprocessing has read it
             self.clip(xs, out=z[i0:i1])
-            ev = torch.cuda.Event()
-            ev.record(main)
+            if not is_raw:
+                ev.record(main)
             pipe["consumed"][slot] = ev
         packed, offsets, lens, _ = self.entropy_bottleneck.compress_to_device(
             z, bias=self.biasing, exp_scale=self._exp_scale(), mode=mode)
@@ -273,11 +275,13 @@ class ClipCompressor(nn.Module):
             pipe["ready"][slot].record(pipe["stream"])
         main.wait_event(pipe["ready"][slot])
         xs = pipe["buf"][slot][:total]
+        ev = torch.cuda.Event()
         if is_raw:
             xs = self._gpu_preprocess(xs, chw=chw)
+            ev.record(main)  # raw pixels: the slot is free as soon as the preprocessing has read it
         z = self.clip(xs)
-        ev = torch.cuda.Event()
-        ev.record(main)
+        if not is_raw:
+            ev.record(main)
         pipe["consumed"][slot] = ev
         packed, offsets, lens, _ = self.entropy_bottleneck.compress_to_device(
             z, bias=self.biasing, exp_scale=self._exp_scale(), mode=mode)
