@@ -129,3 +129,30 @@ def test_vit_cls_only_last_block_is_the_same_function(cuda_device, golden_dir, f
     vit.set_cls_last_block(False)
     z_all = vit(x).float().cpu().numpy()
     assert np.array_equal(z_cls, z_all), np.abs(z_cls - z_all).max()
+
+
+def test_vit_error_is_the_16_bit_floor_not_ours(cuda_device):
+    """|z - z_fp32| of this encoder next to the error a plain torch fp16 ViT (cuBLASLt F.linear + SDPA, LayerNorm in
+    fp32 as CLIP does) makes on the same box, weights and images, both against a float32 run of that torch model on
+    the GPU: the hand-written path (fused LayerNorm statistics, tanh-form QuickGELU, class-token-only last block) is
+    no further from fp32 than the library's 16-bit path -- the error is the storage type's, and the bounds below are
+    what ViT-B/32 in fp16 gives (measured: max 5.5e-3, mean 9.1e-4 here; 5.2e-3 / 9.3e-4 for the library)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location(
+        "torch_vit_yardstick", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "torch_vit_yardstick.py"))
+    ys = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ys)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    vit, sd, cfg = _product_vit(cuda_device)
+    x = torch.randn(64, 3, 224, 224, generator=torch.Generator().manual_seed(5)).half().to(cuda_device)
+    sd16 = {k: v.detach() for k, v in vit.state_dict().items()}
+    sd32 = {k: v.float() for k, v in sd16.items()}
+    with torch.no_grad():
+        z = vit(x).float()
+        z_lib = ys.torch_vit(sd16, x, torch.float16).float()
+        z32 = ys.torch_vit(sd32, x.float(), torch.float32)
+    ours, lib = (z - z32).abs(), (z_lib - z32).abs()
+    assert ours.max().item() < 1.5e-2 and ours.mean().item() < 2e-3, (ours.max().item(), ours.mean().item())
+    assert ours.mean().item() < 1.25 * lib.mean().item(), (ours.mean().item(), lib.mean().item())
+    assert ours.max().item() < 2.0 * lib.max().item(), (ours.max().item(), lib.max().item())
