@@ -128,3 +128,53 @@ def test_two_gpus(cuda_device):
         y = np.load(os.path.join(tmp, "y.npy"))
     assert a == b
     assert y.tolist() == [i % 7 for i in range(45)] and y.dtype == np.uint16
+
+
+def _worker_w8(rank, world, port):
+    """SURVEY 8(d) configuration 3's world size over real NCCL: every rank feeds the product ContrastiveDistortion the
+    inputs the reference's own eight-process gloo run used (tests/golden/ref_losses_w8.npz); ranks 0 / 3 / 7 hold the
+    reference's logits, distortion, negatives count and gradients."""
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    import torch.distributed as dist
+
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from lossyless_b200.distortions import ContrastiveDistortion
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_losses.npz"))
+    g8 = np.load(os.path.join(ROOT, "tests", "golden", "ref_losses_w8.npz"))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from ref_configs import CONTRASTIVE_KW
+
+    m = ContrastiveDistortion(**{**CONTRASTIVE_KW, "project_kwargs": dict(CONTRASTIVE_KW["project_kwargs"])})
+    m.load_state_dict({k[len("contrastive/"):]: torch.from_numpy(np.asarray(g[k])) for k in g.files if k.startswith("contrastive/")})
+    m = m.cuda()
+    z = torch.from_numpy(g8[f"w8/rank{rank}/z_hat"]).cuda().requires_grad_(True)
+    zp = torch.from_numpy(g8[f"w8/rank{rank}/z_pos"]).cuda().requires_grad_(True)
+    logits = m.compute_logits(z, zp, None)
+    d, logs, _ = m(z, zp, None, None)
+    d.mean().backward()
+    assert logits.shape == (8, 64) and int(logs["n_negatives"]) == 63
+    if rank in (0, 3, 7):
+        assert torch.allclose(logits.detach().cpu(), torch.from_numpy(g8[f"w8/rank{rank}/logits"]), atol=2e-6)
+        assert np.allclose(d.detach().cpu().numpy(), g8[f"w8/rank{rank}/distortion"], rtol=1e-4)
+        for got, want in ((z.grad, "g_z_hat"), (zp.grad, "g_z_pos"), (m.logit_scale.grad, "g_logit_scale")):
+            w = torch.from_numpy(np.asarray(g8[f"w8/rank{rank}/{want}"]))
+            assert (got.detach().cpu() - w).abs().max() <= 2e-3 * w.abs().max() + 1e-9, (rank, want)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_eight_gpus_contrastive_matches_reference_run(cuda_device):
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs (gpurun --gpus 8)")
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker_w8, args=(8, port), nprocs=8, join=True)
