@@ -64,7 +64,7 @@ int ll_container_index(const uint8_t *buf, int64_t size, int64_t pos, int64_t n,
 /* ------------------------------------------------------------------ device: rANS codec */
 
 /* Kernel selection for the factorised-prior codec: 0 = by row count (default: one stream per
- * warp below 8192 rows -- latency matters; one stream per lane above -- throughput matters),
+ * warp below 1024 rows to encode / 512 to decode -- latency matters; one stream per lane above -- throughput matters),
  * 1 = always one stream per warp, 2 = always one stream per lane.  Both produce the same
  * bytes (tests/test_codec_gpu.py); the knob exists for tests and benchmarks.  Process-wide. */
 int ll_rans_set_impl(int impl);
