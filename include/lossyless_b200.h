@@ -63,10 +63,12 @@ int ll_container_index(const uint8_t *buf, int64_t size, int64_t pos, int64_t n,
 
 /* ------------------------------------------------------------------ device: rANS codec */
 
-/* Kernel selection for the factorised-prior codec: 0 = by row count (default: one stream per
- * warp below 1024 rows to encode / 512 to decode -- latency matters; one stream per lane above -- throughput matters),
- * 1 = always one stream per warp, 2 = always one stream per lane.  Both produce the same
- * bytes (tests/test_codec_gpu.py); the knob exists for tests and benchmarks.  Process-wide. */
+/* Kernel selection for the factorised-prior codec: 0 = default (encode: one stream per warp below 1024
+ * rows -- latency matters -- and one stream per lane above -- throughput matters; decode: one stream per lane
+ * at every row count, it wins or ties everywhere), 1 = always one stream per warp, 2 = always one stream per
+ * lane.  All produce the same bytes and values (tests/test_codec_gpu.py); the knob exists for tests and
+ * benchmarks.  Conditional priors (per-element table index) always take the stream-per-warp kernels.
+ * Process-wide. */
 int ll_rans_set_impl(int impl);
 
 /* bytes of per-row scratch ll_eb_rans_encode needs for C symbols (worst case, escapes

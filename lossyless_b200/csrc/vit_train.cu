@@ -82,8 +82,10 @@ transpose_pad_scalar_kernel(const uint16_t *__restrict__ src, uint16_t *__restri
 }
 
 // ------------------------------------------------------------------------- column sums
-// out[c] += sum_r src[r, c].  A CTA covers 256 columns x 64 rows: thread = (32 column groups of 8) x (8 row
-// lanes), one 16-byte load per thread and row, two rows in flight; the 8 row lanes are combined through shared
+// out[c] += sum_r src[r, c].  A CTA covers 256 columns x rows_per_cta rows (a multiple of 64 sized for about four
+// CTAs per SM: 4800 32-row CTAs ran at 2.8 TB/s cold, most of a CTA's life being its reduction and its 256 atomics):
+// thread = (32 column groups of 8) x (8 row
+// lanes), one 16-byte load per thread and row, eight rows in flight; the 8 row lanes are combined through shared
 // memory and each CTA adds its 256 partial sums with one atomic per column.  (The first version read 2 bytes
 // per thread: 1.2 TB/s.)  Needs C % 8 == 0 and a 16-byte aligned base; other shapes take the scalar kernel.
 template <typename T>
@@ -138,18 +140,29 @@ colsum_vec_kernel(const T *__restrict__ src, int64_t R, int C, int rows_per_cta,
     const int64_t r_begin = (int64_t)blockIdx.y * rows_per_cta;
     const int64_t r_end = min(R, r_begin + rows_per_cta);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const uint32_t never = rows_per_cta < 0 ? 0xFFFFFFFFu : 0u;  // always 0; unknown to the compiler
     if (c0 < C) {
         int64_t r = r_begin + rl;
-        for (; r + 8 < r_end; r += 16) {  // two independent loads in flight
-            float a[8], b[8];
-            load8<T>(src + r * C + c0, a);
-            load8<T>(src + (r + 8) * C + c0, b);
+        const T *p = src + r * C + c0;
+        const int64_t step = (int64_t)8 * C;  // this thread's next row
+        for (; r + 56 < r_end; r += 64, p += 8 * step) {  // eight independent 16-byte loads in flight per thread
+            uint4 raw[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] += a[k] + b[k];
+            for (int j = 0; j < 8; ++j)  // volatile: issued back to back (the plain loads were scheduled two at a time)
+                asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw[j].x), "=r"(raw[j].y), "=r"(raw[j].z), "=r"(raw[j].w) : "l"(p + j * step));
+            // ptxas would sink the loads between the sums (two or three in flight, the rest stalled behind the first
+            // sum's wait on an in-order pipe); a value it cannot prove zero ties the first sum to the LAST load
+            raw[0].x ^= raw[7].w & never;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const T *e = reinterpret_cast<const T *>(&raw[j]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += to_float<T>(e[k]);
+            }
         }
-        for (; r < r_end; r += 8) {
+        for (; r < r_end; r += 8, p += step) {
             float a[8];
-            load8<T>(src + r * C + c0, a);
+            load8<T>(p, a);
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] += a[k];
         }
@@ -917,8 +930,10 @@ extern "C" int ll_colsum(const void *src, int64_t R, int C, int dtype, float *ou
     LL_REQUIRE(src && out && R > 0 && C > 0, "colsum: bad arguments");
     cudaStream_t s = as_stream(stream);
     if (C % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-        const int rows_per_cta = 64;
-        dim3 grid((unsigned)((C + 255) / 256), (unsigned)((R + rows_per_cta - 1) / rows_per_cta));
+        // about four CTAs per SM, each thread walking its rows in batches of eight loads (64 rows of the CTA)
+        const int64_t col_groups = (C + 255) / 256, target = (int64_t)num_sms() * 4;
+        const int rows_per_cta = (int)std::min<int64_t>(1024, 64 * std::max<int64_t>(1, (R * col_groups / target + 63) / 64));
+        dim3 grid((unsigned)col_groups, (unsigned)((R + rows_per_cta - 1) / rows_per_cta));
         LL_DISPATCH_16(dtype, LL_CUDA_CHECK(launch_pdl(colsum_vec_kernel<__half>, grid, dim3(256), 0, s, static_cast<const __half *>(src), R, C, rows_per_cta, out)),
                        LL_CUDA_CHECK(launch_pdl(colsum_vec_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, static_cast<const __nv_bfloat16 *>(src), R, C, rows_per_cta, out)), "colsum");
         LL_LAUNCH_CHECK();

@@ -188,6 +188,46 @@ def test_stream_per_lane_edge_cases(cuda_device, weights_dir, codec_impl):
     assert torch.equal(small.decompress(got, [1, 1]).reshape(77, 102), small.quantize(z, "dequantize", small._get_medians().reshape(1, -1)))
 
 
+def test_lane_decoder_quotient_paths(cuda_device, weights_dir, codec_impl):
+    """The stream-per-lane decoder (csrc/codec.cu: rans_decode_lanes2_kernel) divides by exp(scaling) through a
+    per-channel refined reciprocal when every dividend of the channel provably stays inside the exponent window of
+    that sequence, and by the IEEE division otherwise: integer / zero / almost-integer medians and extreme scales
+    take the second path.  Symbols equal the encoder's, values are bit-equal to torch's float32 division, and the
+    stream-per-warp and stream-per-lane decoders agree (as does the default choice)."""
+    from lossyless_b200.entropy_models import EntropyBottleneck
+
+    sd = torch.load(os.path.join(weights_dir, "beta5e-02_factorized_rate.pt"), map_location="cpu", weights_only=True)
+    ebsd = {k[len("entropy_bottleneck."):]: v.clone() for k, v in sd.items() if k.startswith("entropy_bottleneck.")}
+    for c, m in ((0, 0.0), (1, 2.0), (2, -1.0), (3, 1e-25), (4, -3e-20), (5, 0.5), (6, 1.0 - 2.0 ** -24)):
+        ebsd["quantiles"][c, 0, :] += m - ebsd["quantiles"][c, 0, 1]
+        ebsd["quantiles"][c, 0, 1] = m   # the value itself, not a rounded sum
+    eb = EntropyBottleneck(512, init_scale=10, filters=[3, 3, 3, 3])
+    eb.load_state_dict(ebsd)
+    eb.update(force=True)
+    eb = eb.to(cuda_device)
+    b = sd["biasing"].to(cuda_device).clone()
+    scaling = sd["scaling"].clone()
+    scaling[7], scaling[8], scaling[9], scaling[10] = 30.0, -30.0, 27.0, -27.0   # exp(+-30) leaves [2^-40, 2^40], exp(+-27) does not
+    es = scaling.exp().to(cuda_device)
+    med = eb._get_medians().reshape(-1)
+    gen = torch.Generator(device=cuda_device).manual_seed(21)
+    z = (torch.randn(4096 + 37, 512, generator=gen, device=cuda_device) * 0.6).half()
+    z[7] *= 30
+    z[100:110, :12] = 0.0
+    outs = []
+    for impl in (1, 2, 0):
+        codec_impl(impl)
+        packed, offsets, lens, sym = eb.compress_to_device(z, b, es, mode=0, want_symbols=True)
+        z_hat, dsym = eb.decompress_from_device(packed, offsets, lens, bias=b, exp_scale=es, want_symbols=True)
+        assert torch.equal(dsym, sym), impl
+        assert torch.equal(z_hat, (sym.float() + med) / es - b), impl
+        outs.append((packed[: int(lens.sum())].clone(), z_hat))
+        # without the affine map: float(symbol) + median
+        z_in_hat, _ = eb.decompress_from_device(packed, offsets, lens)
+        assert torch.equal(z_in_hat, sym.float() + med), impl
+    assert all(torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) for o in outs[1:])
+
+
 def test_large_pack_matches_single_cta_pack(cuda_device, weights_dir, codec_impl):
     """> 4096 rows take the three-launch pack (block sums in the offsets array): identical records."""
     eb, sd, b, es = _module(weights_dir, "beta1e-02", cuda_device)

@@ -60,6 +60,7 @@ def main():
         for rows in [int(r) for r in args.rows.split(",")]:
             z = (torch.randn(rows, 512, generator=g, device=dev) * 0.45).half()
             ref = None
+            zref = None
             for impl, name in ((1, "warp"), (2, "lane")):
                 N.call("ll_rans_set_impl", impl)
                 iters = 20 if rows <= 32768 else 5
@@ -69,13 +70,18 @@ def main():
                     ref = packed[:nbytes].clone()
                 else:
                     assert torch.equal(ref, packed[:nbytes]), "kernels disagree"
-                ms_d, _ = timed(lambda: eb.decompress_from_device(packed, offs, lens, bias=comp.biasing, exp_scale=es), iters)
+                ms_d, z_hat = timed(lambda: eb.decompress_from_device(packed, offs, lens, bias=comp.biasing, exp_scale=es), iters)
+                z_hat = z_hat[0] if isinstance(z_hat, tuple) else z_hat
+                if zref is None:
+                    zref = z_hat.clone()
+                else:
+                    assert torch.equal(zref, z_hat), "decoders disagree"
                 a_e = rows * 512 * 2 + nbytes + 4 * rows
                 a_d = nbytes + rows * 512 * 4
                 lines.append(f"{tag:10s} {rows:7d} {name:>6s} {ms_e * 1e3:12.1f} {a_e / ms_e / 1e6:8.1f} {100 * a_e / ms_e / 1e6 / hbm:6.2f} "
                              f"{ms_d * 1e3:10.1f} {a_d / ms_d / 1e6:8.1f} {100 * a_d / ms_d / 1e6 / hbm:6.2f} {8.0 * nbytes / rows:9.1f}")
                 print(lines[-1], flush=True)
-            del z
+            del z, zref
     N.call("ll_rans_set_impl", 0)
     if args.out:
         with open(args.out, "w") as f:
