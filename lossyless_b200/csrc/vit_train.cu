@@ -270,6 +270,33 @@ __device__ __forceinline__ void unpack8(const uint4 &raw, float *out)
     for (int k = 0; k < 8; ++k) out[k] = to_float<T>(e[k]);
 }
 
+// Epilogue of layernorm_backward_kernel: the CTA's eight per-warp column sums meet in shared memory through plain stores
+// and ONE coalesced atomic per column and CTA goes to global memory (thread t of the CTA owns columns b * 256 + t: a
+// warp's 32 atomics fall into one 128-byte line).  Column c is parked at slot c + c / 32: the writers (lane l holds
+// columns 8 l .. 8 l + 7) and the readers (consecutive columns) are both bank-conflict-free.
+// History, from ncu's source view: shared-memory float atomics are compare-and-swap loops -- 48 of them per thread, eight
+// warps contending for every address -- and cost the first version more than its pass over the rows; a layout that let
+// every warp add to columns 32 bytes apart made each 32-byte sector of the 6 KB target receive 2368 dependent
+// read-modify-writes instead of 296 (a quarter of all warp samples sat behind EXIT waiting for them to drain).
+constexpr int kLnSlots = 256 + 8;  // padded slots per 256-column block
+template <int NB>
+__device__ __forceinline__ void ln_bwd_combine(float (*s_part)[NB * kLnSlots], const float (&acc)[NB][8], float *__restrict__ dst, int lane, int warp)
+{
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_part[warp][b * kLnSlots + lane * 8 + k + lane / 4] = acc[b][k];
+    __syncthreads();
+    const int t = warp * 32 + lane;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += s_part[w][b * kLnSlots + t + t / 32];
+        atomicAdd(dst + b * 256 + t, sum);
+    }
+}
+
 template <typename T, int NB>
 __global__ void __launch_bounds__(256, NB <= 3 ? 2 : 1)
 layernorm_backward_kernel(const T *__restrict__ x, const T *__restrict__ g_h, const float *__restrict__ gamma,
@@ -279,9 +306,8 @@ layernorm_backward_kernel(const T *__restrict__ x, const T *__restrict__ g_h, co
     constexpr int W = NB * 256;
     // gamma permuted so that a lane's two float4 pieces of a block are conflict-free: [block][half][lane][4]
     __shared__ float4 s_gam[NB * 2 * 32];
-    __shared__ float s_gg[W], s_gb[W];
+    __shared__ float s_part[8][NB * kLnSlots];  // the warps' column sums, combined once per CTA (epilogue)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < W; i += 256) s_gg[i] = 0.f, s_gb[i] = 0.f;
     pdl_wait();
     pdl_launch_dependents();
     for (int i = threadIdx.x; i < NB * 64; i += 256) {
@@ -361,18 +387,9 @@ layernorm_backward_kernel(const T *__restrict__ x, const T *__restrict__ g_h, co
             store8<T>(g_x + r * W + b * 256 + lane * 8, g);
         }
     }
-#pragma unroll
-    for (int b = 0; b < NB; ++b)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            atomicAdd(&s_gg[b * 256 + lane * 8 + k], acc_g[b][k]);
-            atomicAdd(&s_gb[b * 256 + lane * 8 + k], acc_b[b][k]);
-        }
+    ln_bwd_combine<NB>(s_part, acc_g, g_gamma, lane, warp);
     __syncthreads();
-    for (int i = threadIdx.x; i < W; i += 256) {
-        atomicAdd(g_gamma + i, s_gg[i]);
-        atomicAdd(g_beta + i, s_gb[i]);
-    }
+    ln_bwd_combine<NB>(s_part, acc_b, g_beta, lane, warp);
 }
 
 // ------------------------------------------------------------------------- attention backward
