@@ -452,6 +452,15 @@ int ll_transpose_pad_colsum(const void *src, void *dst, int64_t R, int C, int64_
                             ll_stream_t stream);
 /* out[c] += sum_r src[r, c] (float32 accumulate: bias gradients).  out must be initialised. */
 int ll_colsum(const void *src, int64_t R, int C, int dtype, float *out, ll_stream_t stream);
+/* VisionTransformer.forward's token assembly for the training path (the inference path fuses it with ln_pre inside
+ * ll_vit_forward): tok [B, S, W] = cat([class_embedding, patch [B, S - 1, W]], dim = 1) + positional_embedding [S, W]
+ * (the reference's clip VisionTransformer.forward; one 16-bit rounding per element, as torch's 16-bit add).  W % 8 == 0. */
+int ll_embed_tokens(const void *patch, const void *cls, const void *pos, void *tok, int64_t B, int S, int W, int dtype,
+                    ll_stream_t stream);
+/* its adjoint, g_tok read once: g_patch [B, S - 1, W] = g_tok[:, 1:, :] (contiguous: conv1's weight-gradient operand),
+ * g_pos [S, W] += sum_b g_tok[b], g_cls [W] += sum_b g_tok[b, 0] (float32; both must be initialised). */
+int ll_embed_backward(const void *g_tok, void *g_patch, float *g_pos, float *g_cls, int64_t B, int S, int W, int dtype,
+                      ll_stream_t stream);
 /* clip/model.py QuickGELU: f = u * sigmoid(1.702 u);  g_u = g_f * d f / d u.  n elements. */
 int ll_quickgelu_forward(const void *u, void *f, int64_t n, int dtype, ll_stream_t stream);
 int ll_quickgelu_backward(const void *u, const void *g_f, void *g_u, int64_t n, int dtype, ll_stream_t stream);

@@ -103,6 +103,8 @@ _SIGNATURES = {
     "ll_transpose_pad": (c_int, [_P, _P, c_int64, c_int, c_int64, _P]),
     "ll_transpose_pad_colsum": (c_int, [_P, _P, c_int64, c_int, c_int64, c_int, _P, _P]),
     "ll_colsum": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    "ll_embed_tokens": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "ll_embed_backward": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "ll_quickgelu_forward": (c_int, [_P, _P, c_int64, c_int, _P]),
     "ll_quickgelu_backward": (c_int, [_P, _P, _P, c_int64, c_int, _P]),
     "ll_layernorm_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),

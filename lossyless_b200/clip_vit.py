@@ -575,7 +575,10 @@ class _VitTrainFn(torch.autograd.Function):
                 a_patch[row: row + n * g * g] = v.to(dt).reshape(n, 3, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(n * g * g, 3 * P * P)
             row += v.shape[0] * g * g
         patch = _gemm(a_patch, w["conv1.weight"])
-        tok = (torch.cat([w["class_embedding"].expand(B, 1, Wd), patch.view(B, g * g, Wd)], 1) + w["positional_embedding"]).reshape(M, Wd)
+        # x = cat([class_embedding, conv1(x)], 1) + positional_embedding in one pass (no concatenated copy)
+        tok = torch.empty((M, Wd), dtype=dt, device=x.device)
+        N.call("ll_embed_tokens", N.ptr(patch), N.ptr(w["class_embedding"].contiguous()), N.ptr(w["positional_embedding"].contiguous()),
+               N.ptr(tok), B, S, Wd, N.dtype_code(tok), N.stream())
         xs = _ln(tok, w["ln_pre.weight"], w["ln_pre.bias"])
         saved = []
         if NATIVE_BLOCKS:
@@ -698,14 +701,14 @@ class _VitTrainFn(torch.autograd.Function):
             if flat is not None:
                 flat.reduce_mat_slice(k)  # this block's four weight gradients (and proj, with the last block) are final
         g_tok, G["ln_pre.weight"], G["ln_pre.bias"] = _ln_backward(st["tok"], g_x, w["ln_pre.weight"], out_w=dst("ln_pre.weight"), out_b=dst("ln_pre.bias"))
-        g_tok = g_tok.view(B, S, Wd)
-        if flat is not None:
-            torch.sum(g_tok, 0, dtype=torch.float32, out=dst("positional_embedding"))
-            torch.sum(g_tok[:, 0], 0, dtype=torch.float32, out=dst("class_embedding"))
-        else:
-            G["positional_embedding"] = g_tok.sum(0, dtype=torch.float32)
-            G["class_embedding"] = g_tok[:, 0].sum(0, dtype=torch.float32)
-        g_patch = g_tok[:, 1:].reshape(B * (S - 1), Wd).contiguous()
+        # adjoint of the token assembly, g_tok read once: the contiguous patch rows for conv1's weight-gradient GEMM and the
+        # batch sums that are the embeddings' gradients (flat mode: accumulated into the zeroed float32 vector buffer)
+        g_pos, g_cls = dst("positional_embedding"), dst("class_embedding")
+        if g_pos is None:
+            g_pos = G["positional_embedding"] = torch.zeros((S, Wd), dtype=torch.float32, device=dev)
+            g_cls = G["class_embedding"] = torch.zeros(Wd, dtype=torch.float32, device=dev)
+        g_patch = torch.empty((B * (S - 1), Wd), dtype=dt, device=dev)
+        N.call("ll_embed_backward", N.ptr(g_tok), N.ptr(g_patch), N.ptr(g_pos), N.ptr(g_cls), B, S, Wd, N.dtype_code(g_tok), N.stream())
         conv_dst = dst("conv1.weight")
         G["conv1.weight"] = _wgrad(g_patch, st["a_patch"], conv_dst.view(Wd, -1) if conv_dst is not None else None).view(vit.conv1.weight.shape)
         if vit._native is not None:

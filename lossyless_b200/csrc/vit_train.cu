@@ -179,6 +179,70 @@ colsum_vec_kernel(const T *__restrict__ src, int64_t R, int C, int rows_per_cta,
     }
 }
 
+// ------------------------------------------------------------------------- token embedding (training forward / backward)
+// VisionTransformer.forward: x = cat([class_embedding, conv1(x)], dim = 1) + positional_embedding.
+//   tok[b, 0, :] = cls + pos[0],  tok[b, s, :] = patch[b, s - 1, :] + pos[s]      (one 16-bit rounding per element, as the
+// 16-bit torch add; replaces a CatArrayBatchedCopy and an elementwise add: 167 us -> one pass over the tensor)
+template <typename T>
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const T *__restrict__ patch, const T *__restrict__ cls, const T *__restrict__ pos, T *__restrict__ tok,
+                    int64_t B, int S, int W)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const int w8 = W / 8;
+    const int64_t n = B * S * w8, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = (int)(i % w8) * 8;
+        const int64_t row = i / w8;
+        const int s = (int)(row % S);
+        const int64_t b = row / S;
+        float a[8], p[8];
+        load8<T>(s == 0 ? cls + c : patch + (b * (S - 1) + (s - 1)) * W + c, a);
+        load8<T>(pos + (int64_t)s * W + c, p);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = a[k] + p[k];
+        store8<T>(tok + row * W + c, a);
+    }
+}
+
+// Its adjoint: g_patch[b, s - 1, :] = g_tok[b, s, :] (the contiguous operand of conv1's weight-gradient GEMM),
+// g_pos[s, :] += sum_b g_tok[b, s, :], g_cls += sum_b g_tok[b, 0, :] (float32) -- g_tok is read once.  A CTA covers 256
+// columns of one token position over a slice of the batch: thread = (32 column groups of 8) x (8 batch lanes).
+template <typename T>
+__global__ void __launch_bounds__(256)
+embed_backward_kernel(const T *__restrict__ g_tok, T *__restrict__ g_patch, float *__restrict__ g_pos, float *__restrict__ g_cls,
+                      int64_t B, int S, int W, int batch_per_cta)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ float part[8][256 + 8];
+    const int cg = threadIdx.x & 31, bl = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 256 + cg * 8, s = blockIdx.y;
+    const int64_t b_begin = (int64_t)blockIdx.z * batch_per_cta, b_end = min(B, b_begin + batch_per_cta);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c0 < W) {
+        for (int64_t b = b_begin + bl; b < b_end; b += 8) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(g_tok + (b * S + s) * W + c0);
+            if (s > 0) *reinterpret_cast<uint4 *>(g_patch + (b * (S - 1) + (s - 1)) * W + c0) = raw;
+            const T *e = reinterpret_cast<const T *>(&raw);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += to_float<T>(e[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part[bl][cg * 8 + k] = acc[k];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < W) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += part[j][threadIdx.x];
+        atomicAdd(g_pos + (int64_t)s * W + c, sum);
+        if (s == 0) atomicAdd(g_cls + c, sum);
+    }
+}
+
 // ------------------------------------------------------------------------- QuickGELU
 // 8 elements (16 bytes) per thread per step; the tail (n % 8) is handled by the last thread scalar-wise.
 template <typename T>
@@ -960,6 +1024,39 @@ extern "C" int ll_colsum(const void *src, int64_t R, int C, int dtype, float *ou
     dim3 grid((unsigned)((C + 63) / 64), (unsigned)((R + rows_per_cta - 1) / rows_per_cta));
     LL_DISPATCH_16(dtype, (colsum_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const __half *>(src), R, C, rows_per_cta, out)),
                    (colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16 *>(src), R, C, rows_per_cta, out)), "colsum");
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+extern "C" int ll_embed_tokens(const void *patch, const void *cls, const void *pos, void *tok, int64_t B, int S, int W,
+                               int dtype, ll_stream_t stream)
+{
+    LL_REQUIRE(patch && cls && pos && tok && B > 0 && S > 1 && W > 0 && W % 8 == 0, "embed_tokens: bad arguments");
+    LL_REQUIRE(((reinterpret_cast<uintptr_t>(patch) | reinterpret_cast<uintptr_t>(cls) | reinterpret_cast<uintptr_t>(pos) |
+                 reinterpret_cast<uintptr_t>(tok)) & 15) == 0, "embed_tokens: tensors must be 16-byte aligned");
+    const int64_t n = B * S * (W / 8);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16));
+    cudaStream_t s = as_stream(stream);
+    LL_DISPATCH_16(dtype, LL_CUDA_CHECK(launch_pdl(embed_tokens_kernel<__half>, dim3(grid), dim3(256), 0, s, static_cast<const __half *>(patch), static_cast<const __half *>(cls), static_cast<const __half *>(pos), static_cast<__half *>(tok), B, S, W)),
+                   LL_CUDA_CHECK(launch_pdl(embed_tokens_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, static_cast<const __nv_bfloat16 *>(patch), static_cast<const __nv_bfloat16 *>(cls), static_cast<const __nv_bfloat16 *>(pos), static_cast<__nv_bfloat16 *>(tok), B, S, W)), "embed_tokens");
+    LL_LAUNCH_CHECK();
+    return LL_OK;
+}
+
+extern "C" int ll_embed_backward(const void *g_tok, void *g_patch, float *g_pos, float *g_cls, int64_t B, int S, int W, int dtype,
+                                 ll_stream_t stream)
+{
+    LL_REQUIRE(g_tok && g_patch && g_pos && g_cls && B > 0 && S > 1 && W > 0 && W % 8 == 0, "embed_backward: bad arguments");
+    LL_REQUIRE(S <= 65535, "embed_backward: too many token positions");
+    LL_REQUIRE(((reinterpret_cast<uintptr_t>(g_tok) | reinterpret_cast<uintptr_t>(g_patch)) & 15) == 0, "embed_backward: tensors must be 16-byte aligned");
+    // about four CTAs per SM; a CTA's eight batch lanes take at least eight images each
+    const int64_t col_groups = (W + 255) / 256, target = (int64_t)num_sms() * 4;
+    const int64_t splits = std::max<int64_t>(1, std::min<int64_t>((B + 63) / 64, target / std::max<int64_t>(1, col_groups * S)));
+    const int batch_per_cta = (int)((B + splits - 1) / splits);
+    dim3 grid((unsigned)col_groups, (unsigned)S, (unsigned)((B + batch_per_cta - 1) / batch_per_cta));
+    cudaStream_t s = as_stream(stream);
+    LL_DISPATCH_16(dtype, LL_CUDA_CHECK(launch_pdl(embed_backward_kernel<__half>, grid, dim3(256), 0, s, static_cast<const __half *>(g_tok), static_cast<__half *>(g_patch), g_pos, g_cls, B, S, W, batch_per_cta)),
+                   LL_CUDA_CHECK(launch_pdl(embed_backward_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, static_cast<const __nv_bfloat16 *>(g_tok), static_cast<__nv_bfloat16 *>(g_patch), g_pos, g_cls, B, S, W, batch_per_cta)), "embed_backward");
     LL_LAUNCH_CHECK();
     return LL_OK;
 }

@@ -42,6 +42,31 @@ def test_transpose_pad_and_colsum(cuda_device):
         assert torch.allclose(db, t.float().sum(0), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_embed_tokens_and_adjoint(cuda_device, dtype):
+    """ll_embed_tokens == cat([class_embedding, patch], 1) + positional_embedding in the 16-bit type (bit-equal: one
+    rounding per element either way); ll_embed_backward returns the patch rows of the gradient bit-equal and the
+    embeddings' gradients (batch sums, float32) within summation-order error, accumulating into its outputs."""
+    from lossyless_b200 import _native as N
+
+    gen = torch.Generator().manual_seed(3)
+    for B, S, W in ((37, 50, 768), (3, 5, 64), (300, 50, 768)):
+        patch = torch.randn(B, S - 1, W, generator=gen).to(cuda_device, dtype)
+        cls = torch.randn(W, generator=gen).to(cuda_device, dtype)
+        pos = torch.randn(S, W, generator=gen).to(cuda_device, dtype)
+        tok = torch.empty(B, S, W, device=cuda_device, dtype=dtype)
+        N.call("ll_embed_tokens", N.ptr(patch), N.ptr(cls), N.ptr(pos), N.ptr(tok), B, S, W, N.dtype_code(tok), N.stream())
+        assert torch.equal(tok, torch.cat([cls.expand(B, 1, W), patch], 1) + pos)
+        g_tok = torch.randn(B, S, W, generator=gen).to(cuda_device, dtype)
+        g_patch = torch.empty(B, S - 1, W, device=cuda_device, dtype=dtype)
+        g_pos = torch.ones(S, W, device=cuda_device)
+        g_cls = torch.full((W,), 2.0, device=cuda_device)
+        N.call("ll_embed_backward", N.ptr(g_tok), N.ptr(g_patch), N.ptr(g_pos), N.ptr(g_cls), B, S, W, N.dtype_code(g_tok), N.stream())
+        assert torch.equal(g_patch, g_tok[:, 1:])
+        assert torch.allclose(g_pos, 1.0 + g_tok.float().sum(0), rtol=1e-5, atol=1e-4)
+        assert torch.allclose(g_cls, 2.0 + g_tok[:, 0].float().sum(0), rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_quickgelu(cuda_device, dtype):
     from lossyless_b200 import _native as N
