@@ -83,7 +83,8 @@ transpose_pad_scalar_kernel(const uint16_t *__restrict__ src, uint16_t *__restri
 
 // ------------------------------------------------------------------------- column sums
 // out[c] += sum_r src[r, c].  A CTA covers 256 columns x rows_per_cta rows (a multiple of 64 sized for about four
-// CTAs per SM: 4800 32-row CTAs ran at 2.8 TB/s cold, most of a CTA's life being its reduction and its 256 atomics):
+// CTAs per SM instead of thousands of 32-row CTAs whose life was mostly their reduction and their 256 atomics: +17 % on
+// the 768-column shape, the wide ones were at the HBM roofline already):
 // thread = (32 column groups of 8) x (8 row
 // lanes), one 16-byte load per thread and row, eight rows in flight; the 8 row lanes are combined through shared
 // memory and each CTA adds its 256 partial sums with one atomic per column.  (The first version read 2 bytes
@@ -338,10 +339,10 @@ __device__ __forceinline__ void unpack8(const uint4 &raw, float *out)
 // and ONE coalesced atomic per column and CTA goes to global memory (thread t of the CTA owns columns b * 256 + t: a
 // warp's 32 atomics fall into one 128-byte line).  Column c is parked at slot c + c / 32: the writers (lane l holds
 // columns 8 l .. 8 l + 7) and the readers (consecutive columns) are both bank-conflict-free.
-// History, from ncu's source view: shared-memory float atomics are compare-and-swap loops -- 48 of them per thread, eight
-// warps contending for every address -- and cost the first version more than its pass over the rows; a layout that let
-// every warp add to columns 32 bytes apart made each 32-byte sector of the 6 KB target receive 2368 dependent
-// read-modify-writes instead of 296 (a quarter of all warp samples sat behind EXIT waiting for them to drain).
+// (The first version used shared-memory float atomics -- compare-and-swap loops, 48 per thread: 35.5 -> 31.1 us per
+// 25 600-row launch without them.  An intermediate layout that let every warp add to columns 32 bytes apart in GLOBAL
+// memory made each 32-byte sector of the 6 KB target receive 2368 dependent read-modify-writes instead of 296: a quarter
+// of ncu's warp samples sat behind EXIT waiting for them to drain, and the kernel took longer than its pass over the rows.)
 constexpr int kLnSlots = 256 + 8;  // padded slots per 256-column block
 template <int NB>
 __device__ __forceinline__ void ln_bwd_combine(float (*s_part)[NB * kLnSlots], const float (&acc)[NB][8], float *__restrict__ dst, int lane, int warp)
