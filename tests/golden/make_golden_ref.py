@@ -19,6 +19,8 @@ clip.visual = the fp32 oracle ViT).  So these files pin, to reference code rathe
                   parameters, inputs, noise draws, every logged scalar, gradients.
   ref_hub.npz     hub/compressor.py ClipCompressor.{compress, decompress, get_rate, compress_dataset,
                   decompress_dataset}: the container file bytes the reference's own writer produced.
+  ref_predictor.npz  lossyless/predictors.py Predictor.{step, loss, forward} (python tests/golden/make_golden_ref.py predictor):
+                  the downstream probe on 512-d representations, train (with gradients) and eval.
 """
 import io
 import math
@@ -37,7 +39,7 @@ sys.path.insert(0, ROOT)
 warnings.filterwarnings("ignore", category=FutureWarning)
 
 import ref_shim  # noqa: E402
-from ref_configs import CONTRASTIVE_KW, SeededImages, step_hparams  # noqa: E402
+from ref_configs import CONTRASTIVE_KW, PREDICTOR_CASES, SeededImages, predictor_hparams, step_hparams  # noqa: E402
 
 TAGS = ["beta1e-01", "beta5e-02", "beta1e-02"]
 WEIGHTS = os.path.join(ROOT, "lossyless_b200", "hub", "weights")
@@ -350,6 +352,44 @@ def make_losses_w8():
             keep = [k for k in res if r in (0, 3, 7) and (r == 3 or k not in ("g_w1", "g_w2"))] if r in (0, 3, 7) else ["z_hat", "z_pos"]
             out.update({f"w8/rank{r}/{k}": res[k] for k in keep})
     npz("ref_losses_w8.npz", out)
+
+
+# --------------------------------------------------------------------------------------------- predictor
+def make_predictor():
+    """lossyless/predictors.py Predictor (the downstream consumer of Z_hat): ``step`` in train mode (loss, every
+    logged scalar, gradients) and in eval mode, ``forward`` as probabilities, for a linear and an MLP classification probe
+    on 512-d representations and an MLP regression probe.  (torchmetrics' ``accuracy`` is the shim's two-line restatement.)"""
+    from lossyless.predictors import Predictor
+
+    out = {}
+    for case, c in PREDICTOR_CASES.items():
+        torch.manual_seed(31)
+        m = Predictor(AD(predictor_hparams(case)))
+        g = torch.Generator().manual_seed(32)
+        x = torch.randn(48, 512, generator=g)
+        y = torch.randint(0, 10, (48,), generator=g) if c["is_clf"] else torch.randn(48, 3, generator=g)
+        pre = case + "/"
+        out.update({pre + "sd/" + k: v.clone() for k, v in m.state_dict().items()})
+        out["x"] = x  # the same seeded representations for every case
+        out[pre + "y"] = y
+        m.train()
+        loss, logs = m.step((x, y))
+        loss.backward()
+        out[pre + "train/loss"] = float(loss)
+        for k, v in logs.items():
+            if k != "inference_time":
+                out[pre + "train/logs/" + k] = float(v)
+        for n, p in m.named_parameters():
+            out[pre + "train/grad/" + n] = p.grad.clone()
+        m.eval()
+        with torch.no_grad():
+            loss_e, logs_e = m.step((x, y))
+            out[pre + "eval/loss"] = float(loss_e)
+            for k, v in logs_e.items():
+                if k != "inference_time":
+                    out[pre + "eval/logs/" + k] = float(v)
+            out[pre + "eval/probs"] = m(x, is_logits=False)
+    npz("ref_predictor.npz", out)
 
 
 if __name__ == "__main__":

@@ -48,3 +48,16 @@ class SeededImages(torch.utils.data.Dataset):
         return torch.randn(3, 224, 224, generator=g), i % 7
 
 
+# lossyless/predictors.py Predictor on 512-d representations (ref_predictor.npz)
+PREDICTOR_CASES = {
+    "linear_clf": dict(arch="linear", arch_kwargs={}, is_clf=True, target_shape=[10]),
+    "mlp_clf": dict(arch="mlp", arch_kwargs=dict(hid_dim=64, n_hid_layers=2, norm_layer="batch"), is_clf=True, target_shape=[10]),
+    "mlp_reg": dict(arch="mlp", arch_kwargs=dict(hid_dim=32, n_hid_layers=1), is_clf=False, target_shape=[3]),
+}
+
+
+def predictor_hparams(case):
+    c = PREDICTOR_CASES[case]
+    return dict(data=dict(target_is_clf=c["is_clf"], shape=[512], target_shape=c["target_shape"], balancing_weights={}),
+                predictor=dict(arch=c["arch"], arch_kwargs=dict(c["arch_kwargs"])), stage="pred",
+                optimizer_pred=dict(mode="Adam", kwargs=dict(lr=1e-3)), scheduler_pred=dict(modes=[], kwargs={}))

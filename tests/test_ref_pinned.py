@@ -281,3 +281,48 @@ def test_container_matches_reference_writer(ref, weights_dir, native_lib):
     N.call("ll_container_index", raw.ctypes.data, raw.size, 4, 20, offsets.ctypes.data, lens.ctypes.data)
     assert lens.tolist() == [len(s) for s in strings]
     assert all(raw[offsets[i]: offsets[i] + lens[i]].tobytes() == strings[i] for i in range(20))
+
+
+# ------------------------------------------------------------------------------------------ downstream probe
+@pytest.mark.parametrize("case", ["linear_clf", "mlp_clf", "mlp_reg"])
+def test_predictor_matches_reference(golden_dir, case):
+    """``lossyless_b200.predictors.Predictor`` (the consumer of the decompressed representations) against
+    what the reference's own ``lossyless/predictors.py`` computed on the same parameters and inputs
+    (tests/golden/ref_predictor.npz): train-mode ``step`` -- loss, every logged scalar, parameter gradients --, eval-mode
+    ``step`` and the class probabilities of ``forward(is_logits=False)``."""
+    import sys
+
+    sys.path.insert(0, golden_dir)
+    from ref_configs import predictor_hparams  # the hparams the fixture was made with
+
+    from lossyless_b200.predictors import Predictor
+
+    g = np.load(os.path.join(golden_dir, "ref_predictor.npz"))
+    pre = case + "/"
+    m = Predictor(predictor_hparams(case))
+    sd = {k[len(pre + "sd/"):]: T(g[k]) for k in g.files if k.startswith(pre + "sd/")}
+    assert set(sd) == set(m.state_dict()), "parameter names differ from the reference module's"
+    m.load_state_dict(sd)
+    x, y = T(g["x"]), T(g[pre + "y"])
+
+    def close(a, b, tol=1e-5):
+        return (math.isnan(a) and math.isnan(b)) or abs(a - b) <= tol * max(1.0, abs(b))
+
+    m.train()
+    loss, logs = m.step((x, y))
+    loss.backward()
+    assert close(float(loss), float(g[pre + "train/loss"]))
+    keys = [k[len(pre + "train/logs/"):] for k in g.files if k.startswith(pre + "train/logs/")]
+    assert set(keys) == set(logs) - {"inference_time"}
+    for k in keys:  # tasks_std of a single task is nan in the reference, and here
+        assert close(float(logs[k]), float(g[pre + "train/logs/" + k])), k
+    for n, p in m.named_parameters():
+        want = T(g[pre + "train/grad/" + n])
+        assert torch.allclose(p.grad, want, rtol=1e-4, atol=1e-7), n
+    m.eval()
+    with torch.no_grad():
+        loss_e, logs_e = m.step((x, y))
+        assert close(float(loss_e), float(g[pre + "eval/loss"]))
+        for k in keys:
+            assert close(float(logs_e[k]), float(g[pre + "eval/logs/" + k])), k
+        assert torch.allclose(m(x, is_logits=False), T(g[pre + "eval/probs"]), rtol=1e-5, atol=1e-7)
