@@ -21,6 +21,9 @@ clip.visual = the fp32 oracle ViT).  So these files pin, to reference code rathe
                   decompress_dataset}: the container file bytes the reference's own writer produced.
   ref_predictor.npz  lossyless/predictors.py Predictor.{step, loss, forward} (python tests/golden/make_golden_ref.py predictor):
                   the downstream probe on 512-d representations, train (with gradients) and eval.
+  ref_optim.npz   LearnableCompressor.configure_optimizers / get_specific_parameters + helpers.append_optimizer_scheduler_ /
+                  get_lr_scheduler on config/main.yaml's optimiser and scheduler groups (... make_golden_ref.py optim):
+                  the main / coder parameter split, optimiser hyper-parameters, learning rate after every epoch.
 """
 import io
 import math
@@ -39,7 +42,7 @@ sys.path.insert(0, ROOT)
 warnings.filterwarnings("ignore", category=FutureWarning)
 
 import ref_shim  # noqa: E402
-from ref_configs import CONTRASTIVE_KW, PREDICTOR_CASES, SeededImages, predictor_hparams, step_hparams  # noqa: E402
+from ref_configs import CONTRASTIVE_KW, PREDICTOR_CASES, SeededImages, optim_hparams, predictor_hparams, step_hparams  # noqa: E402
 
 TAGS = ["beta1e-01", "beta5e-02", "beta1e-02"]
 WEIGHTS = os.path.join(ROOT, "lossyless_b200", "hub", "weights")
@@ -390,6 +393,43 @@ def make_predictor():
                     out[pre + "eval/logs/" + k] = float(v)
             out[pre + "eval/probs"] = m(x, is_logits=False)
     npz("ref_predictor.npz", out)
+
+
+# --------------------------------------------------------------------------------------------- optimisers / schedulers
+def make_optim():
+    """lossyless/learnable_compressors.py ``configure_optimizers`` / ``get_specific_parameters`` with lossyless/helpers.py
+    ``append_optimizer_scheduler_ / get_optimizer / get_lr_scheduler`` on config/main.yaml's groups: which parameters each
+    optimiser owns (main vs coder), its hyper-parameters, and the learning rate after every epoch (``scheduler.step()``
+    once per epoch, Lightning's default interval)."""
+    from lossyless.learnable_compressors import LearnableCompressor
+
+    out = {}
+    for sch, epochs in (("expdecay100", 6), ("unifmultistep100", 8)):
+        torch.manual_seed(3)
+        m = LearnableCompressor(AD(optim_hparams("contrastive", sch, epochs)))
+        names = {id(p): n for n, p in m.named_parameters()}
+        optimizers, schedulers = m.configure_optimizers()
+        pre = sch + "/"
+        out[pre + "n_optimizers"] = len(optimizers)
+        out[pre + "roles"] = np.array([m.idcs_to_compressors[i] for i in range(len(optimizers))])
+        for i, opt in enumerate(optimizers):
+            out[pre + f"opt{i}/class"] = np.array(type(opt).__name__)
+            out[pre + f"opt{i}/params"] = np.array([names[id(p)] for g_ in opt.param_groups for p in g_["params"]])
+            out[pre + f"opt{i}/lr"] = opt.param_groups[0]["lr"]
+            out[pre + f"opt{i}/weight_decay"] = opt.param_groups[0]["weight_decay"]
+            out[pre + f"opt{i}/betas"] = np.array(opt.param_groups[0]["betas"])
+            out[pre + f"opt{i}/eps"] = opt.param_groups[0]["eps"]
+        out[pre + "sched_names"] = np.array([s_["name"] for s_ in schedulers])
+        out[pre + "sched_classes"] = np.array([type(s_["scheduler"]).__name__ for s_ in schedulers])
+        lrs = []
+        for _ in range(epochs):
+            for opt in optimizers:
+                opt.step()  # no gradients: nothing moves; keeps torch's "scheduler before optimizer" check quiet
+            for s_ in schedulers:
+                s_["scheduler"].step()
+            lrs.append([opt.param_groups[0]["lr"] for opt in optimizers])
+        out[pre + "lr_after_epoch"] = np.array(lrs, dtype=np.float64)
+    npz("ref_optim.npz", out)
 
 
 if __name__ == "__main__":

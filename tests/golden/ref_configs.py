@@ -61,3 +61,18 @@ def predictor_hparams(case):
     return dict(data=dict(target_is_clf=c["is_clf"], shape=[512], target_shape=c["target_shape"], balancing_weights={}),
                 predictor=dict(arch=c["arch"], arch_kwargs=dict(c["arch_kwargs"])), stage="pred",
                 optimizer_pred=dict(mode="Adam", kwargs=dict(lr=1e-3)), scheduler_pred=dict(modes=[], kwargs={}))
+
+
+# config/main.yaml's optimiser / scheduler groups (optimizer/AdamW_lr1e-3_w1e-5, optimizer/AdamW_lr3e-4_w1e-5,
+# scheduler/expdecay100, scheduler/unifmultistep100) on top of step_hparams (ref_optim.npz)
+def optim_hparams(distortion, scheduler, epochs):
+    hp = step_hparams(distortion)
+    if scheduler == "expdecay100":
+        sch = dict(modes=["expdecay"], kwargs=dict(expdecay=dict(decay_factor=100, epochs=epochs)))
+    else:
+        sch = dict(modes=["UniformMultiStepLR"], kwargs=dict(UniformMultiStepLR=dict(decay_factor=100, epochs=epochs, k_steps=3)))
+    hp.update(optimizer_feat=dict(mode="AdamW", kwargs=dict(lr=1e-3, weight_decay=1e-5)), scheduler_feat=sch,
+              optimizer_coder=dict(mode="AdamW", kwargs=dict(lr=3e-4, weight_decay=1e-5)),
+              scheduler_coder=dict(modes=list(sch["modes"]), kwargs={k: dict(v) for k, v in sch["kwargs"].items()}))
+    return hp
+

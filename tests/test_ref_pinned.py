@@ -326,3 +326,42 @@ def test_predictor_matches_reference(golden_dir, case):
         for k in keys:
             assert close(float(logs_e[k]), float(g[pre + "eval/logs/" + k])), k
         assert torch.allclose(m(x, is_logits=False), T(g[pre + "eval/probs"]), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------ optimisers / schedulers
+@pytest.mark.parametrize("sch,epochs", [("expdecay100", 6), ("unifmultistep100", 8)])
+def test_configure_optimizers_matches_reference(golden_dir, sch, epochs):
+    """``LearnableCompressor.configure_optimizers`` against the reference's own (tests/golden/ref_optim.npz, config/main.yaml's
+    optimiser and scheduler groups): the same parameters in the same order under the main and the coder optimiser, the
+    same hyper-parameters, the same scheduler classes and names, and -- stepping the schedulers once per epoch as ``fit``
+    does at the end of every call -- the same learning rate after every epoch."""
+    import sys
+
+    sys.path.insert(0, golden_dir)
+    from ref_configs import optim_hparams
+
+    from lossyless_b200.learnable_compressors import LearnableCompressor
+
+    g = np.load(os.path.join(golden_dir, "ref_optim.npz"))
+    pre = sch + "/"
+    m = LearnableCompressor(optim_hparams("contrastive", sch, epochs))
+    names = {id(p): n for n, p in m.named_parameters()}
+    optimizers, schedulers = m.configure_optimizers()
+    assert len(optimizers) == int(g[pre + "n_optimizers"])
+    assert [m.idcs_to_compressors[i] for i in range(len(optimizers))] == list(g[pre + "roles"])
+    for i, opt in enumerate(optimizers):
+        assert issubclass(type(opt), getattr(torch.optim, str(g[pre + f"opt{i}/class"])))
+        assert [names[id(p)] for grp in opt.param_groups for p in grp["params"]] == list(g[pre + f"opt{i}/params"])
+        grp = opt.param_groups[0]
+        assert grp["lr"] == float(g[pre + f"opt{i}/lr"]) and grp["weight_decay"] == float(g[pre + f"opt{i}/weight_decay"])
+        assert tuple(grp["betas"]) == tuple(g[pre + f"opt{i}/betas"]) and grp["eps"] == float(g[pre + f"opt{i}/eps"])
+    assert [s["name"] for s in schedulers] == list(g[pre + "sched_names"])
+    assert [type(s["scheduler"]).__name__ for s in schedulers] == list(g[pre + "sched_classes"])
+    want = g[pre + "lr_after_epoch"]
+    for e in range(epochs):
+        for opt in optimizers:
+            opt.step()
+        for s in schedulers:
+            s["scheduler"].step()
+        got = [opt.param_groups[0]["lr"] for opt in optimizers]
+        assert np.allclose(got, want[e], rtol=1e-12, atol=0), (e, got, want[e])
